@@ -1,0 +1,31 @@
+"""CPU oracle for the VQ-CPC inference hot path.  TEST INFRASTRUCTURE ONLY.
+
+This package is a CPU restatement of the reference algorithm
+(tarepan/VectorQuantizedCPC) for the path named in BASELINE.json:
+``Encoder.encode``, ``VQEmbeddingEMA.encode`` and ``Vocoder.generate`` /
+``Vocoder.forward``.  It exists to CHECK the CUDA product path.
+
+Who may import it: ``tests/``, ``__graft_entry__.smoke()`` and the
+``cpu_baseline`` / ``--impl reference`` legs of ``bench.py``.  Nothing under
+``vectorquantizedcpc_b200/`` imports it, and the product path raises if the
+CUDA library is missing -- there is no CPU fallback.
+
+Pinning status
+--------------
+* ``oracle.encoder`` (conv, LN/ReLU/Linear stack, VQ lookup, LSTM): PINNED.
+  It is checked against outputs of the live reference ``model.py`` (lines
+  1-317 exec'd in the build container, see ``oracle/reference_loader.py``);
+  the resulting golden vectors are committed under ``tests/golden/`` together
+  with the generating script ``tests/golden/make_golden.py``.
+* ``oracle.mulaw``: PINNED against ``/root/reference/preprocess.py:20-35``
+  (formula evaluated in the build container, 256-entry table committed).
+* ``oracle.vocoder`` (prenet biGRU, x160 upsample, autoregressive GRUCell /
+  fc1 / fc2 / sample loop): **PARITY UNPINNED**.  The arithmetic lives in the
+  third-party package ``rnnms`` (tarepan/UniversalVocoding, floating
+  ``rev = "main"`` in ``/root/reference/pyproject.toml:19``), which is neither
+  vendored in the reference tree nor installed, and the reference holds no
+  tests, golden vectors or checkpoints for it.  The oracle restates the
+  published RNN_MS / WaveRNN algorithm with the dimensions the reference pins
+  in ``config.py:62-77,199`` and the glue it pins in
+  ``network_vocoder.py:41-78``.
+"""
