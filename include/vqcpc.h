@@ -1,0 +1,143 @@
+/*
+ * vqcpc.h -- C-ABI of the B200-native VQ-CPC inference hot path (libvqcpc_b200.so).
+ *
+ * The reference (tarepan/VectorQuantizedCPC) is pure Python and has NO plugin/FFI boundary; its
+ * boundary for this path is three Python methods.  Each entry point below names the
+ * reference interface it replaces.  All pointers are DEVICE pointers (plain C types only, no torch
+ * types); `stream` is a cudaStream_t passed as void*.  Every function returns 0 on success and a
+ * non-zero code on failure, with a thread-local message retrievable through vqcpc_last_error().
+ * Outputs are written into caller-allocated buffers; inputs are never modified.
+ *
+ * Built for sm_100a only.  There is no CPU fallback.
+ */
+#ifndef VQCPC_H
+#define VQCPC_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VQCPC_ABI_VERSION 1
+
+/* error codes */
+#define VQCPC_OK 0
+#define VQCPC_ERR_ARG 1      /* bad shape / null pointer / unsupported dimension */
+#define VQCPC_ERR_CUDA 2     /* a CUDA runtime call failed */
+#define VQCPC_ERR_DEVICE 3   /* device is not sm_100 / cannot co-schedule the persistent grid */
+#define VQCPC_ERR_TIMEOUT 4  /* a persistent kernel's exchange timed out (see vqcpc_check_status) */
+
+const char* vqcpc_last_error(void);
+int vqcpc_abi_version(void);
+/* 0 iff `device` is compute capability 10.x with >= 128 SMs (what the persistent kernels need). */
+int vqcpc_device_check(int device);
+
+/* ---- weights of Encoder: state_dict layout of /root/reference/model.py:43-57,90-101 */
+typedef struct {
+    int32_t in_channels;   /* 80  ConfEncoder.in_channels  model.py:27 */
+    int32_t channels;      /* C: 512 or 768 (multiple of 128, <= 1024)  model.py:28 */
+    int32_t n_embeddings;  /* 512 model.py:29 */
+    int32_t z_dim;         /* 64  model.py:30 */
+    int32_t c_dim;         /* 256 model.py:31 */
+    int32_t _pad;
+    const float* conv_w;      /* conv.weight (C, 80, 4) contiguous == (C, 320) */
+    const float* ln_w[5];     /* encoder.{0,3,6,9,12}.weight (C,) */
+    const float* ln_b[5];     /* encoder.{0,3,6,9,12}.bias   (C,) */
+    const float* fc_w[4];     /* encoder.{2,5,8,11}.weight (C, C) */
+    const float* proj_w;      /* encoder.14.weight (64, C) */
+    const float* proj_b;      /* encoder.14.bias (64,) */
+    const float* codebook;    /* codebook.embedding (512, 64) */
+    const float* lstm_w_ih;   /* rnn.weight_ih_l0 (1024, 64) */
+    const float* lstm_w_hh;   /* rnn.weight_hh_l0 (1024, 256) */
+    const float* lstm_b;      /* rnn.bias_ih_l0 + rnn.bias_hh_l0 (1024,)  (host-side sum) */
+} vqcpc_encoder_weights;
+
+/* ---- weights of Vocoder: /root/reference/network_vocoder.py:37-39 + rnnms dims config.py:62-77,199 */
+typedef struct {
+    int32_t n_codes;       /* 512 size_i_codebook */
+    int32_t dim_code;      /* 64  dim_i_embedding */
+    int32_t n_speakers;    /* 102 */
+    int32_t dim_speaker;   /* 64  dim_speaker_embedding */
+    int32_t upsample_t;    /* 160 upsampling_t (hop length) */
+    int32_t _pad;
+    const float* code_emb;      /* code_embedding.weight (512, 64) */
+    const float* spk_emb;       /* speaker_embedding.weight (n_speakers, 64) */
+    /* prenet: 2-layer bidirectional GRU, hidden 128/direction; per layer, directions concatenated */
+    const float* pre_w_ih[2];   /* [fwd;bwd] weight_ih (768, 128) / (768, 256) */
+    const float* pre_b_ih[2];   /* [fwd;bwd] bias_ih (768,) */
+    const float* pre_w_hh[2];   /* [fwd;bwd] weight_hh (2, 384, 128) */
+    const float* pre_b_hh[2];   /* [fwd;bwd] bias_hh (2, 384) */
+    /* autoregressive part */
+    const float* ar_w_ih;       /* rnn weight_ih (2688, 512): [:, :256] acts on the sample embedding */
+    const float* ar_b_ih;       /* (2688,) */
+    const float* ar_w_hh;       /* (2688, 896) */
+    const float* ar_b_hh;       /* (2688,) */
+    const float* fc1_w;         /* (256, 896) */
+    const float* fc1_b;         /* (256,) */
+    const float* fc2_w;         /* (256, 256) */
+    const float* fc2_b;         /* (256,) */
+    const float* ar_emb;        /* embedding (256, 256) */
+    const float* eprime;        /* (256, 2688) = ar_emb . ar_w_ih[:, :256]^T, filled by vqcpc_vocoder_pack */
+    const float* mulaw_lut;     /* (256,) k -> wav, formula of /root/reference/preprocess.py:30-35 */
+} vqcpc_vocoder_weights;
+
+/* ------------------------------------------------------------------ building blocks (also used by tests)
+ * C[m,n] = sum_k A[m*lda+k] * W[n*ldw+k] (+ bias[n]);  fp32, K % 16 == 0, N % 4 == 0, 16-byte aligned rows.
+ * Replaces the implicit cuBLAS calls behind nn.Linear (model.py:50,54). */
+int vqcpc_linear_f32(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias,
+                     float* C, int64_t ldc, int64_t M, int32_t N, int32_t K, void* stream);
+/* In-place relu(LayerNorm(x)) over rows of width C (biased variance, eps 1e-5) -- model.py:47-48,51-52. */
+int vqcpc_layernorm_relu_f32(float* x, const float* w, const float* b, int64_t rows, int32_t C, void* stream);
+
+/* ------------------------------------------------------------------ VQEmbeddingEMA.encode -- model.py:103-115
+ * x (n_frames, 64) fp32 -> out_q (n_frames, 64) = codebook[idx], out_idx (n_frames,) int64 = first argmin of
+ * |e|^2 - 2 x.e (fp32; the |x|^2 term of model.py:107-110 is argmin-invariant and is not added). */
+int vqcpc_vq_lookup(const float* x, const float* codebook, int64_t n_frames, int32_t n_codes, int32_t dim,
+                    float* out_q, int64_t* out_idx, void* stream);
+
+/* ------------------------------------------------------------------ Encoder.encode -- model.py:59-70
+ * mel (B, 80, T) fp32 -> out_z (B, T', 64) quantised, out_c (B, T', 256), out_idx (B, T') int64,
+ * T' = (T-2)/2+1.  Optional (nullable): out_prevq (B, T', 64) = output of encoder.encoder[-1] (what the
+ * forward hook of encode.py:34-40 observes); out_hidden (B, T', C) = its input. */
+size_t vqcpc_encoder_workspace_bytes(int32_t B, int32_t T, int32_t channels);
+int vqcpc_encoder_forward(const vqcpc_encoder_weights* w, const float* mel, int32_t B, int32_t T,
+                          void* workspace, size_t workspace_bytes,
+                          float* out_z, float* out_c, int64_t* out_idx,
+                          float* out_prevq, float* out_hidden, void* stream);
+/* nn.LSTM(64,256) over quantised codes only (model.py:57,69): idx (B, T') -> out_c (B, T', 256). */
+size_t vqcpc_lstm_workspace_bytes(int32_t B, int32_t Tp);
+int vqcpc_lstm_forward(const vqcpc_encoder_weights* w, const int64_t* idx, int32_t B, int32_t Tp,
+                       void* workspace, size_t workspace_bytes, float* out_c, void* stream);
+
+/* ------------------------------------------------------------------ Vocoder -- network_vocoder.py:41-78
+ * vqcpc_vocoder_pack: weight-only precompute, eprime_out (256, 2688). */
+int vqcpc_vocoder_pack(const vqcpc_vocoder_weights* w, float* eprime_out, void* stream);
+/* Conditioning: code/speaker embedding, x2 nearest, concat (network_vocoder.py:73-77), prenet biGRU, and the
+ * hoisted input projection  G[b,f,:] = p[b,f,:] . ar_w_ih[:, 256:]^T + ar_b_ih   (B, 2Tc, 2688).
+ * The x160 upsample of rnnms is the index map t -> t / 160 and is never materialised.
+ * Optional out_p (B, 2Tc, 256): the prenet output. */
+size_t vqcpc_vocoder_workspace_bytes(int32_t B, int32_t Tc);
+int vqcpc_vocoder_condition(const vqcpc_vocoder_weights* w, const int64_t* codes, const int64_t* speaker,
+                            int32_t B, int32_t Tc, void* workspace, size_t workspace_bytes,
+                            float* out_G, float* out_p, void* stream);
+/* Vocoder.generate (network_vocoder.py:69-78): one persistent kernel launch per utterance, L <= 320*Tc steps.
+ * uniforms (B, L) in [0,1): the injected per-(utterance, step) randomness of the inverse-CDF sampler.
+ * out_wav (B, L) fp32; nullable out_codes (B, L) int32 mu-law codes; nullable out_logits (B, L, 256). */
+int vqcpc_vocoder_generate(const vqcpc_vocoder_weights* w, const float* G, const float* uniforms,
+                           int32_t B, int32_t T2, int32_t L, void* workspace, size_t workspace_bytes,
+                           float* out_wav, int32_t* out_codes, float* out_logits, void* stream);
+/* Vocoder.forward (network_vocoder.py:41-67; contract vocoder.py:62-63): teacher-forced energies.
+ * x_in (B, L) int64 mu-law codes (AR input at step t is x_in[:, t]) -> out_logits (B, L, 256). */
+int vqcpc_vocoder_logits_tf(const vqcpc_vocoder_weights* w, const float* G, const int64_t* x_in,
+                            int32_t B, int32_t T2, int32_t L, void* workspace, size_t workspace_bytes,
+                            float* out_logits, void* stream);
+/* Reads (and clears) the device-side status word of the persistent kernels in `workspace` after the stream
+ * has been synchronised by the caller: 0 ok, VQCPC_ERR_TIMEOUT if an exchange timed out. */
+int vqcpc_check_status(void* workspace, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VQCPC_H */

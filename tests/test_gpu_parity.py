@@ -1,0 +1,310 @@
+"""GPU parity tests: the sm_100a CUDA path (through the C ABI / the reference-shaped Python classes) against
+the CPU oracle and the reference-generated golden vectors.  Run on the B200 box: pytest -m gpu."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import encoder as oenc
+from oracle import fixtures, mulaw
+from oracle import vocoder as ovoc
+from vectorquantizedcpc_b200 import ConfEncoder, Encoder, Vocoder, VQEmbeddingEMA, _lib
+
+pytestmark = pytest.mark.gpu
+
+# Tolerances (fp32 parity path).  north_star: encoder z/c within 1e-4 relative in fp32.
+RTOL = 1e-4
+ATOL_ZPRE = 2e-5
+ATOL_C = 2e-5
+ATOL_LOGITS = 2e-4     # teacher-forced logits, absolute (logits are O(0.1 .. 1) at random init)
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def make_encoder(C_, perturbed, seed=13):
+    sd = fixtures.encoder_init_state(C_, seed=seed)
+    if perturbed:
+        sd = fixtures.perturb_encoder_state(sd)
+    enc = Encoder(ConfEncoder(channels=C_))
+    enc.load_state_dict(sd)
+    return enc.to(dev()).eval(), sd
+
+
+_VOC = {}
+
+
+def make_vocoder():
+    if "v" not in _VOC:
+        sd = ovoc.init_state_dict(seed=13)
+        v = Vocoder()
+        v.load_state_dict(sd)
+        _VOC["v"] = (v.to(dev()).eval(), sd)
+    return _VOC["v"]
+
+
+# ------------------------------------------------------------------------------------------ building blocks
+@pytest.mark.parametrize("M,N,K,bias", [(100, 768, 320, False), (1, 64, 768, True), (1000, 2688, 256, True),
+                                        (40000, 768, 768, False), (257, 1024, 64, True), (0, 64, 64, False)])
+def test_linear_f32(M, N, K, bias):
+    g = torch.Generator().manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=g)
+    W = torch.randn(N, K, generator=g) / K ** 0.5
+    b = torch.randn(N, generator=g) if bias else None
+    ref = (A.double() @ W.double().t() + (b.double() if bias else 0)).float()
+    Ad, Wd = A.to(dev()), W.to(dev())
+    bd = b.to(dev()) if bias else None
+    out = torch.empty(M, N, device=dev())
+    st = _lib.lib().vqcpc_linear_f32(_lib.ptr(Ad), K, _lib.ptr(Wd), K, _lib.ptr(bd), _lib.ptr(out), N, M, N, K,
+                                     _lib.current_stream_ptr())
+    _lib.check(st, "linear")
+    torch.cuda.synchronize()
+    assert torch.allclose(out.cpu(), ref, rtol=1e-5, atol=1e-5)
+
+
+def test_linear_rejects_bad_k():
+    A = torch.zeros(4, 20, device=dev())
+    out = torch.empty(4, 8, device=dev())
+    st = _lib.lib().vqcpc_linear_f32(_lib.ptr(A), 20, _lib.ptr(A), 20, None, _lib.ptr(out), 8, 4, 8, 20,
+                                     _lib.current_stream_ptr())
+    with pytest.raises(ValueError):
+        _lib.check(st, "linear")
+
+
+@pytest.mark.parametrize("rows,C_", [(100, 768), (7, 512), (4097, 768), (3, 128)])
+def test_layernorm_relu(rows, C_):
+    g = torch.Generator().manual_seed(rows)
+    x = torch.randn(rows, C_, generator=g) * 3 + 0.5
+    w = torch.randn(C_, generator=g)
+    b = torch.randn(C_, generator=g)
+    ref = torch.relu(oenc.layer_norm(x.double(), w.double(), b.double())).float()
+    xd, wd, bd = x.to(dev()), w.to(dev()), b.to(dev())
+    _lib.check(_lib.lib().vqcpc_layernorm_relu_f32(_lib.ptr(xd), _lib.ptr(wd), _lib.ptr(bd), rows, C_,
+                                                   _lib.current_stream_ptr()), "ln")
+    assert torch.allclose(xd.cpu(), ref, rtol=1e-5, atol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------ VQ lookup
+def run_vq(x, cb):
+    vq = VQEmbeddingEMA(512, 64)
+    vq.embedding.copy_(cb)
+    vq = vq.to(dev())
+    q, idx = vq.encode(x.to(dev()))
+    return q.cpu(), idx.cpu()
+
+
+@pytest.mark.parametrize("kind", ["init", "trained"])
+def test_vq_lookup_matches_oracle_and_golden(golden_dir, kind):
+    g = np.load(os.path.join(golden_dir, "vq_lookup.npz"))
+    x, cb = fixtures.vq_inputs(20000, kind=kind, seed=1234, batch=2)
+    q, idx = run_vq(x, cb)
+    assert idx.dtype == torch.int64 and idx.shape == (2, 20000) and q.shape == x.shape
+    _, idx_o = oenc.vq_lookup(x, cb)
+    rep = oenc.classify_index_mismatches(x, cb, idx, idx_o)
+    assert rep["hard"] == 0, rep                     # zero non-near-tie mismatches vs the oracle
+    rep_g = oenc.classify_index_mismatches(x, cb, idx, torch.from_numpy(g[f"{kind}_indices"].astype(np.int64)))
+    assert rep_g["hard"] == 0, rep_g                 # ... and vs the live reference's golden indices
+    assert rep["mismatches"] <= 20 and rep_g["mismatches"] <= 20
+    # against fp64 truth the kernel (which drops the argmin-invariant |x|^2 term) must be at least as good
+    truth = oenc.vq_scores_exact(x, cb).argmin(dim=-1)
+    rep_t = oenc.classify_index_mismatches(x, cb, idx, truth.view(2, -1))
+    assert rep_t["hard"] == 0 and rep_t["mismatches"] <= rep_g["mismatches"] + 2, (rep_t, rep_g)
+    assert torch.equal(q, cb[idx])                   # gather is bit-exact
+    print(f"[vq {kind}] vs oracle {rep} | vs golden {rep_g} | vs fp64 {rep_t}")
+
+
+def test_vq_exact_tie_and_ragged_sizes():
+    x, cb = fixtures.vq_inputs(16, kind="trained", seed=5)
+    cb[300] = cb[7]
+    xq = cb[[7, 300, 12, 7]][None]
+    _, idx = run_vq(xq, cb)
+    assert idx.tolist() == [[7, 7, 12, 7]]           # lowest index wins (torch.argmin semantics)
+    for n in (1, 127, 128, 129, 1000):
+        x, cb = fixtures.vq_inputs(n, kind="trained", seed=n)
+        q, idx = run_vq(x, cb)
+        _, idx_o = oenc.vq_lookup(x, cb)
+        assert torch.equal(idx, idx_o) and torch.equal(q, cb[idx])
+    q, idx = run_vq(torch.zeros(2, 0, 64), cb)
+    assert q.shape == (2, 0, 64) and idx.shape == (2, 0)
+
+
+def test_vq_full_size_properties():
+    """BASELINE config 2 size (1 M frames): idempotence, index range, checksum of checksums."""
+    x, cb = fixtures.vq_inputs(1_000_000, kind="trained", seed=1234)
+    vq = VQEmbeddingEMA(512, 64)
+    vq.embedding.copy_(cb)
+    vq = vq.to(dev())
+    xd = x.to(dev())
+    q, idx = vq.encode(xd)
+    assert int(idx.min()) >= 0 and int(idx.max()) < 512
+    q2, idx2 = vq.encode(q)                          # quantising a code vector returns the same code
+    cbd = cb.to(dev())
+    assert torch.equal(q2, q)
+    d_self = ((cbd[idx2] - cbd[idx]) ** 2).sum(-1)
+    assert float(d_self.max()) == 0.0
+    assert torch.equal(q, cbd[idx])
+    # every frame's chosen code is at least as close as 64 random other codes (fp64 check on a sample)
+    sel = torch.randint(0, 1_000_000, (2000,))
+    sc = oenc.vq_scores_exact(x[:, sel], cb)
+    best = sc.min(dim=-1).values
+    chosen = sc[torch.arange(2000), idx.cpu()[0, sel]]
+    assert float((chosen - best).max()) < 1e-4
+
+
+# ------------------------------------------------------------------------------------------ encoder
+CASES = ["encoder_c768_T200_init", "encoder_c512_T201_trained", "encoder_c768_T301_B3_trained",
+         "encoder_c768_T8_B2_trained"]
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_encoder_matches_golden(golden_dir, name):
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    enc, sd = make_encoder(int(g["channels"]), bool(g["perturbed"]))
+    mel = fixtures.synthetic_mel(int(g["B"]), int(g["T"]), seed=int(g["mel_seed"]), kind=str(g["mel_kind"]))
+    z, c, idx, prevq = [t.cpu() for t in enc.encode_with_aux(mel.to(dev()))]
+    ref_pre = torch.from_numpy(g["z_pre"])
+    assert z.shape == ref_pre.shape and idx.dtype == torch.int64
+    assert torch.allclose(prevq, ref_pre, rtol=RTOL, atol=ATOL_ZPRE), float((prevq - ref_pre).abs().max())
+    ref_idx = torch.from_numpy(g["indices"])
+    # near-tie slack: |dz| * |e_a - e_b| bound from the pre-VQ tolerance
+    rep = oenc.classify_index_mismatches(ref_pre, sd["codebook.embedding"], idx, ref_idx, slack=1e-5)
+    assert rep["hard"] == 0, rep
+    same = idx == ref_idx
+    assert same.float().mean() >= 0.98, rep
+    assert torch.equal(z[same], torch.from_numpy(g["z"])[same])
+    ref_c = torch.from_numpy(g["c"])
+    ok_utts = same.all(dim=1)
+    assert torch.allclose(c[ok_utts], ref_c[ok_utts], rtol=RTOL, atol=ATOL_C), float((c[ok_utts] - ref_c[ok_utts]).abs().max())
+    print(f"[{name}] idx mismatches {rep}; max|dz_pre| {float((prevq - ref_pre).abs().max()):.2e}; "
+          f"max|dc| {float((c[ok_utts] - ref_c[ok_utts]).abs().max()) if ok_utts.any() else float('nan'):.2e}")
+
+
+def test_encoder_matches_oracle_other_shapes_and_hook():
+    enc, sd = make_encoder(512, True)
+    aux = []
+    h = enc.encoder[-1].register_forward_hook(lambda m, i, o: aux.append((i[0].clone(), o.clone())))
+    for (B, T, seed) in [(1, 2, 5), (5, 33, 6), (2, 100, 7)]:
+        mel = fixtures.synthetic_mel(B, T, seed=seed)
+        z, c, idx = [t.cpu() for t in enc.encode(mel.to(dev()))]
+        zo, co, io, zp = oenc.encode(sd, mel, return_aux=True)
+        hid_in, pre = aux.pop()
+        assert hid_in.shape == (B, (T - 2) // 2 + 1, 512)
+        assert torch.allclose(pre.cpu(), zp, rtol=RTOL, atol=ATOL_ZPRE)
+        assert torch.equal(idx, io) and torch.equal(z, zo)
+        assert torch.allclose(c, co, rtol=RTOL, atol=ATOL_C)
+    h.remove()
+    with pytest.raises(ValueError):
+        enc.encode(torch.zeros(1, 40, 10, device=dev()))
+    with pytest.raises(ValueError):
+        enc.encode(torch.zeros(1, 80, 1, device=dev()))
+
+
+@pytest.mark.parametrize("B,Tp", [(1, 100), (3, 7), (50, 31), (100, 17), (97, 5)])
+def test_lstm_matches_oracle(B, Tp):
+    """Covers the three lockstep widths (NB = 1, 4, 8), odd lengths and a ragged last chunk."""
+    enc, sd = make_encoder(512, True)
+    g = torch.Generator().manual_seed(B * 1000 + Tp)
+    idx = torch.randint(0, 512, (B, Tp), generator=g)
+    ref = oenc.lstm(sd["codebook.embedding"][idx], sd["rnn.weight_ih_l0"], sd["rnn.weight_hh_l0"],
+                    sd["rnn.bias_ih_l0"], sd["rnn.bias_hh_l0"])
+    w, _keep = enc.pack_weights()
+    lib = _lib.lib()
+    ws_bytes = lib.vqcpc_lstm_workspace_bytes(B, Tp)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev())
+    out = torch.empty(B, Tp, 256, device=dev())
+    idxd = idx.to(dev())
+    _lib.check(lib.vqcpc_lstm_forward(C.byref(w), _lib.ptr(idxd), B, Tp, _lib.ptr(ws), ws_bytes, _lib.ptr(out),
+                                      _lib.current_stream_ptr()), "lstm")
+    _lib.check(lib.vqcpc_check_status(_lib.ptr(ws), _lib.current_stream_ptr()), "lstm status")
+    assert torch.allclose(out.cpu(), ref, rtol=RTOL, atol=ATOL_C), float((out.cpu() - ref).abs().max())
+
+
+# ------------------------------------------------------------------------------------------ vocoder
+def test_vocoder_conditioning_matches_oracle():
+    voc, sd = make_vocoder()
+    for (B, Tc, seed) in [(1, 50, 0), (3, 7, 1), (2, 1, 2)]:
+        codes, spk, _ = fixtures.vocoder_inputs(B, Tc, seed=seed)
+        G, p = voc.condition(codes.to(dev()), spk.to(dev()), return_prenet=True)
+        p_o = ovoc.condition(sd, codes, spk)
+        assert torch.allclose(p.cpu(), p_o, rtol=RTOL, atol=2e-5), float((p.cpu() - p_o).abs().max())
+        G_o = p_o @ sd["rnnms.ar.rnn.weight_ih_l0"][:, 256:].t() + sd["rnnms.ar.rnn.bias_ih_l0"]
+        assert torch.allclose(G.cpu(), G_o, rtol=RTOL, atol=2e-5)
+
+
+def test_vocoder_teacher_forced_logits_match_oracle():
+    voc, sd = make_vocoder()
+    B, Tc, L = 2, 2, 500
+    codes, spk, _ = fixtures.vocoder_inputs(B, Tc, seed=3)
+    g = torch.Generator().manual_seed(11)
+    x = torch.randint(0, 256, (B, L), generator=g)
+    logits = voc.forward(x.to(dev()), codes.to(dev()), spk.to(dev())).cpu()
+    ref = ovoc.forward_teacher_forced(sd, x, codes, spk)
+    err = float((logits - ref).abs().max())
+    print(f"[teacher-forced] max |dlogit| = {err:.3e} over {B}x{L} steps")
+    assert logits.shape == (B, L, 256)
+    assert err < ATOL_LOGITS
+
+
+def test_vocoder_generate_matches_oracle_with_injected_uniforms():
+    voc, sd = make_vocoder()
+    B, Tc = 2, 2
+    L = 320 * Tc
+    codes, spk, u = fixtures.vocoder_inputs(B, Tc, seed=0)
+    wav, x, logits = voc.generate(codes.to(dev()), spk.to(dev()), uniforms=u.to(dev()), return_mulaw=True,
+                                  return_logits=True)
+    wav, x, logits = wav.cpu(), x.cpu(), logits.cpu()
+    assert wav.shape == (B, L) and x.shape == (B, L) and x.dtype == torch.int64
+    lut = torch.from_numpy(mulaw.mulaw_decode_lut(8))
+    assert torch.equal(wav, lut[x])                                  # mu-law decode epilogue is bit-exact
+    # (1) free-running match against the oracle with identical uniforms (reported; chaotic after a divergence)
+    wav_o, x_o, _ = ovoc.generate(sd, codes, spk, u, return_all=True)
+    match = (x == x_o)
+    first_div = [int((~m).nonzero()[0]) if (~m).any() else L for m in match]
+    print(f"[generate] free-running sample match rate {float(match.float().mean()):.4f}; first divergence {first_div}")
+    assert min(first_div) >= 50          # an early divergence would mean a wrong recurrence, not a rounding tie
+    # (2) rigorous check: replay the GPU's own samples through the oracle (teacher forced): the logits must
+    # agree and every sample must be consistent with its uniform under the oracle's CDF.
+    x_in = torch.cat([torch.full((B, 1), 128, dtype=torch.int64), x[:, :-1]], dim=1)
+    ref = ovoc.forward_teacher_forced(sd, x_in, codes, spk)
+    err = float((logits - ref).abs().max())
+    assert err < ATOL_LOGITS, err
+    cdf = ovoc.cdf_bounds(ref)
+    hi = torch.gather(cdf, 2, x[..., None])[..., 0]
+    lo = torch.where(x > 0, torch.gather(cdf, 2, (x - 1).clamp(min=0)[..., None])[..., 0], torch.zeros_like(hi))
+    tol = 5e-5
+    ok = (u.double() >= lo - tol) & (u.double() <= hi + tol)
+    assert bool(ok.all()), f"{int((~ok).sum())} samples inconsistent with their uniform"
+
+
+def test_vocoder_generate_full_second_properties():
+    """BASELINE config 3 size (B=1, 1 s = 16 000 steps): determinism under the same uniforms, range, LUT."""
+    voc, _ = make_vocoder()
+    codes, spk, u = fixtures.vocoder_inputs(1, 50, seed=0)
+    a, xa = voc.generate(codes.to(dev()), spk.to(dev()), uniforms=u.to(dev()), return_mulaw=True)
+    b, xb = voc.generate(codes.to(dev()), spk.to(dev()), uniforms=u.to(dev()), return_mulaw=True)
+    assert a.shape == (1, 16000) and torch.equal(a, b) and torch.equal(xa, xb)
+    assert int(xa.min()) >= 0 and int(xa.max()) <= 255 and float(a.abs().max()) <= 1.0
+    assert len(torch.unique(xa)) > 50                 # actually sampling, not stuck
+    c = voc.generate(codes.to(dev()), spk.to(dev()))  # device-side uniforms
+    assert c.shape == (1, 16000) and not torch.equal(a, c)
+    short = voc.generate(codes.to(dev()), spk.to(dev()), uniforms=u[:, :100].to(dev()), n_steps=100)
+    assert torch.equal(short, a[:, :100])
+
+
+def test_vocoder_argument_errors():
+    voc, _ = make_vocoder()
+    z = torch.zeros(1, 2, dtype=torch.int64, device=dev())
+    s = torch.zeros(1, dtype=torch.int64, device=dev())
+    with pytest.raises(IndexError):
+        voc.generate(z + 512, s)
+    with pytest.raises(IndexError):
+        voc.generate(z, s + 102)
+    with pytest.raises(ValueError):
+        voc.generate(z.int(), s)
+    with pytest.raises(ValueError):
+        voc.generate(z, s, uniforms=torch.zeros(1, 5, device=dev()))
+    with pytest.raises(ValueError):
+        voc.forward(torch.zeros(1, 700, dtype=torch.int64, device=dev()), z, s)

@@ -1,0 +1,75 @@
+// Error reporting, device queries and status read-back for libvqcpc_b200 (C ABI in include/vqcpc.h).
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace vqcpc {
+
+static thread_local char g_error[1024] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+}
+
+static int cached_attr(cudaDeviceAttr attr) {
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (cudaDeviceGetAttribute(&v, attr, dev) != cudaSuccess) return 0;
+    return v;
+}
+int device_sm_count() {
+    static thread_local int v = 0;
+    if (v == 0) v = cached_attr(cudaDevAttrMultiProcessorCount);
+    return v;
+}
+int device_cc_major() {
+    static thread_local int v = 0;
+    if (v == 0) v = cached_attr(cudaDevAttrComputeCapabilityMajor);
+    return v;
+}
+
+}  // namespace vqcpc
+
+extern "C" const char* vqcpc_last_error(void) { return vqcpc::g_error; }
+extern "C" int vqcpc_abi_version(void) { return VQCPC_ABI_VERSION; }
+
+extern "C" int vqcpc_device_check(int device) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || device < 0 || device >= n) {
+        vqcpc::set_error("no CUDA device %d (%s)", device, e == cudaSuccess ? "out of range" : cudaGetErrorString(e));
+        return VQCPC_ERR_DEVICE;
+    }
+    int major = 0, sms = 0, coop = 0;
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
+    if (major != 10 || sms < 128 || !coop) {
+        vqcpc::set_error("device %d is not a B200-class GPU (cc major %d, %d SMs, cooperative launch %d); "
+                         "this library is built for sm_100a only", device, major, sms, coop);
+        return VQCPC_ERR_DEVICE;
+    }
+    return VQCPC_OK;
+}
+
+extern "C" int vqcpc_check_status(void* workspace, void* stream) {
+    if (workspace == nullptr) {
+        vqcpc::set_error("check_status: null workspace");
+        return VQCPC_ERR_ARG;
+    }
+    int status = 0;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    VQ_CUDA(cudaMemcpyAsync(&status, workspace, sizeof(int), cudaMemcpyDeviceToHost, s));
+    VQ_CUDA(cudaStreamSynchronize(s));
+    if (status != 0) {
+        VQ_CUDA(cudaMemsetAsync(workspace, 0, sizeof(int), s));
+        vqcpc::set_error("persistent kernel reported status %d (%s)", status,
+                         status == VQCPC_ERR_TIMEOUT ? "LL exchange timed out" : "unknown");
+    }
+    return status;
+}

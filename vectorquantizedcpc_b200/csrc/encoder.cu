@@ -1,0 +1,492 @@
+// Encoder.encode of /root/reference/model.py:59-70 on sm_100a, fp32 parity path:
+//   conv (implicit-im2col GEMM) -> LN+ReLU -> 4x[Linear -> LN+ReLU] -> Linear(C,64)+b -> VQ lookup -> LSTM.
+// This file: LayerNorm+ReLU rows, the exact fp32 VQ nearest-code search + gather, the persistent LSTM
+// (LL exchange between 32-CTA groups, W_hh resident in registers) and the host-side orchestration.
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace vqcpc {
+
+// ------------------------------------------------------------------------------------------------
+// relu(LayerNorm(x)) in place, one warp per row  (nn.LayerNorm(C) + nn.ReLU, model.py:47-48,51-52).
+// mean, then biased variance of (x - mean), eps = 1e-5: the oracle's two-pass formula.
+// ------------------------------------------------------------------------------------------------
+template <int N4>
+__global__ void __launch_bounds__(256) ln_relu_kernel(float* __restrict__ x, const float* __restrict__ w,
+                                                      const float* __restrict__ b, int64_t rows) {
+    constexpr int C = N4 * 128;
+    const int lane = threadIdx.x & 31;
+    const int64_t row = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    float4* p = reinterpret_cast<float4*>(x + row * C);
+    float4 v[N4];
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < N4; ++j) {
+        v[j] = p[j * 32 + lane];
+        s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+    }
+    const float mean = warp_sum(s) * (1.0f / C);
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < N4; ++j) {
+        v[j].x -= mean; v[j].y -= mean; v[j].z -= mean; v[j].w -= mean;
+        q += (v[j].x * v[j].x + v[j].y * v[j].y) + (v[j].z * v[j].z + v[j].w * v[j].w);
+    }
+    const float rstd = 1.0f / sqrtf(warp_sum(q) * (1.0f / C) + 1e-5f);
+#pragma unroll
+    for (int j = 0; j < N4; ++j) {
+        const float4 ww = __ldg(reinterpret_cast<const float4*>(w) + j * 32 + lane);
+        const float4 bb = __ldg(reinterpret_cast<const float4*>(b) + j * 32 + lane);
+        float4 o;
+        o.x = fmaxf(fmaf(v[j].x * rstd, ww.x, bb.x), 0.f);
+        o.y = fmaxf(fmaf(v[j].y * rstd, ww.y, bb.y), 0.f);
+        o.z = fmaxf(fmaf(v[j].z * rstd, ww.z, bb.z), 0.f);
+        o.w = fmaxf(fmaf(v[j].w * rstd, ww.w, bb.w), 0.f);
+        p[j * 32 + lane] = o;
+    }
+}
+
+int layernorm_relu(float* x, const float* w, const float* b, int64_t rows, int C, cudaStream_t stream) {
+    VQ_ARG(x && w && b, "layernorm: null pointer");
+    VQ_ARG(C % 128 == 0 && C >= 128 && C <= 1024, "layernorm: C=%d must be a multiple of 128 in [128,1024]", C);
+    if (rows == 0) return VQCPC_OK;
+    const unsigned grid = static_cast<unsigned>((rows + 7) / 8);
+    switch (C / 128) {
+#define LN_CASE(n) case n: ln_relu_kernel<n><<<grid, 256, 0, stream>>>(x, w, b, rows); break;
+        LN_CASE(1) LN_CASE(2) LN_CASE(3) LN_CASE(4) LN_CASE(5) LN_CASE(6) LN_CASE(7) LN_CASE(8)
+#undef LN_CASE
+    }
+    VQ_CUDA(cudaGetLastError());
+    return VQCPC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// VQ lookup (VQEmbeddingEMA.encode, model.py:103-115), exact fp32 path.
+// score[n,m] = |e_m|^2 - 2 x_n.e_m, dot accumulated over k = 0..63 in order with FMA; first minimum wins.
+// Persistent CTAs; the whole codebook is transposed into shared memory once per CTA (k-major, 128 KB) and
+// each 128-frame tile of x is transposed into a 33 KB k-major tile; 8x8 register micro-tiles, four passes
+// of 128 codes.  The gather re-reads codebook rows from L2 (256 B contiguous per frame).
+// ------------------------------------------------------------------------------------------------
+constexpr int VQ_D = 64, VQ_M = 512, VQ_TF = 128, VQ_LDX = VQ_TF + 4;
+constexpr size_t VQ_SMEM = sizeof(float) * (VQ_D * VQ_M + VQ_D * VQ_LDX + VQ_M) + sizeof(int) * VQ_TF;
+
+__global__ void __launch_bounds__(256, 1)
+vq_lookup_kernel(const float* __restrict__ x, const float* __restrict__ codebook, int64_t n_frames,
+                 float* __restrict__ out_q, int64_t* __restrict__ out_idx) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* Es = reinterpret_cast<float*>(smem_raw);          // [64][512]
+    float* Xs = Es + VQ_D * VQ_M;                             // [64][132]
+    float* e2 = Xs + VQ_D * VQ_LDX;                           // [512]
+    int* best = reinterpret_cast<int*>(e2 + VQ_M);            // [128]
+
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;
+
+    // codebook -> shared, transposed; |e|^2 in the same k order as the oracle's sum (sequential).
+    for (int f = tid; f < VQ_M * (VQ_D / 4); f += 256) {
+        const int m = f >> 4, q = f & 15;
+        const float4 v = __ldg(reinterpret_cast<const float4*>(codebook + m * VQ_D) + q);
+        Es[(4 * q + 0) * VQ_M + m] = v.x;
+        Es[(4 * q + 1) * VQ_M + m] = v.y;
+        Es[(4 * q + 2) * VQ_M + m] = v.z;
+        Es[(4 * q + 3) * VQ_M + m] = v.w;
+    }
+    __syncthreads();
+    for (int m = tid; m < VQ_M; m += 256) {
+        float s = 0.f;
+#pragma unroll 8
+        for (int k = 0; k < VQ_D; ++k) s = fmaf(Es[k * VQ_M + m], Es[k * VQ_M + m], s);
+        e2[m] = s;
+    }
+
+    const int64_t n_tiles = (n_frames + VQ_TF - 1) / VQ_TF;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t f0 = tile * VQ_TF;
+        __syncthreads();   // previous tile's Xs / best fully consumed (also orders e2 on the first pass)
+        {
+            const int row = tid & 127, half = tid >> 7;
+            const int64_t fr = f0 + row;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int q = half * 8 + j;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (fr < n_frames) v = __ldg(reinterpret_cast<const float4*>(x + fr * VQ_D) + q);
+                Xs[(4 * q + 0) * VQ_LDX + row] = v.x;
+                Xs[(4 * q + 1) * VQ_LDX + row] = v.y;
+                Xs[(4 * q + 2) * VQ_LDX + row] = v.z;
+                Xs[(4 * q + 3) * VQ_LDX + row] = v.w;
+            }
+        }
+        __syncthreads();
+
+        float bestv[8];
+        int besti[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { bestv[i] = INFINITY; besti[i] = 0; }
+
+        for (int pass = 0; pass < VQ_M / 128; ++pass) {
+            float acc[8][8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+            const float* eb = Es + pass * 128;
+#pragma unroll 4
+            for (int k = 0; k < VQ_D; ++k) {
+                const float4 a0 = *reinterpret_cast<const float4*>(&Xs[k * VQ_LDX + ty * 4]);
+                const float4 a1 = *reinterpret_cast<const float4*>(&Xs[k * VQ_LDX + 64 + ty * 4]);
+                const float4 b0 = *reinterpret_cast<const float4*>(&eb[k * VQ_M + tx * 4]);
+                const float4 b1 = *reinterpret_cast<const float4*>(&eb[k * VQ_M + 64 + tx * 4]);
+                const float af[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                const float bf[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(af[i], bf[j], acc[i][j]);
+            }
+            // candidates visited in increasing code index inside a thread; strict < keeps the first minimum
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int m = pass * 128 + (j >> 2) * 64 + tx * 4 + (j & 3);
+                const float em = e2[m];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float sc = fmaf(-2.0f, acc[i][j], em);
+                    if (sc < bestv[i]) { bestv[i] = sc; besti[i] = m; }
+                }
+            }
+        }
+        // combine the 16 tx lanes that share a frame: lexicographic (score, index) minimum
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) {
+                const float ov = __shfl_xor_sync(0xffffffffu, bestv[i], o);
+                const int oi = __shfl_xor_sync(0xffffffffu, besti[i], o);
+                if (ov < bestv[i] || (ov == bestv[i] && oi < besti[i])) { bestv[i] = ov; besti[i] = oi; }
+            }
+        }
+        if (tx == 0) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) best[(i >> 2) * 64 + ty * 4 + (i & 3)] = besti[i];
+        }
+        __syncthreads();
+        if (tid < VQ_TF && f0 + tid < n_frames) out_idx[f0 + tid] = best[tid];
+        {
+            const int q = tid & 15;
+#pragma unroll
+            for (int it = 0; it < VQ_TF / 16; ++it) {
+                const int row = it * 16 + (tid >> 4);
+                const int64_t fr = f0 + row;
+                if (fr < n_frames) {
+                    const float4 v = __ldg(reinterpret_cast<const float4*>(codebook + best[row] * VQ_D) + q);
+                    reinterpret_cast<float4*>(out_q + fr * VQ_D)[q] = v;
+                }
+            }
+        }
+    }
+}
+
+int vq_lookup(const float* x, const float* codebook, int64_t n, int n_codes, int dim, float* q, int64_t* idx,
+              cudaStream_t stream) {
+    VQ_ARG(x && codebook && q && idx, "vq_lookup: null pointer");
+    VQ_ARG(n_codes == VQ_M && dim == VQ_D, "vq_lookup: only a 512x64 codebook is supported (got %dx%d)", n_codes, dim);
+    VQ_ARG(n >= 0, "vq_lookup: negative frame count");
+    if (n == 0) return VQCPC_OK;
+    static bool attr_set = false;
+    if (!attr_set) {
+        VQ_CUDA(cudaFuncSetAttribute(vq_lookup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VQ_SMEM));
+        attr_set = true;
+    }
+    const int64_t n_tiles = (n + VQ_TF - 1) / VQ_TF;
+    const int sms = device_sm_count();
+    const unsigned grid = static_cast<unsigned>(n_tiles < sms ? n_tiles : sms);
+    vq_lookup_kernel<<<grid, 256, VQ_SMEM, stream>>>(x, codebook, n, q, idx);
+    VQ_CUDA(cudaGetLastError());
+    return VQCPC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// LSTM(64 -> 256) over the quantised codes (model.py:57,69).
+//   x-projection: z_q takes only 512 values, so  W_ih z_q[t] + b_ih + b_hh = table[idx[t]]  with
+//   table = codebook . W_ih^T + b  (512 x 1024), one small GEMM per call.
+//   Recurrence: groups of 32 CTAs; CTA c of a group owns hidden units 8c..8c+7 (warp w <-> unit 8c+w, its 4
+//   gate rows of W_hh live in registers, 8 columns per lane).  Each step every CTA publishes its 8 new h
+//   values through the LL exchange and polls all 256.  A group advances NB utterances in lockstep to
+//   amortise the exchange latency; groups are independent (utterances never interact).
+// ------------------------------------------------------------------------------------------------
+constexpr int LSTM_H = 256, LSTM_G = 1024, LSTM_GROUP = 32;
+
+struct LstmParams {
+    const float* table;     // (512, 1024)
+    const int64_t* idx;     // (B, Tp)
+    const float* w_hh;      // (1024, 256)
+    float* out;             // (B, Tp, 256)
+    ll_word* ll;            // [n_groups][2][NB][256]
+    int* status;
+    int B, Tp, n_groups;
+};
+
+template <int NB>
+__global__ void __launch_bounds__(256) lstm_kernel(LstmParams p) {
+    __shared__ __align__(16) float hs[2][NB][LSTM_H];
+    __shared__ int abort_flag;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int group = blockIdx.x / LSTM_GROUP, cta = blockIdx.x % LSTM_GROUP;
+    const int unit = cta * 8 + warp;
+
+    // W_hh rows (gate*256 + unit), columns {4*lane..+3, 128+4*lane..+3}
+    float w[4][8];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        const float* row = p.w_hh + static_cast<int64_t>(g * LSTM_H + unit) * LSTM_H;
+        const float4 a = __ldg(reinterpret_cast<const float4*>(row) + lane);
+        const float4 b = __ldg(reinterpret_cast<const float4*>(row + 128) + lane);
+        w[g][0] = a.x; w[g][1] = a.y; w[g][2] = a.z; w[g][3] = a.w;
+        w[g][4] = b.x; w[g][5] = b.y; w[g][6] = b.z; w[g][7] = b.w;
+    }
+    if (tid == 0) abort_flag = 0;
+
+    ll_word* ll = p.ll + static_cast<size_t>(group) * 2 * NB * LSTM_H;
+    const int n_chunks = (p.B + NB - 1) / NB;
+    uint32_t tag = 0;
+
+    for (int chunk = group; chunk < n_chunks; chunk += p.n_groups) {
+        const int b0 = chunk * NB;
+        // lane nb of every warp runs the gate math of utterance slot nb
+        const int my_b = b0 + lane;
+        const bool my_valid = (lane < NB) && (my_b < p.B);
+        float cst = 0.f;
+        __syncthreads();
+        for (int i = tid; i < 2 * NB * LSTM_H; i += 256) (&hs[0][0][0])[i] = 0.f;   // h_{-1} = 0
+        __syncthreads();
+
+        float xp[4] = {0.f, 0.f, 0.f, 0.f};
+        if (my_valid) {
+            const int64_t id = p.idx[static_cast<int64_t>(my_b) * p.Tp];
+            const float* trow = p.table + id * LSTM_G + unit;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) xp[g] = __ldg(trow + g * LSTM_H);
+        }
+
+        for (int t = 0; t < p.Tp; ++t) {
+            ++tag;
+            // slot parity follows the group-global step counter (NOT t): consecutive steps always alternate,
+            // also across utterance chunks with odd Tp
+            const int cur = static_cast<int>(tag & 1u), prev = cur ^ 1;
+            // prefetch next step's x-projection
+            float xn[4] = {0.f, 0.f, 0.f, 0.f};
+            if (my_valid && t + 1 < p.Tp) {
+                const int64_t id = p.idx[static_cast<int64_t>(my_b) * p.Tp + t + 1];
+                const float* trow = p.table + id * LSTM_G + unit;
+#pragma unroll
+                for (int g = 0; g < 4; ++g) xn[g] = __ldg(trow + g * LSTM_H);
+            }
+            float mine[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int nb = 0; nb < NB; ++nb) {
+                const float4 h0 = *reinterpret_cast<const float4*>(&hs[prev][nb][4 * lane]);
+                const float4 h1 = *reinterpret_cast<const float4*>(&hs[prev][nb][128 + 4 * lane]);
+                const float hv[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+                float s[4];
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    float a = 0.f;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) a = fmaf(w[g][k], hv[k], a);
+                    s[g] = a;
+                }
+#pragma unroll
+                for (int g = 0; g < 4; ++g) s[g] = warp_sum(s[g]);
+                if (lane == nb) {
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) mine[g] = s[g];
+                }
+            }
+            if (lane < NB) {
+                // PyTorch gate order i, f, g, o
+                const float ig = sigmoid_fast(mine[0] + xp[0]);
+                const float fg = sigmoid_fast(mine[1] + xp[1]);
+                const float gg = tanh_fast(mine[2] + xp[2]);
+                const float og = sigmoid_fast(mine[3] + xp[3]);
+                cst = fg * cst + ig * gg;
+                const float hn = og * tanh_fast(cst);
+                ll_store(ll + (static_cast<size_t>(cur) * NB + lane) * LSTM_H + unit, hn, tag);
+            }
+#pragma unroll
+            for (int g = 0; g < 4; ++g) xp[g] = xn[g];
+
+            // gather all 256 hidden values of every slot: thread tid polls column tid
+            float got[NB];
+            {
+                const ll_word* src = ll + static_cast<size_t>(cur) * NB * LSTM_H + tid;
+                const long long t0 = clock64();
+                bool done = false;
+                while (!done) {
+                    ll_word wv[NB];
+#pragma unroll
+                    for (int nb = 0; nb < NB; ++nb) wv[nb] = ll_load(src + nb * LSTM_H);
+                    done = true;
+#pragma unroll
+                    for (int nb = 0; nb < NB; ++nb) {
+                        done = done && (ll_tag(wv[nb]) == tag);
+                        got[nb] = ll_val(wv[nb]);
+                    }
+                    if (!done && clock64() - t0 > LL_TIMEOUT_CYCLES) {
+                        abort_flag = 1;
+                        atomicExch(p.status, VQCPC_ERR_TIMEOUT);
+                        break;
+                    }
+                }
+            }
+#pragma unroll
+            for (int nb = 0; nb < NB; ++nb) hs[cur][nb][tid] = got[nb];
+            // CTA nb writes slot nb's output row (coalesced 1 KB)
+            if (cta < NB && b0 + cta < p.B) {
+                float v = got[0];
+#pragma unroll
+                for (int nb = 1; nb < NB; ++nb) v = (cta == nb) ? got[nb] : v;
+                p.out[(static_cast<int64_t>(b0 + cta) * p.Tp + t) * LSTM_H + tid] = v;
+            }
+            __syncthreads();
+            if (abort_flag) return;
+        }
+    }
+}
+
+static size_t lstm_ll_bytes(int n_groups, int nb) { return sizeof(ll_word) * n_groups * 2 * nb * LSTM_H; }
+constexpr int LSTM_MAX_GROUPS = 32;
+constexpr int LSTM_MAX_NB = 8;
+
+template <int NB>
+static int lstm_launch(LstmParams prm, void* ll_mem, cudaStream_t stream) {
+    int per_sm = 0;
+    VQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lstm_kernel<NB>, 256, 0));
+    const int capacity = per_sm * device_sm_count() / LSTM_GROUP;
+    if (capacity < 1) {
+        set_error("lstm: device cannot co-schedule one 32-CTA group");
+        return VQCPC_ERR_DEVICE;
+    }
+    const int n_chunks = (prm.B + NB - 1) / NB;
+    int n_groups = n_chunks < capacity ? n_chunks : capacity;
+    if (n_groups > LSTM_MAX_GROUPS) n_groups = LSTM_MAX_GROUPS;
+    prm.n_groups = n_groups;
+    prm.ll = static_cast<ll_word*>(ll_mem);
+    VQ_CUDA(cudaMemsetAsync(ll_mem, 0, lstm_ll_bytes(n_groups, NB), stream));
+    void* args[] = {&prm};
+    VQ_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(lstm_kernel<NB>), dim3(n_groups * LSTM_GROUP),
+                                        dim3(256), args, 0, stream));
+    return VQCPC_OK;
+}
+
+// workspace: [header][table 512x1024][ll]
+static size_t lstm_ws_bytes() {
+    return sizeof(WorkspaceHeader) + align_up(sizeof(float) * VQ_M * LSTM_G, 256) +
+           lstm_ll_bytes(LSTM_MAX_GROUPS, LSTM_MAX_NB);
+}
+
+int lstm_forward(const vqcpc_encoder_weights* w, const int64_t* idx, int B, int Tp, void* ws, size_t ws_bytes,
+                 float* out_c, cudaStream_t stream) {
+    VQ_ARG(w && idx && ws && out_c, "lstm: null pointer");
+    VQ_ARG(w->n_embeddings == VQ_M && w->z_dim == VQ_D && w->c_dim == LSTM_H,
+           "lstm: only 512 codes x 64 -> 256 is supported");
+    VQ_ARG(ws_bytes >= lstm_ws_bytes(), "lstm: workspace too small (%zu < %zu)", ws_bytes, lstm_ws_bytes());
+    if (B == 0 || Tp == 0) return VQCPC_OK;
+    unsigned char* base = static_cast<unsigned char*>(ws);
+    WorkspaceHeader* hdr = reinterpret_cast<WorkspaceHeader*>(base);
+    float* table = reinterpret_cast<float*>(base + sizeof(WorkspaceHeader));
+    void* ll = base + sizeof(WorkspaceHeader) + align_up(sizeof(float) * VQ_M * LSTM_G, 256);
+    VQ_CUDA(cudaMemsetAsync(hdr, 0, sizeof(WorkspaceHeader), stream));
+    int rc = gemm_dense(w->codebook, VQ_D, w->lstm_w_ih, VQ_D, w->lstm_b, table, LSTM_G, VQ_M, LSTM_G, VQ_D, stream);
+    if (rc) return rc;
+    LstmParams prm{};
+    prm.table = table;
+    prm.idx = idx;
+    prm.w_hh = w->lstm_w_hh;
+    prm.out = out_c;
+    prm.status = &hdr->status;
+    prm.B = B;
+    prm.Tp = Tp;
+    // lockstep width: latency case keeps one utterance per group, large batches amortise the exchange
+    if (B >= 8 * 12) return lstm_launch<8>(prm, ll, stream);
+    if (B >= 4 * 12) return lstm_launch<4>(prm, ll, stream);
+    return lstm_launch<1>(prm, ll, stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Orchestration of Encoder.encode.
+// workspace: [lstm workspace][act0 M*C][act1 M*C][z_pre M*64]
+// ------------------------------------------------------------------------------------------------
+static size_t encoder_ws_bytes(int B, int T, int C) {
+    const int Tp = T >= 2 ? (T - 2) / 2 + 1 : 0;
+    const size_t M = static_cast<size_t>(B) * Tp;
+    return align_up(lstm_ws_bytes(), 256) + 2 * align_up(M * C * sizeof(float), 256) +
+           align_up(M * VQ_D * sizeof(float), 256);
+}
+
+int encoder_forward(const vqcpc_encoder_weights* w, const float* mel, int B, int T, void* ws, size_t ws_bytes,
+                    float* out_z, float* out_c, int64_t* out_idx, float* out_prevq, float* out_hidden,
+                    cudaStream_t stream) {
+    VQ_ARG(w && mel && ws && out_z && out_c && out_idx, "encoder: null pointer");
+    VQ_ARG(B >= 0 && T >= 2, "encoder: bad shape B=%d T=%d (T must be >= 2)", B, T);
+    const int C = w->channels;
+    VQ_ARG(w->in_channels == 80, "encoder: in_channels must be 80");
+    VQ_ARG(C % 128 == 0 && C >= 128 && C <= 1024, "encoder: channels=%d must be a multiple of 128 in [128,1024]", C);
+    VQ_ARG(ws_bytes >= encoder_ws_bytes(B, T, C), "encoder: workspace too small");
+    if (B == 0) return VQCPC_OK;
+    const int Tp = (T - 2) / 2 + 1;
+    const int64_t M = static_cast<int64_t>(B) * Tp;
+    unsigned char* base = static_cast<unsigned char*>(ws);
+    void* lstm_ws = base;
+    size_t off = align_up(lstm_ws_bytes(), 256);
+    float* act[2];
+    act[0] = reinterpret_cast<float*>(base + off); off += align_up(M * C * sizeof(float), 256);
+    act[1] = reinterpret_cast<float*>(base + off); off += align_up(M * C * sizeof(float), 256);
+    float* zpre = out_prevq ? out_prevq : reinterpret_cast<float*>(base + off);
+
+    int rc;
+    if ((rc = gemm_conv(mel, B, T, 80, w->conv_w, act[0], C, stream))) return rc;
+    if ((rc = layernorm_relu(act[0], w->ln_w[0], w->ln_b[0], M, C, stream))) return rc;
+    int cur = 0;
+    for (int j = 0; j < 4; ++j) {
+        if ((rc = gemm_dense(act[cur], C, w->fc_w[j], C, nullptr, act[cur ^ 1], C, M, C, C, stream))) return rc;
+        cur ^= 1;
+        if ((rc = layernorm_relu(act[cur], w->ln_w[j + 1], w->ln_b[j + 1], M, C, stream))) return rc;
+    }
+    if (out_hidden)
+        VQ_CUDA(cudaMemcpyAsync(out_hidden, act[cur], M * C * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+    if ((rc = gemm_dense(act[cur], C, w->proj_w, C, w->proj_b, zpre, VQ_D, M, VQ_D, C, stream))) return rc;
+    if ((rc = vq_lookup(zpre, w->codebook, M, VQ_M, VQ_D, out_z, out_idx, stream))) return rc;
+    return lstm_forward(w, out_idx, B, Tp, lstm_ws, lstm_ws_bytes(), out_c, stream);
+}
+
+}  // namespace vqcpc
+
+// ------------------------------------------------------------------------------------------------ C ABI
+extern "C" int vqcpc_layernorm_relu_f32(float* x, const float* w, const float* b, int64_t rows, int32_t C,
+                                        void* stream) {
+    return vqcpc::layernorm_relu(x, w, b, rows, C, static_cast<cudaStream_t>(stream));
+}
+extern "C" int vqcpc_vq_lookup(const float* x, const float* codebook, int64_t n_frames, int32_t n_codes, int32_t dim,
+                               float* out_q, int64_t* out_idx, void* stream) {
+    return vqcpc::vq_lookup(x, codebook, n_frames, n_codes, dim, out_q, out_idx, static_cast<cudaStream_t>(stream));
+}
+extern "C" size_t vqcpc_encoder_workspace_bytes(int32_t B, int32_t T, int32_t channels) {
+    return vqcpc::encoder_ws_bytes(B, T, channels);
+}
+extern "C" int vqcpc_encoder_forward(const vqcpc_encoder_weights* w, const float* mel, int32_t B, int32_t T,
+                                     void* workspace, size_t workspace_bytes, float* out_z, float* out_c,
+                                     int64_t* out_idx, float* out_prevq, float* out_hidden, void* stream) {
+    return vqcpc::encoder_forward(w, mel, B, T, workspace, workspace_bytes, out_z, out_c, out_idx, out_prevq,
+                                  out_hidden, static_cast<cudaStream_t>(stream));
+}
+extern "C" size_t vqcpc_lstm_workspace_bytes(int32_t B, int32_t Tp) {
+    (void)B; (void)Tp;
+    return vqcpc::lstm_ws_bytes();
+}
+extern "C" int vqcpc_lstm_forward(const vqcpc_encoder_weights* w, const int64_t* idx, int32_t B, int32_t Tp,
+                                  void* workspace, size_t workspace_bytes, float* out_c, void* stream) {
+    return vqcpc::lstm_forward(w, idx, B, Tp, workspace, workspace_bytes, out_c, static_cast<cudaStream_t>(stream));
+}

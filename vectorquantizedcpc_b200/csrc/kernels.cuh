@@ -1,0 +1,27 @@
+// Internal (non-exported) launchers shared between translation units of libvqcpc_b200.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace vqcpc {
+
+// gemm_f32.cu
+int gemm_dense(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias, float* C, int64_t ldc,
+               int64_t M, int N, int K, cudaStream_t stream);
+int gemm_conv(const float* mel, int B, int T, int Cin, const float* W, float* C, int Cout, cudaStream_t stream);
+
+// encoder.cu
+int layernorm_relu(float* x, const float* w, const float* b, int64_t rows, int C, cudaStream_t stream);
+int vq_lookup(const float* x, const float* codebook, int64_t n, int n_codes, int dim, float* q, int64_t* idx,
+              cudaStream_t stream);
+
+// persistent-kernel workspace header (first bytes of every workspace handed to a persistent kernel)
+struct WorkspaceHeader {
+    int status;       // 0 ok, else VQCPC_ERR_*
+    int reserved[63];
+};
+
+int device_sm_count();
+int device_cc_major();
+
+}  // namespace vqcpc

@@ -1,0 +1,188 @@
+"""Host-side mirror of /root/reference/model.py:17-155 (``ConfEncoder``, ``Encoder``, ``VQEmbeddingEMA``).
+
+Same class names, constructor fields, attribute names (``conv``, ``encoder``, ``codebook``, ``rnn``) and
+``state_dict`` layout as the reference, so ``load_state_dict`` of a reference checkpoint and the forward
+hook of encode.py:34-40 resolve unchanged.  The ``nn`` sub-modules are PARAMETER CONTAINERS only: every
+operation of ``encode`` runs in hand-written sm_100a CUDA behind the C ABI of include/vqcpc.h.
+There is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from itertools import chain
+from typing import Tuple
+
+import torch
+import torch.nn as nn
+from torch import Tensor
+
+from . import _lib
+
+
+@dataclass
+class ConfEncoder:
+    """/root/reference/model.py:17-31 (defaults = the values config.py:28-33 resolves to, channels per the
+    north-star headline; the reference YAML default is 512)."""
+    in_channels: int = 80
+    channels: int = 768
+    n_embeddings: int = 512
+    z_dim: int = 64
+    c_dim: int = 256
+
+
+def _check_no_grad(*tensors: Tensor) -> None:
+    if torch.is_grad_enabled() and any(t.requires_grad for t in tensors):
+        raise RuntimeError("vectorquantizedcpc_b200 is inference-only: call under torch.no_grad() "
+                           "(as convert.py:75 / encode.py:45 do) or detach the inputs")
+
+
+class VQEmbeddingEMA(nn.Module):
+    """/root/reference/model.py:89-115.  ``encode`` is the hot path; ``forward`` (EMA codebook update,
+    commitment loss -- model.py:117-155) is training-only and out of scope."""
+
+    def __init__(self, n_embeddings: int, embedding_dim: int, commitment_cost: float = 0.25, decay: float = 0.999,
+                 epsilon: float = 1e-5):
+        super().__init__()
+        self.commitment_cost = commitment_cost
+        self.decay = decay
+        self.epsilon = epsilon
+        init_bound = 1 / 512
+        embedding = torch.Tensor(n_embeddings, embedding_dim)
+        embedding.uniform_(-init_bound, init_bound)
+        self.register_buffer("embedding", embedding)
+        self.register_buffer("ema_count", torch.zeros(n_embeddings))
+        self.register_buffer("ema_weight", self.embedding.clone())
+
+    def encode(self, x: Tensor) -> Tuple[Tensor, Tensor]:
+        """x (B, T, D) -> (quantized (B, T, D), indices (B, T) int64) -- model.py:103-115."""
+        _lib.require_cuda(x, "x")
+        _lib.require_cuda(self.embedding, "codebook")
+        _check_no_grad(x)
+        if x.dim() != 3 or x.shape[-1] != self.embedding.shape[1]:
+            raise ValueError(f"x must be (B, T, {self.embedding.shape[1]}), got {tuple(x.shape)}")
+        xf = x.detach().to(torch.float32).contiguous()
+        cb = self.embedding.detach().to(torch.float32).contiguous()
+        B, T, D = xf.shape
+        q = torch.empty_like(xf)
+        idx = torch.empty(B, T, dtype=torch.int64, device=xf.device)
+        with torch.cuda.device(xf.device):
+            st = _lib.lib().vqcpc_vq_lookup(_lib.ptr(xf), _lib.ptr(cb), B * T, cb.shape[0], D, _lib.ptr(q),
+                                            _lib.ptr(idx), _lib.current_stream_ptr())
+        _lib.check(st, "VQEmbeddingEMA.encode")
+        return q, idx
+
+    def forward(self, x):
+        raise NotImplementedError("VQEmbeddingEMA.forward is the training path (EMA update, model.py:117-155): "
+                                  "out of scope of the inference hot path; use .encode()")
+
+
+def _repeat_modules(atom_gen, n_repeat):
+    return list(chain.from_iterable([atom_gen() for _ in range(n_repeat)]))
+
+
+class Encoder(nn.Module):
+    """/root/reference/model.py:33-70.  Conv1d/k4s2 - LN - ReLU - [FC - LN - ReLU]x4 - FC - VQ + LSTM."""
+
+    def __init__(self, conf: ConfEncoder | None = None, **kwargs):
+        super().__init__()
+        if conf is None:
+            conf = ConfEncoder(**kwargs)        # stale call style Encoder(**cfg.model.encoder), convert.py:32
+        elif kwargs:
+            raise TypeError("pass either a ConfEncoder or keyword fields, not both")
+        self.conf = conf
+        # construction order == reference (same RNG stream under the same seed)
+        self.conv = nn.Conv1d(conf.in_channels, conf.channels, 4, 2, 1, bias=False)
+        self.encoder = nn.Sequential(
+            nn.LayerNorm(conf.channels),
+            nn.ReLU(True),
+            *_repeat_modules(lambda: [nn.Linear(conf.channels, conf.channels, bias=False),
+                                      nn.LayerNorm(conf.channels), nn.ReLU(True)], 4),
+            nn.Linear(conf.channels, conf.z_dim),
+        )
+        self.codebook = VQEmbeddingEMA(conf.n_embeddings, conf.z_dim)
+        self.rnn = nn.LSTM(conf.z_dim, conf.c_dim, batch_first=True)
+        self._packed = None
+        self._packed_key = None
+
+    # -------------------------------------------------------------------------------- weights
+    def _weight_tensors(self):
+        e = self.encoder
+        return [self.conv.weight, *[e[i].weight for i in (0, 3, 6, 9, 12)], *[e[i].bias for i in (0, 3, 6, 9, 12)],
+                *[e[i].weight for i in (2, 5, 8, 11)], e[14].weight, e[14].bias, self.codebook.embedding,
+                self.rnn.weight_ih_l0, self.rnn.weight_hh_l0, self.rnn.bias_ih_l0, self.rnn.bias_hh_l0]
+
+    def pack_weights(self):
+        """Build (and cache, keyed on parameter storage + version) the ``vqcpc_encoder_weights`` struct."""
+        ts = self._weight_tensors()
+        key = tuple((t.data_ptr(), t._version, t.device) for t in ts)
+        if self._packed is not None and key == self._packed_key:
+            return self._packed
+        for t in ts:
+            _lib.require_cuda(t, "Encoder parameter")
+        keep = [t.detach().to(torch.float32).contiguous() for t in ts]
+        (conv_w, l0, l1, l2, l3, l4, b0, b1, b2, b3, b4, f0, f1, f2, f3, pw, pb, cb, wih, whh, bih, bhh) = keep
+        lstm_b = (bih + bhh).contiguous()
+        keep.append(lstm_b)
+        w = _lib.EncoderWeights()
+        w.in_channels, w.channels = self.conf.in_channels, self.conf.channels
+        w.n_embeddings, w.z_dim, w.c_dim = self.conf.n_embeddings, self.conf.z_dim, self.conf.c_dim
+        w.conv_w = conv_w.data_ptr()
+        for i, t in enumerate((l0, l1, l2, l3, l4)):
+            w.ln_w[i] = t.data_ptr()
+        for i, t in enumerate((b0, b1, b2, b3, b4)):
+            w.ln_b[i] = t.data_ptr()
+        for i, t in enumerate((f0, f1, f2, f3)):
+            w.fc_w[i] = t.data_ptr()
+        w.proj_w, w.proj_b, w.codebook = pw.data_ptr(), pb.data_ptr(), cb.data_ptr()
+        w.lstm_w_ih, w.lstm_w_hh, w.lstm_b = wih.data_ptr(), whh.data_ptr(), lstm_b.data_ptr()
+        self._packed, self._packed_key = (w, keep), key
+        return self._packed
+
+    # -------------------------------------------------------------------------------- hot path
+    def encode(self, mel: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
+        """mel (B, 80, T) fp32 -> (z (B,T',64) quantised, c (B,T',256), indices (B,T') int64) -- model.py:59-70."""
+        z, c, idx, _, _ = self._encode(mel, want_aux=bool(self.encoder[-1]._forward_hooks))
+        return z, c, idx
+
+    def encode_with_aux(self, mel: Tensor):
+        """``encode`` plus the pre-VQ projection (B,T',64) -- what encode.py:34-40 captures with a forward hook."""
+        z, c, idx, prevq, _ = self._encode(mel, want_aux=True)
+        return z, c, idx, prevq
+
+    def _encode(self, mel: Tensor, want_aux: bool):
+        _lib.require_cuda(mel, "mel")
+        _check_no_grad(mel)
+        if mel.dim() != 3 or mel.shape[1] != self.conf.in_channels:
+            raise ValueError(f"mel must be (B, {self.conf.in_channels}, T), got {tuple(mel.shape)}")
+        if mel.shape[2] < 2:
+            raise ValueError("mel needs at least 2 frames (Conv1d kernel 4, stride 2, padding 1)")
+        w, _keep = self.pack_weights()
+        mel = mel.detach().to(torch.float32).contiguous()
+        B, _, T = mel.shape
+        Tp = (T - 2) // 2 + 1
+        dev = mel.device
+        lib = _lib.lib()
+        z = torch.empty(B, Tp, self.conf.z_dim, device=dev)
+        c = torch.empty(B, Tp, self.conf.c_dim, device=dev)
+        idx = torch.empty(B, Tp, dtype=torch.int64, device=dev)
+        prevq = torch.empty(B, Tp, self.conf.z_dim, device=dev) if want_aux else None
+        hidden = torch.empty(B, Tp, self.conf.channels, device=dev) if want_aux else None
+        ws_bytes = lib.vqcpc_encoder_workspace_bytes(B, T, self.conf.channels)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            st = lib.vqcpc_encoder_forward(C.byref(w), _lib.ptr(mel), B, T, _lib.ptr(ws), ws_bytes, _lib.ptr(z),
+                                           _lib.ptr(c), _lib.ptr(idx), _lib.ptr(prevq), _lib.ptr(hidden),
+                                           _lib.current_stream_ptr())
+            _lib.check(st, "Encoder.encode")
+            if B > 0:
+                _lib.check(lib.vqcpc_check_status(_lib.ptr(ws), _lib.current_stream_ptr()), "Encoder.encode (LSTM)")
+        if want_aux:
+            last = self.encoder[-1]
+            for hook in list(last._forward_hooks.values()):
+                hook(last, (hidden,), prevq)
+        return z, c, idx, prevq, hidden
+
+    def forward(self, mels):
+        raise NotImplementedError("Encoder.forward is the CPC training path (model.py:72-86): out of scope of "
+                                  "the inference hot path; use .encode()")
