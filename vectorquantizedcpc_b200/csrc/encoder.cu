@@ -48,6 +48,7 @@ __global__ void __launch_bounds__(256) ln_relu_kernel(float* __restrict__ x, con
 }
 
 int layernorm_relu(float* x, const float* w, const float* b, int64_t rows, int C, cudaStream_t stream) {
+    if (rows == 0) return VQCPC_OK;
     VQ_ARG(x && w && b, "layernorm: null pointer");
     VQ_ARG(C % 128 == 0 && C >= 128 && C <= 1024, "layernorm: C=%d must be a multiple of 128 in [128,1024]", C);
     if (rows == 0) return VQCPC_OK;
@@ -190,6 +191,7 @@ vq_lookup_kernel(const float* __restrict__ x, const float* __restrict__ codebook
 
 int vq_lookup(const float* x, const float* codebook, int64_t n, int n_codes, int dim, float* q, int64_t* idx,
               cudaStream_t stream) {
+    if (n == 0) return VQCPC_OK;
     VQ_ARG(x && codebook && q && idx, "vq_lookup: null pointer");
     VQ_ARG(n_codes == VQ_M && dim == VQ_D, "vq_lookup: only a 512x64 codebook is supported (got %dx%d)", n_codes, dim);
     VQ_ARG(n >= 0, "vq_lookup: negative frame count");
@@ -429,6 +431,7 @@ static size_t encoder_ws_bytes(int B, int T, int C) {
 int encoder_forward(const vqcpc_encoder_weights* w, const float* mel, int B, int T, void* ws, size_t ws_bytes,
                     float* out_z, float* out_c, int64_t* out_idx, float* out_prevq, float* out_hidden,
                     cudaStream_t stream) {
+    if (B == 0) return VQCPC_OK;
     VQ_ARG(w && mel && ws && out_z && out_c && out_idx, "encoder: null pointer");
     VQ_ARG(B >= 0 && T >= 2, "encoder: bad shape B=%d T=%d (T must be >= 2)", B, T);
     const int C = w->channels;

@@ -173,6 +173,7 @@ static int launch_gemm(ALoader a, const float* W, int64_t ldw, const float* bias
 
 int gemm_dense(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias, float* C, int64_t ldc,
                int64_t M, int N, int K, cudaStream_t stream) {
+    if (M == 0) return VQCPC_OK;
     VQ_ARG(A && W && C, "gemm: null pointer");
     VQ_ARG(lda % 4 == 0, "gemm: lda must be a multiple of 4");
     DenseA a{A, lda};
