@@ -1,0 +1,346 @@
+#!/usr/bin/env python
+"""bench.py -- the reference's headline metric on B200: vocoder samples/s (x real-time) + encoder frames/s.
+
+    python bench.py --gpus N --steps K --warmup W                 # our arm (N>1: launched under torchrun)
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's CPU path, timed beside it
+
+Headline workload (N = 1): BASELINE.json configs[2] -- ``Vocoder.generate`` batch 1, 1 s @ 16 kHz (Tc = 50 code
+frames -> 16 000 autoregressive steps) from random codes + speaker id, random-init weights (seed 13), synthetic
+inputs.  A "step" is one full generate call (conditioning + one persistent sample-loop launch).  With N > 1
+every rank generates its own utterance (utterances shard, weak scaling) and rank 0 gathers the waveforms (NCCL).
+``value`` is measured with inputs resident in HBM; ``e2e`` goes through the public Python API from pinned host
+buffers and reads the waveform back.  ``extra`` carries the other BASELINE configs measured in the same run
+(VQ lookup 1 M frames, Encoder.encode one 2 s utterance, batched encode) -- parity for all of them lives in tests/.
+Prints exactly ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "vocoder samples/sec (x real-time) + encoder frames/sec"
+SR = 16000
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return dict(hbm_gbs=float(d["hbm_gbs"]), bf16_tflops=float(d["bf16_tflops"]),
+                    bf16_tflops_sustained=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), source="measured")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.path = tempfile.mktemp(prefix="clocks_", suffix=".csv")
+        self.proc = None
+        self.idx = gpu_index
+
+    def start(self):
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0)
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, mx, reasons = [], [], set()
+        for line in open(self.path):
+            p = [x.strip() for x in line.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1])); mx.append(float(p[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        if sm:
+            sm.sort()
+            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def cpu_generate_sample(n_steps: int, warm: int = 50):
+    """The restated reference generate loop (oracle/vocoder.py, unhoisted as the reference writes it) on the
+    host cores: returns (samples/s, seconds).  Bounded sample of the B=1 workload; the loop is stationary."""
+    import torch
+    from oracle import fixtures
+    from oracle import vocoder as ovoc
+    sd = ovoc.init_state_dict(seed=13)
+    codes, spk, u = fixtures.vocoder_inputs(1, 50, seed=0)
+    with torch.no_grad():
+        ovoc.generate(sd, codes, spk, u, n_steps=warm)
+        t0 = time.perf_counter()
+        ovoc.generate(sd, codes, spk, u, n_steps=n_steps)
+        dt = time.perf_counter() - t0
+    return n_steps / dt, dt
+
+
+def reference_arm(args):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    n_ar = 800
+    cores = torch.get_num_threads()
+    for _ in range(max(args.warmup, 1)):
+        cpu_generate_sample(200, warm=20)
+    t = []
+    for _ in range(args.steps):
+        sps, dt = cpu_generate_sample(n_ar, warm=20)
+        t.append(dt)
+    total = sum(t)
+    value = n_ar * args.steps / total
+    sample = f"{n_ar} AR steps of the B=1 generate loop per step (prenet included), restated rnnms loop in PyTorch CPU"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "vocoder_generate_b1_1s (BASELINE configs[2])", "sample": sample},
+        "x_realtime": value / SR,
+        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="generate_b1", choices=["generate_b1", "convert_b64"])
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary configs (VQ / encoder)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return reference_arm(args)
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    from oracle import fixtures
+    from oracle import vocoder as ovoc
+    from vectorquantizedcpc_b200 import ConfEncoder, Encoder, Vocoder, VQEmbeddingEMA, _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.lib()
+    _lib.check(lib.vqcpc_device_check(local), "device check")
+    peaks = load_peaks()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
+
+    flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def flush_l2():
+        flush_buf.fill_(1)
+
+    def timed(fn, steps, warmup, flush=True):
+        """per-step CUDA events on the current stream, L2 flushed (untimed) between steps -> total ms, max over ranks"""
+        for _ in range(warmup):
+            fn()
+        barrier()
+        evs = []
+        for _ in range(steps):
+            if flush:
+                flush_l2()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            evs.append((a, b))
+        barrier()
+        return max_over_ranks(sum(a.elapsed_time(b) for a, b in evs))
+
+    # ---- model + inputs (random-init weights, seed 13; synthetic inputs per SURVEY.md 8d)
+    vsd = ovoc.init_state_dict(seed=13)
+    voc = Vocoder()
+    voc.load_state_dict(vsd)
+    voc = voc.to(dev).eval()
+    if args.workload == "generate_b1":
+        B, Tc, wname = 1, 50, "vocoder_generate_b1_1s (BASELINE configs[2])"
+    else:
+        B, Tc, wname = 64, 150, "convert_generate_b64_3s (BASELINE configs[4], generate part)"
+    L = 320 * Tc
+    codes, spk, _ = fixtures.vocoder_inputs(B, Tc, seed=rank)
+    codes_d, spk_d = codes.to(dev), spk.to(dev)
+    gen = torch.Generator(device=dev).manual_seed(7 + rank)
+    codes_h, spk_h = codes.pin_memory(), spk.pin_memory()
+    wav_h = torch.empty(B, L).pin_memory()
+    gathered = [torch.empty(B, L, device=dev) for _ in range(world)] if (world > 1 and rank == 0) else None
+
+    def gather(wav):
+        if world > 1:
+            dist.gather(wav, gathered, dst=0)
+
+    def step_resident():
+        with torch.no_grad():
+            wav = voc.generate(codes_d, spk_d, generator=gen)
+        gather(wav)
+
+    def step_e2e():
+        with torch.no_grad():
+            c = codes_h.to(dev, non_blocking=True)
+            s = spk_h.to(dev, non_blocking=True)
+            wav = voc.generate(c, s, generator=gen)
+            gather(wav)
+            wav_h.copy_(wav, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    with torch.no_grad():
+        voc.pack_weights()
+    sampler = ClockSampler(local)
+    n0 = lib.vqcpc_launch_count()
+    if rank == 0:
+        sampler.start()
+    t_ms = timed(step_resident, args.steps, args.warmup)
+    launches = (lib.vqcpc_launch_count() - n0) * args.steps // (args.steps + args.warmup)
+    t_e2e_ms = timed(step_e2e, args.steps, args.warmup)
+    clocks = sampler.stop() if rank == 0 else {}
+    samples_per_step = B * L * world
+    value = samples_per_step * args.steps / (t_ms * 1e-3)
+    e2e_value = samples_per_step * args.steps / (t_e2e_ms * 1e-3)
+
+    # ---- dominant kernel alone (ar_kernel): CUDA events around the C-ABI generate call, conditioning excluded
+    import ctypes as C
+    w, _keep = voc.pack_weights()
+    with torch.no_grad():
+        G = voc.condition(codes_d, spk_d)
+    uni = torch.rand(B, L, device=dev, generator=gen)
+    wav = torch.empty(B, L, device=dev)
+    ws_bytes = lib.vqcpc_vocoder_workspace_bytes(1, 1)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+
+    def ar_only():
+        _lib.check(lib.vqcpc_vocoder_generate(C.byref(w), _lib.ptr(G), _lib.ptr(uni), B, 2 * Tc, L, _lib.ptr(ws), ws_bytes,
+                                              _lib.ptr(wav), None, None, _lib.current_stream_ptr()), "generate")
+
+    t_ar_ms = timed(ar_only, args.steps, 3) / args.steps / B          # per launch (one utterance per launch)
+    # algorithmic HBM bytes of one launch: weights read once + E' + G + uniforms in + wav out
+    ar_bytes = 4 * (2688 * 896 + 256 * 896 + 256 * 256 + 2688 + 512 + 256 * 2688 + 2 * Tc * 2688 + 2 * L + 256)
+    roofline = {"kernel": "ar_kernel", "bound": "hbm", "achieved": ar_bytes / (t_ar_ms * 1e-3) / 1e9,
+                "peak": peaks["hbm_gbs"], "unit": "GB/s", "traffic": None,
+                "note": "latency-bound persistent kernel: see latency.us_per_step vs the exchange floor (DESIGN.md)",
+                "peak_source": peaks["source"]}
+    roofline["frac"] = roofline["achieved"] / roofline["peak"]
+    latency = {"us_per_step": 1e3 * t_ar_ms / L, "x_realtime_kernel_only": (L / (t_ar_ms * 1e-3)) / SR,
+               "target_us_per_step": 1.25}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": t_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wname, "batch_per_gpu": B, "code_frames": Tc, "samples_per_utterance": L,
+                   "weights": "random init seed 13", "timing": "CUDA events per step, L2 flushed (256 MiB write) between steps",
+                   "parallelism": f"utterances sharded over {world} GPU(s), NCCL gather of waveforms"},
+        "x_realtime": value / SR, "x_realtime_per_utterance": value / SR / (B * world),
+        "e2e": {"value": e2e_value, "unit": "samples/s", "x_realtime": e2e_value / SR,
+                "h2d_bytes_per_step": int(codes.numel() * 8 + spk.numel() * 8), "d2h_bytes_per_step": int(B * L * 4),
+                "ms_per_step": t_e2e_ms / args.steps},
+        "gpu_launches": int(launches), "roofline": roofline, "latency": latency, "clocks": clocks,
+    }
+
+    # ---- the other BASELINE configs, measured in the same run on rank 0's GPU (N = 1 only)
+    if not args.no_extra and world == 1:
+        extra = {}
+        # configs[1]: VQ lookup microbench, 512x64 codebook, 1 M frames (HBM-bound: 520 B/frame algorithmic)
+        for kind in ("init", "trained"):
+            x, cb = fixtures.vq_inputs(1_000_000, kind=kind, seed=1234)
+            vq = VQEmbeddingEMA(512, 64)
+            vq.embedding.copy_(cb)
+            vq = vq.to(dev)
+            xd = x.to(dev)
+            ms = timed(lambda: vq.encode(xd), 5, 3) / 5
+            extra[f"vq_lookup_1M_{kind}"] = {"frames_per_s": 1e6 / (ms * 1e-3), "ms": ms,
+                                            "roofline": {"bound": "hbm", "achieved": 520e6 / (ms * 1e-3) / 1e9,
+                                                         "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                                         "frac": 520e6 / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"]}}
+            del xd
+        # configs[0]: Encoder.encode on one 2 s utterance (latency), C = 768 and 512
+        for Cc in (768, 512):
+            sd = fixtures.encoder_init_state(Cc, seed=13)
+            enc = Encoder(ConfEncoder(channels=Cc))
+            enc.load_state_dict(sd)
+            enc = enc.to(dev).eval()
+            mel = fixtures.synthetic_mel(1, 200, seed=0).to(dev)
+            with torch.no_grad():
+                ms = timed(lambda: enc.encode(mel), 20, 3) / 20
+            extra[f"encode_1utt_2s_c{Cc}"] = {"ms": ms, "frames_per_s": 100 / (ms * 1e-3)}
+            if Cc == 768:
+                # configs[3] (per-GPU share at 8 GPUs = 512 utterances x 3 s): batched encode throughput
+                melb = fixtures.synthetic_mel(512, 300, seed=0).to(dev)
+                with torch.no_grad():
+                    ms = timed(lambda: enc.encode(melb), 3, 3) / 3
+                frames = 512 * 150
+                extra["encode_batch_512x3s_c768"] = {"ms": ms, "frames_per_s": frames / (ms * 1e-3),
+                                                     "tflops_fp32": frames * 6.029e6 / (ms * 1e-3) / 1e12}
+                del melb
+        line["extra"] = extra
+
+    # ---- CPU baseline (rank 0, N = 1): the restated reference loop on the host cores, bounded sample
+    if rank == 0 and world == 1 and not args.no_cpu:
+        n_ar = 1500
+        sps, dt = cpu_generate_sample(n_ar, warm=100)
+        line["cpu_baseline"] = {"value": sps, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
+                                "x_realtime": sps / SR,
+                                "sample": f"{n_ar} AR steps (after 100 warm-up) of the B=1 generate loop, oracle/vocoder.py"}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -31,6 +31,8 @@ extern "C" {
 
 const char* vqcpc_last_error(void);
 int vqcpc_abi_version(void);
+/* Number of kernels this library has launched in the calling process so far (diagnostic counter). */
+uint64_t vqcpc_launch_count(void);
 /* 0 iff `device` is compute capability 10.x with >= 128 SMs (what the persistent kernels need). */
 int vqcpc_device_check(int device);
 
@@ -133,6 +135,11 @@ int vqcpc_vocoder_generate(const vqcpc_vocoder_weights* w, const float* G, const
 int vqcpc_vocoder_logits_tf(const vqcpc_vocoder_weights* w, const float* G, const int64_t* x_in,
                             int32_t B, int32_t T2, int32_t L, void* workspace, size_t workspace_bytes,
                             float* out_logits, void* stream);
+/* Diagnostics: while device_buf is non-NULL, sample-loop launches record 8 clock64() phase timestamps per step of
+ * CTA `cta` for steps [first_step, first_step + n_steps) into device_buf[n_steps][8] (see profiles/). */
+int vqcpc_debug_set_ar_trace(long long* device_buf, int32_t cta, int32_t first_step, int32_t n_steps);
+/* Tuning: cycles between the two in-flight poll rounds of the sample loop's exchanges (default 350). */
+int vqcpc_debug_set_ar_poll_gap(int32_t cycles);
 /* Reads (and clears) the device-side status word of the persistent kernels in `workspace` after the stream
  * has been synchronised by the caller: 0 ok, VQCPC_ERR_TIMEOUT if an exchange timed out. */
 int vqcpc_check_status(void* workspace, void* stream);

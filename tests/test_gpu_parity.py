@@ -294,6 +294,25 @@ def test_vocoder_generate_full_second_properties():
     assert torch.equal(short, a[:, :100])
 
 
+def test_vocoder_batched_generate_equals_single_utterance_runs():
+    """B = 7 -> interleaved groups of 4 + 2 + 1 inside the persistent kernel: every utterance must reproduce its own
+    single-utterance run bit for bit (same uniforms), in generate and in teacher-forced mode."""
+    voc, sd = make_vocoder()
+    B, Tc, L = 7, 2, 300
+    codes, spk, u = fixtures.vocoder_inputs(B, Tc, seed=4, n_steps=L)
+    cd, sdv, ud = codes.to(dev()), spk.to(dev()), u.to(dev())
+    wav, x = voc.generate(cd, sdv, uniforms=ud, n_steps=L, return_mulaw=True)
+    for b in (0, 3, 4, 6):
+        w1, x1 = voc.generate(cd[b:b + 1], sdv[b:b + 1], uniforms=ud[b:b + 1], n_steps=L, return_mulaw=True)
+        assert torch.equal(x1[0], x[b]) and torch.equal(w1[0], wav[b]), b
+    x_in = torch.cat([torch.full((B, 1), 128, dtype=torch.int64, device=dev()), x[:, :-1]], dim=1)
+    tf = voc.forward(x_in, cd, sdv)
+    ref = ovoc.forward_teacher_forced(sd, x_in[:2].cpu(), codes[:2], spk[:2])
+    assert float((tf[:2].cpu() - ref).abs().max()) < ATOL_LOGITS
+    tf1 = voc.forward(x_in[5:6], cd[5:6], sdv[5:6])
+    assert torch.equal(tf1[0], tf[5])
+
+
 def test_vocoder_argument_errors():
     voc, _ = make_vocoder()
     z = torch.zeros(1, 2, dtype=torch.int64, device=dev())

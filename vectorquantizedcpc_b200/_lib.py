@@ -46,6 +46,7 @@ _vp, _i32, _i64, _sz = C.c_void_p, C.c_int32, C.c_int64, C.c_size_t
 SIGNATURES = {
     "vqcpc_last_error": (C.c_char_p, []),
     "vqcpc_abi_version": (C.c_int, []),
+    "vqcpc_launch_count": (C.c_uint64, []),
     "vqcpc_device_check": (C.c_int, [C.c_int]),
     "vqcpc_linear_f32": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _i64, _i32, _i32, _vp]),
     "vqcpc_layernorm_relu_f32": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _vp]),
@@ -60,6 +61,8 @@ SIGNATURES = {
     "vqcpc_vocoder_generate": (C.c_int, [C.POINTER(VocoderWeights), _vp, _vp, _i32, _i32, _i32, _vp, _sz, _vp, _vp, _vp, _vp]),
     "vqcpc_vocoder_logits_tf": (C.c_int, [C.POINTER(VocoderWeights), _vp, _vp, _i32, _i32, _i32, _vp, _sz, _vp, _vp]),
     "vqcpc_check_status": (C.c_int, [_vp, _vp]),
+    "vqcpc_debug_set_ar_trace": (C.c_int, [_vp, _i32, _i32, _i32]),
+    "vqcpc_debug_set_ar_poll_gap": (C.c_int, [_i32]),
 }
 
 _lib = None

@@ -8,6 +8,9 @@
 namespace vqcpc {
 
 static thread_local char g_error[1024] = "";
+static unsigned long long g_launches = 0;   // kernels launched by this library (diagnostic, not thread-safe-exact)
+
+void count_launch(int n) { g_launches += static_cast<unsigned long long>(n); }
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -37,6 +40,7 @@ int device_cc_major() {
 
 extern "C" const char* vqcpc_last_error(void) { return vqcpc::g_error; }
 extern "C" int vqcpc_abi_version(void) { return VQCPC_ABI_VERSION; }
+extern "C" uint64_t vqcpc_launch_count(void) { return vqcpc::g_launches; }
 
 extern "C" int vqcpc_device_check(int device) {
     int n = 0;

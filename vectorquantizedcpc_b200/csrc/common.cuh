@@ -47,8 +47,10 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 
 // sigmoid / tanh from ex2.approx: abs error ~1e-7, saturate correctly for large |x|.
-__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
-__device__ __forceinline__ float tanh_fast(float x) { return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * x)); }
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, __fadd_rn(1.0f, __expf(-x))); }
+__device__ __forceinline__ float tanh_fast(float x) {
+    return __fsub_rn(1.0f, __fdividef(2.0f, __fadd_rn(1.0f, __expf(__fmul_rn(2.0f, x)))));
+}
 
 // Named barriers (ids 1..15; 0 is __syncthreads).  arrive = producer side, sync = consumer side.
 __device__ __forceinline__ void bar_sync(int id, int nthreads) {

@@ -59,6 +59,7 @@ int layernorm_relu(float* x, const float* w, const float* b, int64_t rows, int C
 #undef LN_CASE
     }
     VQ_CUDA(cudaGetLastError());
+    count_launch(1);
     return VQCPC_OK;
 }
 
@@ -206,6 +207,7 @@ int vq_lookup(const float* x, const float* codebook, int64_t n, int n_codes, int
     const unsigned grid = static_cast<unsigned>(n_tiles < sms ? n_tiles : sms);
     vq_lookup_kernel<<<grid, 256, VQ_SMEM, stream>>>(x, codebook, n, q, idx);
     VQ_CUDA(cudaGetLastError());
+    count_launch(1);
     return VQCPC_OK;
 }
 
@@ -380,6 +382,7 @@ static int lstm_launch(LstmParams prm, void* ll_mem, cudaStream_t stream) {
     void* args[] = {&prm};
     VQ_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(lstm_kernel<NB>), dim3(n_groups * LSTM_GROUP),
                                         dim3(256), args, 0, stream));
+    count_launch(1);
     return VQCPC_OK;
 }
 

@@ -168,6 +168,7 @@ static int launch_gemm(ALoader a, const float* W, int64_t ldw, const float* bias
         sgemm_tn_kernel<1, 1, ALoader><<<grid, 256, 0, stream>>>(a, W, ldw, bias, C, ldc, M, N, K);
     }
     VQ_CUDA(cudaGetLastError());
+    count_launch(1);
     return VQCPC_OK;
 }
 

@@ -21,6 +21,7 @@ struct WorkspaceHeader {
     int reserved[63];
 };
 
+void count_launch(int n);
 int device_sm_count();
 int device_cc_major();
 

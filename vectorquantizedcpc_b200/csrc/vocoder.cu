@@ -20,7 +20,6 @@ constexpr int AR_COND = 256;         // dim_voc_latent
 constexpr int AR_CTAS = 128;         // persistent grid: one CTA per SM on 128 SMs
 constexpr int AR_U = AR_H / AR_CTAS; // 7 hidden units per CTA
 constexpr int AR_R = AR_FC / AR_CTAS;  // 2 fc1 rows and 2 fc2 rows per CTA
-constexpr int AR_THREADS = 32 * (1 + AR_U);   // warp 0 = chain warp, warps 1..7 = W_hh warps
 constexpr int X_INIT = 128;
 
 // ------------------------------------------------------------------------------------------------
@@ -104,16 +103,39 @@ bigru_layer_kernel(const float* __restrict__ xproj, const float* __restrict__ w_
 //   b_t   = W_hh h_{t-1} + b_hh
 //   r = s(a_r + b_r) ; z = s(a_z + b_z) ; n = tanh(a_n + r b_n) ; h_t = (1-z) n + z h_{t-1}
 //   o_t   = fc2(relu(fc1 h_t))  ;  x_t = min{k : cumsum(exp(o - max))_k > u_t * S}
-// Grid: 128 CTAs x 256 threads, cooperative (all co-resident).  CTA j owns hidden units 7j..7j+6 (their 21
-// W_hh rows in the registers of warps 1..7, one unit per warp, 28 columns per lane), fc1 rows 2j,2j+1 and
-// fc2 rows 2j,2j+1 (registers of warp 0), and the 21 matching columns of E' (21.5 KB shared memory).
-// Warp 0 ("chain warp") runs the sequential dependency chain of a step alone:
-//   gates -> publish h_t -> poll all 896 h -> fc1 rows -> publish -> poll 256 -> fc2 rows -> publish ->
-//   poll 256 logits -> softmax + inverse-CDF sample (every CTA redundantly: bit-identical) -> next gates.
-// It hands h_t to warps 1..7 through shared memory (named barrier 1); they compute W_hh h_t + b_hh for the
-// NEXT step off the critical path and hand the 21 sums back (named barrier 2).
-// Teacher-forced mode (Vocoder.forward): x_{t-1} comes from x_in, logits are written out, no third exchange.
+// Grid: 128 CTAs x 224 threads, cooperative (all co-resident), ONE launch per group of <= NB utterances.
+// CTA j owns hidden units 7j..7j+6 (their 21 W_hh rows in the registers of warps 3..6, a column quarter each,
+// 7 columns per lane), fc1 rows 2j,2j+1, fc2 rows 2j,2j+1 and the 21 matching columns of E' (21.5 KB smem).
+// A step is three all-to-all LL exchanges (h_t, relu(fc1 h_t), logits).  What B200 measures for them
+// (profiles/r01_ll_microbench_*.txt): reading a line another SM has just written costs ~750 cycles one way;
+// a 128-way exchange costs ~2050 cycles when every producer owns its own 64/128-byte slot and 3600-6400 when
+// producers share lines; replicating the buffers does not help; > 32 outstanding strong stores per publish
+// serialise at ~21 cycles each; weak (.cg) loads never observe remote stores.  Hence:
+//   * every producer owns a padded slot (h: 64 B, r / o: one 128 B line), one copy, <= 8 stores per publish;
+//   * three ROLE warps, each polling one buffer and publishing the next one, chained by shared-memory flags:
+//       warp 0 "H": poll h_t -> hand h_t to the W_hh warps (smem, named barrier) -> fc1 rows -> publish r_t
+//       warp 1 "R": poll r_t -> fc2 rows -> publish o_t          (teacher-forced mode: write logits instead)
+//       warp 2 "O": poll o_{t-1} -> softmax + inverse-CDF sample x_{t-1} (every CTA redundantly, bit-identical)
+//                   -> GRU gates of step t (needs W_hh h_{t-1} from warps 3..6) -> publish h_t
+//   * the per-utterance latency is exchange-bound, so a launch interleaves NB utterances: every role walks
+//     the utterances round-robin and works on one while the others' exchanges are in flight.
 // ------------------------------------------------------------------------------------------------
+constexpr int AR_ROLE_WARPS = 3;
+constexpr int AR_HH_WARPS = 4;                            // each takes 224 of the 896 columns of the CTA's 21 W_hh rows
+constexpr int AR_THREADS = 32 * (AR_ROLE_WARPS + AR_HH_WARPS);   // 224 (register file is allotted per 128 threads:
+                                                                  // 256 threads -> up to 255 registers each)
+constexpr int AR_HH_THREADS = 32 * AR_HH_WARPS;           // 128
+constexpr int AR_BAR_COUNT = AR_HH_THREADS + 32;          // W_hh warps + one role warp
+constexpr int AR_NROW = AR_U * 3;                         // 21 W_hh rows per CTA
+constexpr int AR_HSLOT = 8;                               // words per producer in the h exchange (7 + 1 pad = 64 B)
+constexpr int AR_RSLOT = 16;                              // words per producer in the r / o exchanges (own 128 B line)
+constexpr int AR_HPAD = AR_CTAS * AR_HSLOT;               // 1024: padded length of h (column c*8 + w <-> unit 7c + w)
+constexpr int AR_NB_MAX = 4;                              // utterances interleaved per launch
+constexpr size_t AR_LL_H = 2 * AR_HPAD;                   // LL words per utterance: h [2][128][8]
+constexpr size_t AR_LL_R = 2 * AR_CTAS * AR_RSLOT;        //                          r, o [2][128][16]
+constexpr size_t AR_LL_PER_UTT = AR_LL_H + 2 * AR_LL_R;
+constexpr size_t AR_LL_WORDS = AR_NB_MAX * AR_LL_PER_UTT;
+
 struct ArParams {
     const float* w_hh;      // (2688, 896)
     const float* b_hh;      // (2688,)
@@ -122,221 +144,376 @@ struct ArParams {
     const float* fc2_w;     // (256, 256)
     const float* fc2_b;
     const float* eprime;    // (256, 2688)
-    const float* G;         // (T2, 2688) for this utterance
-    const float* uniforms;  // (L,)   generate mode
-    const int64_t* x_in;    // (L,)   teacher-forced mode (nullptr in generate mode)
     const float* lut;       // (256,)
+    // per-utterance arrays of this launch's group: utterance nb lives at base + nb * stride
+    const float* G;         // (T2, 2688)           stride g_stride
+    const float* uniforms;  // (L,)   generate mode  stride L
+    const int64_t* x_in;    // (L,)   teacher-forced mode (nullptr in generate mode), stride L
     float* out_wav;         // (L,) or null
     int32_t* out_codes;     // (L,) or null
     float* out_logits;      // (L, 256) or null
-    ll_word* ll_h;          // [2][896]
-    ll_word* ll_r;          // [2][256]
-    ll_word* ll_o;          // [2][256]
+    ll_word* ll;            // [nb][ h: 2*1024 | r: 2*128*16 | o: 2*128*16 ]
     int* status;
-    int L, upsample;
+    long long* trace;       // optional phase timestamps (debug): [trace_n][8] clock64 values of CTA trace_cta, utterance 0
+    int trace_cta, trace_t0, trace_n;
+    long long g_stride;
+    int L, upsample, nb_active;
+    int poll_delay, poll_backoff;   // cycles before the first poll round / between failed rounds
 };
 
-constexpr int AR_LL_WORDS = 2 * AR_H + 2 * AR_FC + 2 * AR_Q;
-
-// poll `N2` 16-byte pairs (2 slots each) starting at `base + 2*first_pair`, stride `pair_stride` pairs
+// Poll N2 16-byte pairs (lane reads pairs at base + 2*k*pair_stride) until every word carries `tag`.
+// The first round is issued `first_delay` cycles after the call, failed rounds are retried after `backoff`.
 template <int N2>
-__device__ __forceinline__ bool ll_poll_pairs(const ll_word* base, int pair_stride, uint32_t tag, float* out) {
+__device__ __forceinline__ bool ll_poll(const ll_word* base, int pair_stride, uint32_t tag, float* out,
+                                        int first_delay, int backoff, volatile int* abort_flag) {
+    ll_word a0[N2], b0[N2];
     const long long t0 = clock64();
+    if (first_delay) while (clock64() - t0 < first_delay) {}
     for (;;) {
-        ll_word a[N2], b[N2];
 #pragma unroll
-        for (int k = 0; k < N2; ++k) ll_load2(base + 2 * k * pair_stride, a[k], b[k]);
+        for (int k = 0; k < N2; ++k) ll_load2(base + 2 * k * pair_stride, a0[k], b0[k]);
         bool ok = true;
 #pragma unroll
-        for (int k = 0; k < N2; ++k) {
-            ok = ok && (ll_tag(a[k]) == tag) && (ll_tag(b[k]) == tag);
-            out[2 * k] = ll_val(a[k]);
-            out[2 * k + 1] = ll_val(b[k]);
+        for (int k = 0; k < N2; ++k) ok = ok && (ll_tag(a0[k]) == tag) && (ll_tag(b0[k]) == tag);
+        if (__all_sync(0xffffffffu, ok)) {
+#pragma unroll
+            for (int k = 0; k < N2; ++k) { out[2 * k] = ll_val(a0[k]); out[2 * k + 1] = ll_val(b0[k]); }
+            return true;
         }
-        if (__all_sync(0xffffffffu, ok)) return true;
-        if (clock64() - t0 > LL_TIMEOUT_CYCLES) return false;
+        if (*abort_flag || clock64() - t0 > LL_TIMEOUT_CYCLES) return false;
+        if (backoff) { const long long t1 = clock64(); while (clock64() - t1 < backoff) {} }
     }
 }
 
+// wait until a shared-memory sequence flag reaches `want` (set by another role warp of this CTA)
+__device__ __forceinline__ bool wait_seq(volatile int* flag, int want, volatile int* abort_flag) {
+    const long long t0 = clock64();
+    while (*flag < want) {
+        if (*abort_flag || clock64() - t0 > LL_TIMEOUT_CYCLES) return false;
+    }
+    return true;
+}
+
+template <int NB>
 __global__ void __launch_bounds__(AR_THREADS, 1) ar_kernel(ArParams p) {
-    __shared__ __align__(16) float hs[2][AR_H];
-    __shared__ float hhres[2][AR_U * 3 + 3];
-    __shared__ float Es[AR_Q * AR_U * 3];
+    extern __shared__ __align__(16) float ar_dyn_smem[];
+    float (*hs)[2][AR_HPAD] = reinterpret_cast<float (*)[2][AR_HPAD]>(ar_dyn_smem);   // [NB][2][1024]
+    __shared__ float hhpart[NB][2][AR_HH_WARPS][AR_NROW + 3];   // per-warp partial sums of W_hh h_t (column quarters)
+    __shared__ float Es[AR_Q * AR_NROW];
     __shared__ volatile int abort_flag;
+    __shared__ volatile int seq_h[NB], seq_r[NB], seq_o[NB];    // steps whose h / r / o this CTA has published
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int cta = blockIdx.x;
-    const int L = p.L;
+    const int L = p.L, nba = p.nb_active;
 
-    for (int i = tid; i < AR_Q * AR_U * 3; i += AR_THREADS) {
-        const int x = i / (AR_U * 3), j = i % (AR_U * 3), u = j / 3, g = j % 3;
+    for (int i = tid; i < AR_Q * AR_NROW; i += AR_THREADS) {
+        const int x = i / AR_NROW, j = i % AR_NROW, u = j / 3, g = j % 3;
         Es[i] = __ldg(p.eprime + static_cast<int64_t>(x) * AR_G + g * AR_H + cta * AR_U + u);
     }
-    if (tid < AR_U * 3) {
-        const int u = tid / 3, g = tid % 3;
-        hhres[1][tid] = __ldg(p.b_hh + g * AR_H + cta * AR_U + u);   // W_hh h_{-1} + b_hh with h_{-1} = 0
+    for (int i = tid; i < NB * AR_HH_WARPS * (AR_NROW + 3); i += AR_THREADS) {
+        const int nb = i / (AR_HH_WARPS * (AR_NROW + 3)), rest = i % (AR_HH_WARPS * (AR_NROW + 3));
+        hhpart[nb][1][rest / (AR_NROW + 3)][rest % (AR_NROW + 3)] = 0.f;   // W_hh h_{-1} with h_{-1} = 0
     }
+    if (tid < NB) { seq_h[tid] = 0; seq_r[tid] = 0; seq_o[tid] = 0; }
     if (tid == 0) abort_flag = 0;
     __syncthreads();
 
-    if (warp > 0) {
+    const bool teacher = (p.x_in != nullptr);
+    const bool tracing = (p.trace != nullptr) && (cta == p.trace_cta) && (lane == 0);
+#define AR_TRACE(k, tt)                                                                              \
+    if (tracing && nb == 0 && (tt) >= p.trace_t0 && (tt) < p.trace_t0 + p.trace_n) p.trace[((tt) - p.trace_t0) * 8 + (k)] = clock64();
+#define AR_FAIL()                                                          \
+    do {                                                                   \
+        abort_flag = 1;                                                    \
+        if (lane == 0) atomicExch(p.status, VQCPC_ERR_TIMEOUT);            \
+        __threadfence_block();                                             \
+    } while (0)
+
+    if (warp >= AR_ROLE_WARPS) {
         // ----------------------------------------------------------------- W_hh warps (off the critical path)
-        const int u = warp - 1, gu = cta * AR_U + u;
-        float w[3][28];
-        float bias[3];
+        // warp q holds columns {224q + 32k + lane : k < 7} of all 21 rows (unit u, gate g -> row index 3u + g)
+        const int q = warp - AR_ROLE_WARPS;
+        float w[AR_NROW][7];
+        int poff[7];
 #pragma unroll
-        for (int g = 0; g < 3; ++g) {
-            const float* row = p.w_hh + static_cast<int64_t>(g * AR_H + gu) * AR_H;
-#pragma unroll
-            for (int k = 0; k < 7; ++k) {
-                const float4 v = __ldg(reinterpret_cast<const float4*>(row + 128 * k) + lane);
-                w[g][4 * k] = v.x; w[g][4 * k + 1] = v.y; w[g][4 * k + 2] = v.z; w[g][4 * k + 3] = v.w;
-            }
-            bias[g] = __ldg(p.b_hh + g * AR_H + gu);
+        for (int k = 0; k < 7; ++k) {
+            const int col = 224 * q + 32 * k + lane;
+            poff[k] = (col / AR_U) * AR_HSLOT + col % AR_U;
         }
-        for (int t = 0; t < L; ++t) {
-            bar_sync(1, AR_THREADS);                  // h_t is in hs[t&1]
-            if (abort_flag) break;
-            const float* h = hs[t & 1];
-            float a0 = 0.f, a1 = 0.f, a2 = 0.f;
 #pragma unroll
-            for (int k = 0; k < 7; ++k) {
-                const float4 hv = *reinterpret_cast<const float4*>(&h[128 * k + 4 * lane]);
-                a0 = fmaf(w[0][4 * k], hv.x, a0); a0 = fmaf(w[0][4 * k + 1], hv.y, a0);
-                a0 = fmaf(w[0][4 * k + 2], hv.z, a0); a0 = fmaf(w[0][4 * k + 3], hv.w, a0);
-                a1 = fmaf(w[1][4 * k], hv.x, a1); a1 = fmaf(w[1][4 * k + 1], hv.y, a1);
-                a1 = fmaf(w[1][4 * k + 2], hv.z, a1); a1 = fmaf(w[1][4 * k + 3], hv.w, a1);
-                a2 = fmaf(w[2][4 * k], hv.x, a2); a2 = fmaf(w[2][4 * k + 1], hv.y, a2);
-                a2 = fmaf(w[2][4 * k + 2], hv.z, a2); a2 = fmaf(w[2][4 * k + 3], hv.w, a2);
+        for (int r = 0; r < AR_NROW; ++r) {
+            const int u = r / 3, g = r % 3;
+            const float* row = p.w_hh + static_cast<int64_t>(g * AR_H + cta * AR_U + u) * AR_H + 224 * q + lane;
+#pragma unroll
+            for (int k = 0; k < 7; ++k) w[r][k] = __ldg(row + 32 * k);
+        }
+        bool dead = false;
+        for (int t = 0; t < L && !dead; ++t) {
+#pragma unroll
+            for (int nb = 0; nb < NB; ++nb) {
+                if (nb >= nba || dead) continue;
+                bar_sync(1 + 2 * nb, AR_BAR_COUNT);       // h_t[nb] is in hs[nb][t&1]
+                if (abort_flag) { dead = true; continue; }
+                const float* h = hs[nb][t & 1];
+                float hv[7];
+#pragma unroll
+                for (int k = 0; k < 7; ++k) hv[k] = h[poff[k]];
+                float acc[AR_NROW];
+#pragma unroll
+                for (int r = 0; r < AR_NROW; ++r) {
+                    float a = __fmul_rn(w[r][0], hv[0]);
+#pragma unroll
+                    for (int k = 1; k < 7; ++k) a = __fmaf_rn(w[r][k], hv[k], a);
+                    acc[r] = a;
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                    for (int r = 0; r < AR_NROW; ++r) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], o);
+                }
+                float mine = acc[0];
+#pragma unroll
+                for (int r = 1; r < AR_NROW; ++r) mine = (lane == r) ? acc[r] : mine;
+                if (lane < AR_NROW) hhpart[nb][t & 1][q][lane] = mine;
+                bar_arrive(2 + 2 * nb, AR_BAR_COUNT);
             }
-            a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2);
-            if (lane < 3) hhres[t & 1][u * 3 + lane] = (lane == 0 ? a0 : (lane == 1 ? a1 : a2)) + bias[lane];
-            bar_arrive(2, AR_THREADS);
+        }
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb) bar_arrive(2 + 2 * nb, AR_BAR_COUNT);   // on abort: never leave role O waiting
+        return;
+    }
+
+    if (warp == 0) {
+        // ----------------------------------------------------------------- role H: h_t -> fc1 rows -> r_t
+        // pair k of lane l = words {64k + 2l, 64k + 2l + 1} of the padded h vector: producer c = 8k + l/4,
+        // units 7c + 2(l%4) + {0,1} (the second one of l%4 == 3 is the pad word).
+        float w1[AR_R][32], b1[AR_R];
+#pragma unroll
+        for (int r = 0; r < AR_R; ++r) {
+            const float* row = p.fc1_w + static_cast<int64_t>(cta * AR_R + r) * AR_H;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                const int c = 8 * k + (lane >> 2), wd = 2 * (lane & 3);
+                w1[r][2 * k] = __ldg(row + AR_U * c + wd);
+                w1[r][2 * k + 1] = (wd + 1 < AR_U) ? __ldg(row + AR_U * c + wd + 1) : 0.f;
+            }
+            b1[r] = __ldg(p.fc1_b + cta * AR_R + r);
+        }
+        bool dead = false;
+        for (int t = 0; t < L && !dead; ++t) {
+            const uint32_t tag = static_cast<uint32_t>(t) + 1u;
+            const int par = t & 1;
+#pragma unroll
+            for (int nb = 0; nb < NB; ++nb) {
+                if (nb >= nba || dead) continue;
+                ll_word* llb = p.ll + nb * AR_LL_PER_UTT;
+                if (!wait_seq(&seq_h[nb], t + 1, &abort_flag)) { AR_FAIL(); dead = true; continue; }
+                AR_TRACE(1, t)
+                float hv[32];
+                if (!ll_poll<16>(llb + par * AR_HPAD + 2 * lane, 32, tag, hv, p.poll_delay, p.poll_backoff, &abort_flag)) {
+                    AR_FAIL(); dead = true; continue;
+                }
+                AR_TRACE(2, t)
+#pragma unroll
+                for (int k = 0; k < 16; ++k)
+                    *reinterpret_cast<float2*>(&hs[nb][par][64 * k + 2 * lane]) = make_float2(hv[2 * k], hv[2 * k + 1]);
+                bar_arrive(1 + 2 * nb, AR_BAR_COUNT);     // W_hh warps may start on h_t[nb]
+                float s0a = 0.f, s0b = 0.f, s1a = 0.f, s1b = 0.f;
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    s0a = fmaf(w1[0][2 * k], hv[2 * k], s0a); s0b = fmaf(w1[0][2 * k + 1], hv[2 * k + 1], s0b);
+                    s1a = fmaf(w1[1][2 * k], hv[2 * k], s1a); s1b = fmaf(w1[1][2 * k + 1], hv[2 * k + 1], s1b);
+                }
+                float s0 = s0a + s0b, s1 = s1a + s1b;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {       // two interleaved butterflies
+                    s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+                    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+                }
+                if (lane < AR_R) {
+                    const float v = fmaxf((lane ? s1 : s0) + (lane ? b1[1] : b1[0]), 0.f);
+                    ll_store(llb + AR_LL_H + (par * AR_CTAS + cta) * AR_RSLOT + lane, v, tag);
+                }
+                __syncwarp();
+                if (lane == 0) seq_r[nb] = t + 1;
+                AR_TRACE(3, t)
+            }
+        }
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb) bar_arrive(1 + 2 * nb, AR_BAR_COUNT);   // on abort: release the W_hh warps
+        return;
+    }
+
+    if (warp == 1) {
+        // ----------------------------------------------------------------- role R: r_t -> fc2 rows -> o_t
+        // pair k of lane l = the two r values of producer 32k + l: columns 2(32k + l) + {0,1}
+        float w2[AR_R][8], b2[AR_R];
+#pragma unroll
+        for (int r = 0; r < AR_R; ++r) {
+            const float* row = p.fc2_w + static_cast<int64_t>(cta * AR_R + r) * AR_FC;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float2 v = __ldg(reinterpret_cast<const float2*>(row + 64 * k) + lane);
+                w2[r][2 * k] = v.x; w2[r][2 * k + 1] = v.y;
+            }
+            b2[r] = __ldg(p.fc2_b + cta * AR_R + r);
+        }
+        bool dead = false;
+        for (int t = 0; t < L && !dead; ++t) {
+            const uint32_t tag = static_cast<uint32_t>(t) + 1u;
+            const int par = t & 1;
+#pragma unroll
+            for (int nb = 0; nb < NB; ++nb) {
+                if (nb >= nba || dead) continue;
+                ll_word* llb = p.ll + nb * AR_LL_PER_UTT;
+                if (!wait_seq(&seq_r[nb], t + 1, &abort_flag)) { AR_FAIL(); dead = true; continue; }
+                float rv[8];
+                if (!ll_poll<4>(llb + AR_LL_H + (par * AR_CTAS + lane) * AR_RSLOT, 32 * AR_RSLOT / 2, tag, rv, p.poll_delay,
+                                p.poll_backoff, &abort_flag)) {
+                    AR_FAIL(); dead = true; continue;
+                }
+                AR_TRACE(4, t)
+                float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { s0 = fmaf(w2[0][k], rv[k], s0); s1 = fmaf(w2[1][k], rv[k], s1); }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+                    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+                }
+                const float v = (lane & 1 ? s1 : s0) + (lane & 1 ? b2[1] : b2[0]);
+                if (p.out_logits != nullptr && lane < AR_R)
+                    p.out_logits[(static_cast<int64_t>(nb) * L + t) * AR_Q + cta * AR_R + lane] = v;
+                if (!teacher) {
+                    if (lane < AR_R) ll_store(llb + AR_LL_H + AR_LL_R + (par * AR_CTAS + cta) * AR_RSLOT + lane, v, tag);
+                    __syncwarp();
+                    if (lane == 0) seq_o[nb] = t + 1;
+                }
+                AR_TRACE(5, t)
+            }
         }
         return;
     }
 
-    // --------------------------------------------------------------------- chain warp
-    float w1[AR_R][28], w2[AR_R][8], b1[AR_R], b2[AR_R];
+    // --------------------------------------------------------------------- role O
+    // for t = 0..L:  [t > 0: poll o_{t-1} -> sample x_{t-1} -> output]  [t < L: gates_t -> publish h_t]
+    // lanes 0..6 <-> hidden units 7*cta + lane; lane 7 publishes the pad word.
+    const bool gate_lane = lane < AR_U;
+    const int gu = cta * AR_U + (gate_lane ? lane : 0);
+    float hown[NB], g_r[NB], g_z[NB], g_n[NB], u_next[NB];
+    int x[NB];
 #pragma unroll
-    for (int r = 0; r < AR_R; ++r) {
-        const int row = cta * AR_R + r;
-#pragma unroll
-        for (int k = 0; k < 14; ++k) {
-            const float2 v = __ldg(reinterpret_cast<const float2*>(p.fc1_w + static_cast<int64_t>(row) * AR_H + 64 * k) + lane);
-            w1[r][2 * k] = v.x; w1[r][2 * k + 1] = v.y;
-        }
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            const float4 v = __ldg(reinterpret_cast<const float4*>(p.fc2_w + static_cast<int64_t>(row) * AR_FC + 8 * lane) + k);
-            w2[r][4 * k] = v.x; w2[r][4 * k + 1] = v.y; w2[r][4 * k + 2] = v.z; w2[r][4 * k + 3] = v.w;
-        }
-        b1[r] = __ldg(p.fc1_b + row);
-        b2[r] = __ldg(p.fc2_b + row);
-    }
-    const bool teacher = (p.x_in != nullptr);
-    const int gu = cta * AR_U + (lane < AR_U ? lane : 0);
-    float hown = 0.f, g_r = 0.f, g_z = 0.f, g_n = 0.f;
-    int x = X_INIT;
-    bool failed = false;
-
-    for (int t = 0; t < L; ++t) {
-        const uint32_t tag = static_cast<uint32_t>(t) + 1u;
+    for (int nb = 0; nb < NB; ++nb) { hown[nb] = 0.f; g_r[nb] = g_z[nb] = g_n[nb] = 0.f; u_next[nb] = 0.f; x[nb] = X_INIT; }
+    const float bh_r = __ldg(p.b_hh + gu), bh_z = __ldg(p.b_hh + AR_H + gu), bh_n = __ldg(p.b_hh + 2 * AR_H + gu);
+    int frame_left = 0, frame = 0;
+    bool dead = false;
+    for (int t = 0; t <= L && !dead; ++t) {
         const int par = t & 1;
-        if (t % p.upsample == 0 && lane < AR_U) {
-            const float* g = p.G + static_cast<int64_t>(t / p.upsample) * AR_G + gu;
-            g_r = __ldg(g); g_z = __ldg(g + AR_H); g_n = __ldg(g + 2 * AR_H);
-        }
-        const float u_t = teacher ? 0.f : __ldg(p.uniforms + t);
-        if (teacher) x = static_cast<int>(__ldg(p.x_in + t)) & (AR_Q - 1);
-
-        // gates: lane u <-> hidden unit 7*cta + u
-        if (lane < AR_U) {
-            const float* e = &Es[x * (AR_U * 3) + lane * 3];
-            const float* hb = &hhres[par ^ 1][lane * 3];
-            const float r = sigmoid_fast(e[0] + g_r + hb[0]);
-            const float z = sigmoid_fast(e[1] + g_z + hb[1]);
-            const float n = tanh_fast(e[2] + g_n + r * hb[2]);
-            hown = (1.0f - z) * n + z * hown;
-            ll_store(p.ll_h + par * AR_H + gu, hown, tag);
-        }
-        // gather h_t: lane l takes columns {64k + 2l, 64k + 2l + 1}, k = 0..13 (512 B contiguous per warp load)
-        float hv[28];
-        if (!ll_poll_pairs<14>(p.ll_h + par * AR_H + 2 * lane, 32, tag, hv)) { failed = true; break; }
+        if (t < L) {
+            if (frame_left == 0) {
+                if (gate_lane) {
 #pragma unroll
-        for (int k = 0; k < 14; ++k)
-            *reinterpret_cast<float2*>(&hs[par][64 * k + 2 * lane]) = make_float2(hv[2 * k], hv[2 * k + 1]);
-        bar_arrive(1, AR_THREADS);                   // W_hh warps may start on h_t
-
-        // fc1 rows
-        float r1[AR_R];
-#pragma unroll
-        for (int r = 0; r < AR_R; ++r) {
-            float a = 0.f, b = 0.f;
-#pragma unroll
-            for (int k = 0; k < 14; ++k) { a = fmaf(w1[r][2 * k], hv[2 * k], a); b = fmaf(w1[r][2 * k + 1], hv[2 * k + 1], b); }
-            r1[r] = fmaxf(warp_sum(a + b) + b1[r], 0.f);
-        }
-        if (lane < AR_R) ll_store(p.ll_r + par * AR_FC + cta * AR_R + lane, lane == 0 ? r1[0] : r1[1], tag);
-        // gather relu(fc1): lane l takes columns 8l..8l+7
-        float rv[8];
-        if (!ll_poll_pairs<4>(p.ll_r + par * AR_FC + 8 * lane, 1, tag, rv)) { failed = true; break; }
-        float o2[AR_R];
-#pragma unroll
-        for (int r = 0; r < AR_R; ++r) {
-            float a = 0.f;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) a = fmaf(w2[r][k], rv[k], a);
-            o2[r] = warp_sum(a) + b2[r];
-        }
-        if (p.out_logits != nullptr && lane < AR_R)
-            p.out_logits[static_cast<int64_t>(t) * AR_Q + cta * AR_R + lane] = lane == 0 ? o2[0] : o2[1];
-
-        if (!teacher) {
-            if (lane < AR_R) ll_store(p.ll_o + par * AR_Q + cta * AR_R + lane, lane == 0 ? o2[0] : o2[1], tag);
-            float ov[8];
-            if (!ll_poll_pairs<4>(p.ll_o + par * AR_Q + 8 * lane, 1, tag, ov)) { failed = true; break; }
-            // softmax + inverse-CDF sample over classes in index order (lane l holds classes 8l..8l+7)
-            float m = ov[0];
-#pragma unroll
-            for (int k = 1; k < 8; ++k) m = fmaxf(m, ov[k]);
-            m = warp_max(m);
-            float c[8];
-            float run = 0.f;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) { run += __expf(ov[k] - m); c[k] = run; }
-            float incl = run;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const float v = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += v;
+                    for (int nb = 0; nb < NB; ++nb) {
+                        if (nb >= nba) continue;
+                        const float* g = p.G + nb * p.g_stride + static_cast<int64_t>(frame) * AR_G + gu;
+                        g_r[nb] = __ldg(g); g_z[nb] = __ldg(g + AR_H); g_n[nb] = __ldg(g + 2 * AR_H);
+                    }
+                }
+                frame_left = p.upsample; ++frame;
             }
-            const float excl = incl - run;
-            const float S = __shfl_sync(0xffffffffu, incl, 31);
-            const float thr = u_t * S;
-            int loc = 8;
+            --frame_left;
+        }
 #pragma unroll
-            for (int k = 7; k >= 0; --k) if (excl + c[k] > thr) loc = k;
-            const unsigned hit = __ballot_sync(0xffffffffu, loc < 8);
-            if (hit == 0u) x = AR_Q - 1;
-            else {
-                const int src = __ffs(hit) - 1;
-                x = 8 * src + __shfl_sync(0xffffffffu, loc, src);
+        for (int nb = 0; nb < NB; ++nb) {
+            if (nb >= nba || dead) continue;
+            ll_word* llb = p.ll + nb * AR_LL_PER_UTT;
+            AR_TRACE(0, t)
+            if (t > 0 && !teacher) {
+                // ---- sample x_{t-1}[nb] from o_{t-1}: lane l holds classes {64k + 2l + j : k < 4, j < 2}
+                const int tp = t - 1, ppar = tp & 1;
+                const float u_t = u_next[nb];
+                if (!wait_seq(&seq_o[nb], t, &abort_flag)) { AR_FAIL(); dead = true; continue; }
+                float ov[8];
+                if (!ll_poll<4>(llb + AR_LL_H + AR_LL_R + (ppar * AR_CTAS + lane) * AR_RSLOT, 32 * AR_RSLOT / 2,
+                                static_cast<uint32_t>(t), ov, p.poll_delay, p.poll_backoff, &abort_flag)) {
+                    AR_FAIL(); dead = true; continue;
+                }
+                AR_TRACE(6, tp)
+                float m = fmaxf(fmaxf(fmaxf(ov[0], ov[1]), fmaxf(ov[2], ov[3])), fmaxf(fmaxf(ov[4], ov[5]), fmaxf(ov[6], ov[7])));
+                m = warp_max(m);
+                float e0[4], e1[4], inc[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    e0[k] = __expf(ov[2 * k] - m); e1[k] = __expf(ov[2 * k + 1] - m);
+                    inc[k] = e0[k] + e1[k];
+                }
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {       // four interleaved inclusive scans over lanes
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const float v = __shfl_up_sync(0xffffffffu, inc[k], o);
+                        if (lane >= o) inc[k] += v;
+                    }
+                }
+                float pre[4];                             // sum of all classes below block k
+                float run = 0.f;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { pre[k] = run; run += __shfl_sync(0xffffffffu, inc[k], 31); }
+                const float thr = u_t * run;
+                int xs = AR_Q - 1;
+                bool found = false;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float c1 = pre[k] + inc[k];                 // cumulative sum through class 64k + 2l + 1
+                    const float c0 = pre[k] + (inc[k] - e1[k]);       //                 through class 64k + 2l
+                    const unsigned h1 = __ballot_sync(0xffffffffu, c1 > thr);
+                    const unsigned h0 = __ballot_sync(0xffffffffu, c0 > thr);
+                    if (!found && h1 != 0u) {
+                        const int src = __ffs(h1) - 1;
+                        xs = 64 * k + 2 * src + (((h0 >> src) & 1u) ? 0 : 1);
+                        found = true;
+                    }
+                }
+                x[nb] = xs;
+                if (cta == 0 && lane == 0) {
+                    if (p.out_wav) p.out_wav[static_cast<int64_t>(nb) * L + tp] = __ldg(p.lut + xs);
+                    if (p.out_codes) p.out_codes[static_cast<int64_t>(nb) * L + tp] = xs;
+                }
+                AR_TRACE(7, tp)
             }
-            if (cta == 0 && lane == 0) {
-                if (p.out_wav) p.out_wav[t] = __ldg(p.lut + x);
-                if (p.out_codes) p.out_codes[t] = x;
+            if (t < L) {
+                // ---- gates of step t for utterance nb
+                if (teacher) x[nb] = static_cast<int>(__ldg(p.x_in + static_cast<int64_t>(nb) * L + t)) & (AR_Q - 1);
+                if (t > 0) bar_sync(2 + 2 * nb, AR_BAR_COUNT);   // quarter sums of W_hh h_{t-1}[nb] are in hhpart[nb][par ^ 1]
+                if (abort_flag) { dead = true; continue; }
+                const uint32_t tag = static_cast<uint32_t>(t) + 1u;
+                float hnew = 0.f;
+                if (gate_lane) {
+                    const float* e = &Es[x[nb] * AR_NROW + lane * 3];
+                    const float* hp = &hhpart[nb][par ^ 1][0][lane * 3];
+                    constexpr int HS = AR_NROW + 3;
+                    const float hb_r = __fadd_rn(__fadd_rn(__fadd_rn(hp[0], hp[HS]), __fadd_rn(hp[2 * HS], hp[3 * HS])), bh_r);
+                    const float hb_z = __fadd_rn(__fadd_rn(__fadd_rn(hp[1], hp[HS + 1]), __fadd_rn(hp[2 * HS + 1], hp[3 * HS + 1])), bh_z);
+                    const float hb_n = __fadd_rn(__fadd_rn(__fadd_rn(hp[2], hp[HS + 2]), __fadd_rn(hp[2 * HS + 2], hp[3 * HS + 2])), bh_n);
+                    // explicit FMA forms: identical bits in every template instantiation / batch composition
+                    const float r = sigmoid_fast(__fadd_rn(__fadd_rn(e[0], g_r[nb]), hb_r));
+                    const float z = sigmoid_fast(__fadd_rn(__fadd_rn(e[1], g_z[nb]), hb_z));
+                    const float n = tanh_fast(__fmaf_rn(r, hb_n, __fadd_rn(e[2], g_n[nb])));
+                    hnew = __fmaf_rn(z, __fsub_rn(hown[nb], n), n);          // (1-z) n + z h
+                    hown[nb] = hnew;
+                }
+                if (lane < AR_HSLOT) ll_store(llb + par * AR_HPAD + cta * AR_HSLOT + lane, hnew, tag);
+                __syncwarp();
+                if (lane == 0) seq_h[nb] = t + 1;
+                if (!teacher) u_next[nb] = __ldg(p.uniforms + static_cast<int64_t>(nb) * L + t);   // consumed one step later
             }
         }
-        bar_sync(2, AR_THREADS);                     // W_hh h_t + b_hh is in hhres[par]
     }
-    if (failed) {
-        abort_flag = 1;
-        if (lane == 0) atomicExch(p.status, VQCPC_ERR_TIMEOUT);
-        __threadfence_block();
-        bar_arrive(1, AR_THREADS);                   // release the W_hh warps so the CTA can exit
-    }
+#undef AR_TRACE
+#undef AR_FAIL
 }
+
 
 // ------------------------------------------------------------------------------------------------ host
 // workspace layout: [header][u B*2Tc*128][xproj B*2Tc*768][p0 B*2Tc*256][p1 B*2Tc*256][ll words]
@@ -385,18 +562,41 @@ int vocoder_condition(const vqcpc_vocoder_weights* w, const int64_t* codes, cons
         embed_concat_kernel<<<grid, 256, 0, stream>>>(w->code_emb, w->spk_emb, codes, speaker, u, B, Tc, w->dim_code,
                                                       w->dim_speaker);
         VQ_CUDA(cudaGetLastError());
+        count_launch(1);
     }
     // layer 0
     if ((rc = gemm_dense(u, 128, w->pre_w_ih[0], 128, w->pre_b_ih[0], xproj, 768, rows, 768, 128, stream))) return rc;
     bigru_layer_kernel<<<dim3(2, B), PRE_G, 0, stream>>>(xproj, w->pre_w_hh[0], w->pre_b_hh[0], p0, T2);
     VQ_CUDA(cudaGetLastError());
+    count_launch(1);
     // layer 1 (input = [fwd;bwd] of layer 0)
     if ((rc = gemm_dense(p0, 256, w->pre_w_ih[1], 256, w->pre_b_ih[1], xproj, 768, rows, 768, 256, stream))) return rc;
     bigru_layer_kernel<<<dim3(2, B), PRE_G, 0, stream>>>(xproj, w->pre_w_hh[1], w->pre_b_hh[1], p1, T2);
     VQ_CUDA(cudaGetLastError());
+    count_launch(1);
     // hoisted conditioning half of the AR input projection: G = p . W_ih[:, 256:]^T + b_ih
     return gemm_dense(p1, 256, w->ar_w_ih + AR_EMB, AR_EMB + AR_COND, w->ar_b_ih, out_G, AR_G, rows, AR_G, AR_COND,
                       stream);
+}
+
+static int g_poll_gap = 400;     // bits 0..11: first-poll delay, bits 12..23: backoff (cycles); see vqcpc_debug_set_ar_poll_gap
+static int g_nb_cap = AR_NB_MAX;
+struct ArTrace { long long* buf; int cta, t0, n; };
+static ArTrace g_trace = {nullptr, 0, 0, 0};
+
+template <int NB>
+static int ar_launch(ArParams& p, cudaStream_t stream) {
+    void* args[] = {&p};
+    constexpr size_t dyn = sizeof(float) * NB * 2 * AR_HPAD;
+    static bool attr_set = false;
+    if (!attr_set) {
+        VQ_CUDA(cudaFuncSetAttribute(ar_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+        attr_set = true;
+    }
+    VQ_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(ar_kernel<NB>), dim3(AR_CTAS), dim3(AR_THREADS), args, dyn,
+                                        stream));
+    count_launch(1);
+    return VQCPC_OK;
 }
 
 static int ar_run(const vqcpc_vocoder_weights* w, const float* G, const float* uniforms, const int64_t* x_in, int B,
@@ -420,25 +620,32 @@ static int ar_run(const vqcpc_vocoder_weights* w, const float* G, const float* u
     WorkspaceHeader* hdr = reinterpret_cast<WorkspaceHeader*>(base);
     ll_word* ll = reinterpret_cast<ll_word*>(base + sizeof(WorkspaceHeader));
     VQ_CUDA(cudaMemsetAsync(hdr, 0, sizeof(WorkspaceHeader), stream));
-    for (int b = 0; b < B; ++b) {
-        VQ_CUDA(cudaMemsetAsync(ll, 0, sizeof(ll_word) * AR_LL_WORDS, stream));
+    // groups of up to NB utterances share one persistent launch (their steps are interleaved inside the kernel)
+    for (int b = 0; b < B;) {
+        int nb = B - b < g_nb_cap ? B - b : g_nb_cap;
+        VQ_CUDA(cudaMemsetAsync(ll, 0, sizeof(ll_word) * AR_LL_PER_UTT * nb, stream));
         ArParams p{};
         p.w_hh = w->ar_w_hh; p.b_hh = w->ar_b_hh;
         p.fc1_w = w->fc1_w; p.fc1_b = w->fc1_b; p.fc2_w = w->fc2_w; p.fc2_b = w->fc2_b;
         p.eprime = w->eprime;
+        p.lut = w->mulaw_lut;
         p.G = G + static_cast<int64_t>(b) * T2 * AR_G;
+        p.g_stride = static_cast<long long>(T2) * AR_G;
         p.uniforms = uniforms ? uniforms + static_cast<int64_t>(b) * L : nullptr;
         p.x_in = x_in ? x_in + static_cast<int64_t>(b) * L : nullptr;
-        p.lut = w->mulaw_lut;
         p.out_wav = out_wav ? out_wav + static_cast<int64_t>(b) * L : nullptr;
         p.out_codes = out_codes ? out_codes + static_cast<int64_t>(b) * L : nullptr;
         p.out_logits = out_logits ? out_logits + static_cast<int64_t>(b) * L * AR_Q : nullptr;
-        p.ll_h = ll; p.ll_r = ll + 2 * AR_H; p.ll_o = ll + 2 * AR_H + 2 * AR_FC;
+        p.ll = ll;
+        p.trace = g_trace.buf; p.trace_cta = g_trace.cta; p.trace_t0 = g_trace.t0; p.trace_n = g_trace.n;
         p.status = &hdr->status;
-        p.L = L; p.upsample = w->upsample_t;
-        void* args[] = {&p};
-        VQ_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(ar_kernel), dim3(AR_CTAS), dim3(AR_THREADS), args,
-                                            0, stream));
+        p.L = L; p.upsample = w->upsample_t; p.nb_active = nb;
+        p.poll_delay = g_poll_gap & 0xfff; p.poll_backoff = (g_poll_gap >> 12) & 0xfff;
+        if (nb == 1) rc = ar_launch<1>(p, stream);
+        else if (nb == 2) rc = ar_launch<2>(p, stream);
+        else rc = ar_launch<4>(p, stream);
+        if (rc) return rc;
+        b += nb;
     }
     return VQCPC_OK;
 }
@@ -446,6 +653,16 @@ static int ar_run(const vqcpc_vocoder_weights* w, const float* G, const float* u
 }  // namespace vqcpc
 
 // ------------------------------------------------------------------------------------------------ C ABI
+extern "C" int vqcpc_debug_set_ar_poll_gap(int32_t packed) {
+    vqcpc::g_poll_gap = packed < 0 ? 0 : (packed & 0xffffff);
+    const int cap = (packed >> 24) & 0xf;          // bits 24..27: cap on utterances per launch (0 = default)
+    vqcpc::g_nb_cap = (cap >= 1 && cap <= vqcpc::AR_NB_MAX) ? cap : vqcpc::AR_NB_MAX;
+    return VQCPC_OK;
+}
+extern "C" int vqcpc_debug_set_ar_trace(long long* device_buf, int32_t cta, int32_t first_step, int32_t n_steps) {
+    vqcpc::g_trace = vqcpc::ArTrace{device_buf, cta, first_step, n_steps};
+    return VQCPC_OK;
+}
 extern "C" int vqcpc_vocoder_pack(const vqcpc_vocoder_weights* w, float* eprime_out, void* stream) {
     return vqcpc::vocoder_pack(w, eprime_out, static_cast<cudaStream_t>(stream));
 }
