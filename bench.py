@@ -274,8 +274,17 @@ def main():
                 "note": "latency-bound persistent kernel: see latency.us_per_step vs the exchange floor (DESIGN.md)",
                 "peak_source": peaks["source"]}
     roofline["frac"] = roofline["achieved"] / roofline["peak"]
+    # latency floor of the role-warp design: three bare 128-way LL exchanges per step, measured live
+    fl_ws = torch.empty(1 << 17, dtype=torch.uint8, device=dev)
+    mean_cyc = C.c_double(0.0)
+    _lib.check(lib.vqcpc_debug_exchange_floor(_lib.ptr(fl_ws), fl_ws.numel(), 2000, C.byref(mean_cyc),
+                                              _lib.current_stream_ptr()), "exchange floor")
+    sm_mhz = float(clocks.get("sm_mhz") or 1965.0)      # median SM clock sampled during the timed region
+    floor_us = 3.0 * mean_cyc.value / sm_mhz
     latency = {"us_per_step": 1e3 * t_ar_ms / L, "x_realtime_kernel_only": (L / (t_ar_ms * 1e-3)) / SR,
-               "target_us_per_step": 1.25}
+               "target_us_per_step": 1.25, "exchange_cycles": mean_cyc.value, "sm_mhz_used": sm_mhz,
+               "floor_us_per_step": floor_us, "floor_frac": floor_us / (1e3 * t_ar_ms / L),
+               "note": "floor = 3 bare 128-way LL exchanges per step (h, relu(fc1 h), logits), no compute"}
 
     line = {
         "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
@@ -294,6 +303,14 @@ def main():
     # ---- the other BASELINE configs, measured in the same run on rank 0's GPU (N = 1 only)
     if not args.no_extra and world == 1:
         extra = {}
+        # interleaved-utterance throughput of the sample loop (B = 4: one launch; B = 16: four launches), 1 s each
+        for Bb in (4, 16):
+            cb, sb, _ = fixtures.vocoder_inputs(Bb, 50, seed=100 + Bb)
+            cbd, sbd = cb.to(dev), sb.to(dev)
+            with torch.no_grad():
+                ms = timed(lambda: voc.generate(cbd, sbd, generator=gen), 3, 3) / 3
+            extra[f"generate_b{Bb}_1s"] = {"ms": ms, "samples_per_s": Bb * 16000 / (ms * 1e-3),
+                                          "x_realtime_aggregate": Bb / (ms * 1e-3), "us_per_step": ms * 1e3 / 16000}
         # configs[1]: VQ lookup microbench, 512x64 codebook, 1 M frames (HBM-bound: 520 B/frame algorithmic)
         for kind in ("init", "trained"):
             x, cb = fixtures.vq_inputs(1_000_000, kind=kind, seed=1234)

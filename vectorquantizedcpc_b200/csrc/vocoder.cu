@@ -515,6 +515,32 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_kernel(ArParams p) {
 }
 
 
+// ------------------------------------------------------------------------------------------------
+// Exchange floor (diagnostic, used by bench.py): the bare 128-way all-to-all of the sample loop -- every CTA
+// publishes 2 LL words into its own 128-byte slot and polls all 128 slots -- with no compute in between.
+// Three of these per step are the latency floor of the role-warp design on this GPU.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32, 1) exchange_floor_kernel(ll_word* buf, int iters, long long* cycles) {
+    const int lane = threadIdx.x, cta = blockIdx.x;
+    const long long t0 = clock64();
+    for (int it = 1; it <= iters; ++it) {
+        const int par = it & 1;
+        if (lane < 2) ll_store(buf + (par * AR_CTAS + cta) * AR_RSLOT + lane, 0.f, static_cast<uint32_t>(it));
+        const long long ts = clock64();
+        for (;;) {
+            ll_word a[4], b[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) ll_load2(buf + (par * AR_CTAS + 32 * k + lane) * AR_RSLOT, a[k], b[k]);
+            bool ok = true;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) ok = ok && ll_tag(a[k]) == static_cast<uint32_t>(it) && ll_tag(b[k]) == static_cast<uint32_t>(it);
+            if (__all_sync(0xffffffffu, ok)) break;
+            if (clock64() - ts > LL_TIMEOUT_CYCLES) { if (lane == 0) cycles[cta] = -1; return; }
+        }
+    }
+    if (lane == 0) cycles[cta] = clock64() - t0;
+}
+
 // ------------------------------------------------------------------------------------------------ host
 // workspace layout: [header][u B*2Tc*128][xproj B*2Tc*768][p0 B*2Tc*256][p1 B*2Tc*256][ll words]
 static size_t vocoder_ws_bytes(int B, int Tc) {
@@ -653,6 +679,31 @@ static int ar_run(const vqcpc_vocoder_weights* w, const float* G, const float* u
 }  // namespace vqcpc
 
 // ------------------------------------------------------------------------------------------------ C ABI
+extern "C" int vqcpc_debug_exchange_floor(void* workspace, size_t workspace_bytes, int32_t iters, double* mean_cycles,
+                                          void* stream) {
+    using namespace vqcpc;
+    VQ_ARG(workspace && mean_cycles && iters > 0, "exchange_floor: bad arguments");
+    const size_t need = sizeof(ll_word) * AR_LL_R + sizeof(long long) * AR_CTAS;
+    VQ_ARG(workspace_bytes >= need, "exchange_floor: workspace too small");
+    if (device_sm_count() < AR_CTAS) { set_error("exchange_floor: needs %d SMs", AR_CTAS); return VQCPC_ERR_DEVICE; }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    ll_word* buf = static_cast<ll_word*>(workspace);
+    long long* cyc = reinterpret_cast<long long*>(buf + AR_LL_R);
+    VQ_CUDA(cudaMemsetAsync(workspace, 0, need, s));
+    void* args[] = {&buf, &iters, &cyc};
+    VQ_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(exchange_floor_kernel), dim3(AR_CTAS), dim3(32), args, 0, s));
+    count_launch(1);
+    long long host[AR_CTAS];
+    VQ_CUDA(cudaMemcpyAsync(host, cyc, sizeof(host), cudaMemcpyDeviceToHost, s));
+    VQ_CUDA(cudaStreamSynchronize(s));
+    double sum = 0;
+    for (int i = 0; i < AR_CTAS; ++i) {
+        if (host[i] < 0) { set_error("exchange_floor: timed out"); return VQCPC_ERR_TIMEOUT; }
+        sum += static_cast<double>(host[i]);
+    }
+    *mean_cycles = sum / AR_CTAS / iters;
+    return VQCPC_OK;
+}
 extern "C" int vqcpc_debug_set_ar_poll_gap(int32_t packed) {
     vqcpc::g_poll_gap = packed < 0 ? 0 : (packed & 0xffffff);
     const int cap = (packed >> 24) & 0xf;          // bits 24..27: cap on utterances per launch (0 = default)

@@ -1,0 +1,59 @@
+"""Utterance-level data parallelism: utterances are independent in every stage of the path
+(/root/reference/model.py:59-70, network_vocoder.py:69-78), so ranks take contiguous blocks of utterances,
+weights are replicated and the ONLY collective is one gather of the outputs.  One process per GPU
+(torchrun); backend nccl on GPUs, gloo for the CPU tests of this host logic."""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous block [lo, hi) of ``n`` utterances for ``rank``: ceil(n/world) per rank, trailing ranks may be short/empty."""
+    per = (n + world - 1) // world
+    lo = min(rank * per, n)
+    return lo, min(lo + per, n)
+
+
+def shard(t: torch.Tensor, rank: Optional[int] = None, world: Optional[int] = None) -> torch.Tensor:
+    """This rank's block of utterances (dim 0)."""
+    rank = dist.get_rank() if rank is None else rank
+    world = dist.get_world_size() if world is None else world
+    lo, hi = shard_range(t.shape[0], rank, world)
+    return t[lo:hi]
+
+
+def gather_utterances(local: torch.Tensor, n_total: int, dst: int = 0) -> Optional[torch.Tensor]:
+    """Gather per-rank blocks (dim 0, possibly ragged / empty) back into utterance order on ``dst``.
+    Blocks are padded to the common block size so one fixed-size ``gather`` suffices.  Returns the full
+    tensor on ``dst`` and None elsewhere."""
+    world, rank = dist.get_world_size(), dist.get_rank()
+    per = (n_total + world - 1) // world
+    pad = torch.zeros((per,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[: local.shape[0]] = local
+    bufs: Optional[List[torch.Tensor]] = [torch.empty_like(pad) for _ in range(world)] if rank == dst else None
+    dist.gather(pad, bufs, dst=dst)
+    if rank != dst:
+        return None
+    parts = []
+    for r in range(world):
+        lo, hi = shard_range(n_total, r, world)
+        parts.append(bufs[r][: hi - lo])
+    return torch.cat(parts, dim=0)
+
+
+def convert_sharded(encoder, vocoder, mel: torch.Tensor, speaker: torch.Tensor, dst: int = 0, **generate_kw):
+    """End-to-end conversion of a batch of equal-length utterances (convert.py:72-77) sharded over the ranks:
+    every rank encodes + generates its block; indices and waveforms are gathered on ``dst``."""
+    n = mel.shape[0]
+    m, s = shard(mel), shard(speaker)
+    if m.shape[0] > 0:
+        _, _, idx = encoder.encode(m)
+        wav = vocoder.generate(idx, s, **generate_kw)
+    else:
+        Tp = (mel.shape[2] - 2) // 2 + 1
+        idx = torch.empty(0, Tp, dtype=torch.int64, device=mel.device)
+        wav = torch.empty(0, 320 * Tp, device=mel.device)
+    return gather_utterances(idx, n, dst), gather_utterances(wav, n, dst)
