@@ -90,6 +90,12 @@ typedef struct {
  * Replaces the implicit cuBLAS calls behind nn.Linear (model.py:50,54). */
 int vqcpc_linear_f32(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias,
                      float* C, int64_t ldc, int64_t M, int32_t N, int32_t K, void* stream);
+/* Same product on the tensor cores (tcgen05 / TMEM accumulators / TMA operand tiles).  A (M, K) and W (N, K) fp32 are
+ * split into bf16 hi/lo planes (a_planes: M x 2K bf16, w_planes: N x 2K bf16, caller-provided scratch) and multiplied
+ * as hi*hi + hi*lo + lo*hi with fp32 accumulation (mode 3; error ~2^-16 relative).  K % 64 == 0, N % 64 == 0.
+ * err_flag: device int, set non-zero if a pipeline wait timed out. */
+int vqcpc_linear_tc(const float* A, const float* W, const float* bias, float* C, int64_t M, int32_t N, int32_t K,
+                    int32_t mode, void* a_planes, void* w_planes, int32_t* err_flag, void* stream);
 /* In-place relu(LayerNorm(x)) over rows of width C (biased variance, eps 1e-5) -- model.py:47-48,51-52. */
 int vqcpc_layernorm_relu_f32(float* x, const float* w, const float* b, int64_t rows, int32_t C, void* stream);
 

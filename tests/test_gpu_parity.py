@@ -65,6 +65,31 @@ def test_linear_f32(M, N, K, bias):
     assert torch.allclose(out.cpu(), ref, rtol=1e-5, atol=1e-5)
 
 
+@pytest.mark.parametrize("M,N,K,bias", [(1000, 768, 320, False), (300, 64, 768, True), (128, 512, 512, False),
+                                        (1, 256, 64, True), (40000, 768, 768, False), (4097, 128, 128, True)])
+def test_linear_tensor_core_split(M, N, K, bias):
+    """tcgen05 path with the bf16 hi/lo split (3 MMA terms): fp32-grade accuracy against an fp64 product."""
+    g = torch.Generator().manual_seed(M + N + K + 1)
+    A = torch.randn(M, K, generator=g)
+    W = torch.randn(N, K, generator=g) / K ** 0.5
+    b = torch.randn(N, generator=g) if bias else None
+    ref = (A.double() @ W.double().t() + (b.double() if bias else 0)).float()
+    Ad, Wd = A.to(dev()), W.to(dev())
+    bd = b.to(dev()) if bias else None
+    out = torch.full((M, N), float("nan"), device=dev())
+    ap = torch.empty(M, 2 * K, dtype=torch.bfloat16, device=dev())
+    wp = torch.empty(N, 2 * K, dtype=torch.bfloat16, device=dev())
+    err = torch.zeros(1, dtype=torch.int32, device=dev())
+    st = _lib.lib().vqcpc_linear_tc(_lib.ptr(Ad), _lib.ptr(Wd), _lib.ptr(bd), _lib.ptr(out), M, N, K, 3, _lib.ptr(ap),
+                                    _lib.ptr(wp), _lib.ptr(err), _lib.current_stream_ptr())
+    _lib.check(st, "linear_tc")
+    torch.cuda.synchronize()
+    assert int(err) == 0, "tensor-core pipeline timed out"
+    e = float((out.cpu() - ref).abs().max())
+    print(f"[linear_tc {M}x{N}x{K}] max abs err {e:.2e}")
+    assert torch.allclose(out.cpu(), ref, rtol=1e-4, atol=3e-5), e
+
+
 def test_linear_rejects_bad_k():
     A = torch.zeros(4, 20, device=dev())
     out = torch.empty(4, 8, device=dev())

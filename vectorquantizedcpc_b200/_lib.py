@@ -49,6 +49,7 @@ SIGNATURES = {
     "vqcpc_launch_count": (C.c_uint64, []),
     "vqcpc_device_check": (C.c_int, [C.c_int]),
     "vqcpc_linear_f32": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _i64, _i32, _i32, _vp]),
+    "vqcpc_linear_tc": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
     "vqcpc_layernorm_relu_f32": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _vp]),
     "vqcpc_vq_lookup": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp]),
     "vqcpc_encoder_workspace_bytes": (_sz, [_i32, _i32, _i32]),

@@ -1,0 +1,359 @@
+// tcgen05 / TMEM / TMA GEMM for sm_100a:   C[m, n] = sum_k A'[m, k] * W'[n, k]  (+ bias[n]),  fp32 out.
+//
+// A' and W' are bf16, K-major.  fp32-grade accuracy comes from a hi/lo split: every fp32 operand x is stored as
+// two bf16 planes  hi = bf16(x), lo = bf16(x - hi)  side by side ([hi | lo], 2K columns), and the kernel walks
+// THREE K-segments  (A_hi, W_hi), (A_hi, W_lo), (A_lo, W_hi)  accumulating all of them into the same fp32 TMEM
+// accumulator -- the dropped lo*lo term is 2^-16 relative.  nseg = 1 gives the plain bf16 product.
+//
+// Structure (one CTA per SM, persistent over output tiles, 192 threads):
+//   warp 0   : TMA producer   -- cp.async.bulk.tensor.2d of a 128 x 64 A tile and a BN x 64 W tile per stage
+//                               (SWIZZLE_128B, 4 stages, mbarrier complete_tx)
+//   warp 1   : MMA issuer     -- one lane issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16) x 4 per
+//                               stage, accumulators in TMEM (2 x BN columns: double buffered against the epilogue),
+//                               tcgen05.commit releases smem stages / publishes finished accumulators
+//   warps 2-5: epilogue       -- tcgen05.ld 32 lanes x 32 columns, (+bias), fp32 stores; each thread owns one row
+// Every mbarrier wait is bounded; on timeout the kernel raises a device-side error flag and drains.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace vqcpc {
+
+constexpr int TC_BM = 128, TC_BK = 64, TC_STAGES = 4;
+constexpr int TC_THREADS = 192;
+constexpr long long TC_TIMEOUT = 4000000000LL;
+
+// ---------------------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// bounded wait: false on timeout (caller drains)
+__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, int* err) {
+    if (mbar_try_wait(bar, parity)) return true;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > TC_TIMEOUT) { atomicExch(err, VQCPC_ERR_TIMEOUT); return false; }
+    }
+    return true;
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{ .reg .pred p; setp.ne.b32 p, %4, 0; tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p; }"
+                 ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start >> 4, LBO = 1 (unused
+// for swizzled K-major), SBO = 1024 B (8 rows x 128 B) >> 4, version = 1 (Blackwell), layout type 2 = SWIZZLE_128B.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3fff);
+    d |= static_cast<uint64_t>(1) << 16;
+    d |= static_cast<uint64_t>(1024 >> 4) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(2) << 61;
+    return d;
+}
+
+struct TcParams {
+    float* C;
+    const float* bias;      // nullable
+    int* err;
+    long long ldc;
+    int M, N, K;            // K = columns of ONE plane (multiple of 64)
+    int nseg;               // 1: plain bf16 product; 3: hi/lo split, planes stored [hi | lo] (2K columns)
+};
+
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, TcParams p) {
+    constexpr uint32_t A_BYTES = TC_BM * TC_BK * 2;        // 16 KB
+    constexpr uint32_t W_BYTES = BN * TC_BK * 2;           // 32 KB at BN = 256
+    constexpr uint32_t STAGE_BYTES = A_BYTES + W_BYTES;
+    constexpr uint32_t TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;     // power of two >= 32 (BN in {64, 128, 256})
+    // instruction descriptor: D = F32, A = B = BF16, both K-major, N = BN, M = 128
+    constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(BN >> 3) << 17) |
+                               (static_cast<uint32_t>(TC_BM >> 4) << 24);
+
+    extern __shared__ __align__(1024) unsigned char tc_smem[];
+    __shared__ __align__(8) uint64_t full_bar[TC_STAGES], empty_bar[TC_STAGES], tfull_bar[2], tempty_bar[2];
+    __shared__ uint32_t tmem_base_slot;
+
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tc_smem) + 1023) & ~uintptr_t(1023));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                     "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_slot;
+
+    const int tiles_m = (p.M + TC_BM - 1) / TC_BM, tiles_n = p.N / BN;
+    const int n_tiles = tiles_m * tiles_n;
+    const int kb_per_seg = p.K / TC_BK;
+    const int n_kb = kb_per_seg * p.nseg;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            bool ok = true;
+            for (int tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x) {
+                const int tm = tile / tiles_n, tn = tile % tiles_n;       // consecutive CTAs share an A row block
+                for (int kb = 0; kb < n_kb && ok; ++kb) {
+                    ok = mbar_wait(&empty_bar[stage], phase ^ 1, p.err);
+                    if (!ok) break;
+                    const int seg = kb / kb_per_seg, kk = (kb - seg * kb_per_seg) * TC_BK;
+                    const int a_col = (seg == 2 ? p.K : 0) + kk;           // (hi, hi, lo)
+                    const int w_col = (seg == 1 ? p.K : 0) + kk;           // (hi, lo, hi)
+                    unsigned char* sa = smem + stage * STAGE_BYTES;
+                    mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+                    tma_load_2d(sa, &map_a, a_col, tm * TC_BM, &full_bar[stage]);
+                    tma_load_2d(sa + A_BYTES, &map_w, w_col, tn * BN, &full_bar[stage]);
+                    if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase[2] = {0, 0};
+            bool ok = true;
+            for (int tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x) {
+                ok = mbar_wait(&tempty_bar[acc], acc_phase[acc] ^ 1, p.err);     // epilogue has drained this accumulator
+                if (!ok) break;
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int kb = 0; kb < n_kb && ok; ++kb) {
+                    ok = mbar_wait(&full_bar[stage], phase, p.err);
+                    if (!ok) break;
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+                    const uint64_t adesc = umma_desc_sw128(sa), bdesc = umma_desc_sw128(sa + A_BYTES);
+#pragma unroll
+                    for (int k = 0; k < TC_BK / 16; ++k)        // +32 bytes (>> 4 = 2) per K = 16 step inside the 128 B atom
+                        tc_mma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, IDESC, (kb > 0 || k > 0) ? 1u : 0u);
+                    tc_commit(&empty_bar[stage]);               // smem stage reusable once these MMAs have read it
+                    if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+                }
+                tc_commit(&tfull_bar[acc]);                     // accumulator complete
+                acc_phase[acc] ^= 1;
+                acc ^= 1;
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue (warps 2..5)
+        const int quarter = warp & 3;                           // TMEM lanes 32*quarter .. +31 are this warp's
+        int acc = 0;
+        uint32_t acc_phase[2] = {0, 0};
+        bool ok = true;
+        for (int tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x) {
+            const int tm = tile / tiles_n, tn = tile % tiles_n;
+            ok = mbar_wait(&tfull_bar[acc], acc_phase[acc], p.err);
+            ok = __all_sync(0xffffffffu, ok);
+            if (!ok) break;
+            tc_fence_after();
+            const int row = tm * TC_BM + quarter * 32 + lane;
+            float* crow = p.C + static_cast<long long>(row) * p.ldc + tn * BN;
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t v[32];
+                tc_ld32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + c0, v);
+                tc_wait_ld();
+                if (row < p.M) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        float4 o;
+                        o.x = __uint_as_float(v[j]); o.y = __uint_as_float(v[j + 1]);
+                        o.z = __uint_as_float(v[j + 2]); o.w = __uint_as_float(v[j + 3]);
+                        if (p.bias != nullptr) {
+                            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + tn * BN + c0 + j));
+                            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+                        }
+                        *reinterpret_cast<float4*>(crow + c0 + j) = o;
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            acc_phase[acc] ^= 1;
+            acc ^= 1;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+    static PFN_encodeTiled fn = nullptr;
+    if (fn == nullptr) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_encodeTiled>(p);
+    }
+    return fn;
+}
+
+// bf16 row-major (rows x cols), box = 64 columns (128 B) x box_rows, SWIZZLE_128B, zero fill out of bounds
+static int make_map(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld_elems, int box_rows) {
+    PFN_encodeTiled fn = get_encode_fn();
+    if (fn == nullptr) { set_error("gemm_tc: cuTensorMapEncodeTiled is unavailable"); return VQCPC_ERR_CUDA; }
+    cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+    cuuint64_t gstr[1] = {static_cast<cuuint64_t>(ld_elems) * 2};
+    cuuint32_t box[2] = {TC_BK, static_cast<cuuint32_t>(box_rows)};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("gemm_tc: cuTensorMapEncodeTiled failed (%d)", static_cast<int>(r)); return VQCPC_ERR_CUDA; }
+    return VQCPC_OK;
+}
+
+template <int BN>
+static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mw, const TcParams& p, cudaStream_t stream) {
+    constexpr size_t smem = TC_STAGES * (TC_BM * TC_BK * 2 + BN * TC_BK * 2) + 1024;
+    static bool attr_set = false;
+    if (!attr_set) {
+        VQ_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        attr_set = true;
+    }
+    const int tiles = ((p.M + TC_BM - 1) / TC_BM) * (p.N / BN);
+    const int sms = device_sm_count();
+    gemm_tc_kernel<BN><<<tiles < sms ? tiles : sms, TC_THREADS, smem, stream>>>(ma, mw, p);
+    VQ_CUDA(cudaGetLastError());
+    count_launch(1);
+    return VQCPC_OK;
+}
+
+// A planes (M x nplanes*K) bf16, W planes (N x nplanes*K) bf16 with nplanes = (nseg == 3 ? 2 : 1).
+int gemm_tc(const void* a_planes, const void* w_planes, const float* bias, float* C, long long ldc, int M, int N, int K,
+            int nseg, int* err_flag, cudaStream_t stream) {
+    if (M == 0) return VQCPC_OK;
+    VQ_ARG(a_planes && w_planes && C && err_flag, "gemm_tc: null pointer");
+    VQ_ARG(nseg == 1 || nseg == 3, "gemm_tc: nseg must be 1 or 3");
+    VQ_ARG(K % TC_BK == 0 && K > 0, "gemm_tc: K=%d must be a multiple of %d", K, TC_BK);
+    VQ_ARG(N % 64 == 0 && ldc % 4 == 0, "gemm_tc: N=%d must be a multiple of 64", N);
+    const int planes = nseg == 3 ? 2 : 1;
+    const int BN = (N % 256 == 0) ? 256 : (N % 128 == 0 ? 128 : 64);
+    CUtensorMap ma, mw;
+    int rc = make_map(&ma, a_planes, M, static_cast<long long>(planes) * K, static_cast<long long>(planes) * K, TC_BM);
+    if (rc) return rc;
+    rc = make_map(&mw, w_planes, N, static_cast<long long>(planes) * K, static_cast<long long>(planes) * K, BN);
+    if (rc) return rc;
+    TcParams p{C, bias, err_flag, ldc, M, N, K, nseg};
+    if (BN == 256) return launch_tc<256>(ma, mw, p, stream);
+    if (BN == 128) return launch_tc<128>(ma, mw, p, stream);
+    return launch_tc<64>(ma, mw, p, stream);
+}
+
+// ---------------------------------------------------------------------------------------------- bf16 hi/lo planes
+__device__ __forceinline__ void split2(float x, float y, __nv_bfloat162& hi, __nv_bfloat162& lo) {
+    const __nv_bfloat16 hx = __float2bfloat16_rn(x), hy = __float2bfloat16_rn(y);
+    hi = __halves2bfloat162(hx, hy);
+    lo = __halves2bfloat162(__float2bfloat16_rn(x - __bfloat162float(hx)), __float2bfloat16_rn(y - __bfloat162float(hy)));
+}
+
+// fp32 (rows x K, leading dimension ld) -> bf16 planes (rows x 2K): [hi | lo]
+__global__ void split_planes_kernel(const float* __restrict__ x, long long ld, __nv_bfloat16* __restrict__ out, long long rows, int K) {
+    const long long total = rows * (K / 4);
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long r = i / (K / 4);
+        const int q = static_cast<int>(i - r * (K / 4));
+        const float4 v = __ldg(reinterpret_cast<const float4*>(x + r * ld) + q);
+        __nv_bfloat162 h0, l0, h1, l1;
+        split2(v.x, v.y, h0, l0);
+        split2(v.z, v.w, h1, l1);
+        __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(out + r * 2 * K + 4 * q);
+        __nv_bfloat162* ol = reinterpret_cast<__nv_bfloat162*>(out + r * 2 * K + K + 4 * q);
+        oh[0] = h0; oh[1] = h1; ol[0] = l0; ol[1] = l1;
+    }
+}
+
+int split_planes(const float* x, long long ld, void* out, long long rows, int K, cudaStream_t stream) {
+    if (rows == 0) return VQCPC_OK;
+    VQ_ARG(x && out && K % 4 == 0 && ld % 4 == 0, "split_planes: bad arguments");
+    const long long total = rows * (K / 4);
+    const unsigned grid = static_cast<unsigned>((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+    split_planes_kernel<<<grid, 256, 0, stream>>>(x, ld, static_cast<__nv_bfloat16*>(out), rows, K);
+    VQ_CUDA(cudaGetLastError());
+    count_launch(1);
+    return VQCPC_OK;
+}
+
+}  // namespace vqcpc
+
+// ---------------------------------------------------------------------------------------------- C ABI
+// C = A . W^T (+bias) through the tensor-core path; A (M x K) and W (N x K) fp32 in, split on the fly into the
+// caller-provided plane buffers (a_planes: M x 2K bf16, w_planes: N x 2K bf16).  mode 3 = hi/lo split (fp32-grade),
+// mode 1 = plain bf16.
+extern "C" int vqcpc_linear_tc(const float* A, const float* W, const float* bias, float* C, int64_t M, int32_t N, int32_t K,
+                               int32_t mode, void* a_planes, void* w_planes, int32_t* err_flag, void* stream) {
+    using namespace vqcpc;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    int rc;
+    if ((rc = split_planes(A, K, a_planes, M, K, s))) return rc;
+    if ((rc = split_planes(W, K, w_planes, N, K, s))) return rc;
+    // mode 1 reads only the hi plane (plane row stride stays 2K)
+    if (mode == 3) return gemm_tc(a_planes, w_planes, bias, C, N, static_cast<int>(M), N, K, 3, err_flag, s);
+    vqcpc::set_error("vqcpc_linear_tc: only mode 3 is exposed");
+    return VQCPC_ERR_ARG;
+}

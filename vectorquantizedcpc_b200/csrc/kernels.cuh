@@ -10,6 +10,11 @@ int gemm_dense(const float* A, int64_t lda, const float* W, int64_t ldw, const f
                int64_t M, int N, int K, cudaStream_t stream);
 int gemm_conv(const float* mel, int B, int T, int Cin, const float* W, float* C, int Cout, cudaStream_t stream);
 
+// gemm_tc.cu  (tcgen05 / TMEM / TMA)
+int gemm_tc(const void* a_planes, const void* w_planes, const float* bias, float* C, long long ldc, int M, int N, int K,
+            int nseg, int* err_flag, cudaStream_t stream);
+int split_planes(const float* x, long long ld, void* out, long long rows, int K, cudaStream_t stream);
+
 // encoder.cu
 int layernorm_relu(float* x, const float* w, const float* b, int64_t rows, int C, cudaStream_t stream);
 int vq_lookup(const float* x, const float* codebook, int64_t n, int n_codes, int dim, float* q, int64_t* idx,
