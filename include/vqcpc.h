@@ -54,7 +54,16 @@ typedef struct {
     const float* lstm_w_ih;   /* rnn.weight_ih_l0 (1024, 64) */
     const float* lstm_w_hh;   /* rnn.weight_hh_l0 (1024, 256) */
     const float* lstm_b;      /* rnn.bias_ih_l0 + rnn.bias_hh_l0 (1024,)  (host-side sum) */
+    /* bf16 hi/lo planes of the GEMM weights for the tensor-core mode ([hi | lo], 2K columns, built once with
+     * vqcpc_split_planes); may be NULL when only VQCPC_GEMM_FP32 is used. */
+    const void* conv_wp;      /* (C, 2*320) */
+    const void* fc_wp[4];     /* (C, 2*C) */
+    const void* proj_wp;      /* (64, 2*C) */
 } vqcpc_encoder_weights;
+
+/* GEMM arithmetic of Encoder.encode */
+#define VQCPC_GEMM_FP32 0     /* fp32 FMA on the CUDA cores: exact-order parity path */
+#define VQCPC_GEMM_BF16X3 1   /* tcgen05 tensor cores, bf16 hi/lo split (hi*hi + hi*lo + lo*hi), fp32 accumulate */
 
 /* ---- weights of Vocoder: /root/reference/network_vocoder.py:37-39 + rnnms dims config.py:62-77,199 */
 typedef struct {
@@ -96,6 +105,8 @@ int vqcpc_linear_f32(const float* A, int64_t lda, const float* W, int64_t ldw, c
  * err_flag: device int, set non-zero if a pipeline wait timed out. */
 int vqcpc_linear_tc(const float* A, const float* W, const float* bias, float* C, int64_t M, int32_t N, int32_t K,
                     int32_t mode, void* a_planes, void* w_planes, int32_t* err_flag, void* stream);
+/* fp32 (rows, K) with leading dimension ld -> bf16 planes (rows, 2K): [bf16(x) | bf16(x - bf16(x))]. */
+int vqcpc_split_planes(const float* x, int64_t ld, void* out_planes, int64_t rows, int32_t K, void* stream);
 /* In-place relu(LayerNorm(x)) over rows of width C (biased variance, eps 1e-5) -- model.py:47-48,51-52. */
 int vqcpc_layernorm_relu_f32(float* x, const float* w, const float* b, int64_t rows, int32_t C, void* stream);
 
@@ -114,6 +125,11 @@ int vqcpc_encoder_forward(const vqcpc_encoder_weights* w, const float* mel, int3
                           void* workspace, size_t workspace_bytes,
                           float* out_z, float* out_c, int64_t* out_idx,
                           float* out_prevq, float* out_hidden, void* stream);
+/* Same with an explicit GEMM arithmetic (VQCPC_GEMM_*); workspace from vqcpc_encoder_workspace_bytes_ex. */
+size_t vqcpc_encoder_workspace_bytes_ex(int32_t B, int32_t T, int32_t channels, int32_t gemm_mode);
+int vqcpc_encoder_forward_ex(const vqcpc_encoder_weights* w, const float* mel, int32_t B, int32_t T,
+                             void* workspace, size_t workspace_bytes, float* out_z, float* out_c, int64_t* out_idx,
+                             float* out_prevq, float* out_hidden, int32_t gemm_mode, void* stream);
 /* nn.LSTM(64,256) over quantised codes only (model.py:57,69): idx (B, T') -> out_c (B, T', 256). */
 size_t vqcpc_lstm_workspace_bytes(int32_t B, int32_t Tp);
 int vqcpc_lstm_forward(const vqcpc_encoder_weights* w, const int64_t* idx, int32_t B, int32_t Tp,

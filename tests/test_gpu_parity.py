@@ -207,6 +207,32 @@ def test_encoder_matches_golden(golden_dir, name):
           f"max|dc| {float((c[ok_utts] - ref_c[ok_utts]).abs().max()) if ok_utts.any() else float('nan'):.2e}")
 
 
+@pytest.mark.parametrize("C_,B,T", [(768, 8, 300), (512, 33, 101)])
+def test_encoder_tensor_core_mode_matches_oracle(C_, B, T):
+    """tcgen05 GEMMs with the bf16 hi/lo split: pre-VQ z within 1e-4 relative (the north-star fp32 bound); indices
+    equal to the oracle's except near-ties of the size the z error allows; c compared where the indices agree."""
+    enc, sd = make_encoder(C_, True)
+    enc.gemm_mode = "bf16x3"
+    mel = fixtures.synthetic_mel(B, T, seed=21)
+    z, c, idx, prevq = [t.cpu() for t in enc.encode_with_aux(mel.to(dev()))]
+    enc.gemm_mode = "fp32"
+    z32, c32, idx32, prevq32 = [t.cpu() for t in enc.encode_with_aux(mel.to(dev()))]
+    zo, co, io, zp = oenc.encode(sd, mel, return_aux=True)
+    scale = float(zp.abs().max())
+    err = float((prevq - zp).abs().max())
+    print(f"[encoder bf16x3 C={C_}] max|dz_pre| = {err:.2e} (scale {scale:.2f}; fp32 path {float((prevq32 - zp).abs().max()):.2e})")
+    assert err <= 1e-4 * scale + 1e-5
+    rep = oenc.classify_index_mismatches(zp, sd["codebook.embedding"], idx, io, slack=4 * err * 2.0)
+    assert rep["hard"] == 0, rep
+    same = idx == io
+    assert same.float().mean() > 0.99
+    assert torch.equal(z[same], zo[same])
+    ok = same.all(dim=1)
+    assert ok.any()
+    assert torch.allclose(c[ok], co[ok], rtol=RTOL, atol=ATOL_C)
+    assert torch.equal(idx32, io)
+
+
 def test_encoder_matches_oracle_other_shapes_and_hook():
     enc, sd = make_encoder(512, True)
     aux = []

@@ -12,6 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libvqcpc_b200.so")
 
 ERR_ARG, ERR_CUDA, ERR_DEVICE, ERR_TIMEOUT = 1, 2, 3, 4
+GEMM_FP32, GEMM_BF16X3 = 0, 1
 f32p = C.POINTER(C.c_float)
 
 
@@ -24,6 +25,7 @@ class EncoderWeights(C.Structure):
         ("ln_w", C.c_void_p * 5), ("ln_b", C.c_void_p * 5), ("fc_w", C.c_void_p * 4),
         ("proj_w", C.c_void_p), ("proj_b", C.c_void_p), ("codebook", C.c_void_p),
         ("lstm_w_ih", C.c_void_p), ("lstm_w_hh", C.c_void_p), ("lstm_b", C.c_void_p),
+        ("conv_wp", C.c_void_p), ("fc_wp", C.c_void_p * 4), ("proj_wp", C.c_void_p),
     ]
 
 
@@ -50,10 +52,13 @@ SIGNATURES = {
     "vqcpc_device_check": (C.c_int, [C.c_int]),
     "vqcpc_linear_f32": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _i64, _i32, _i32, _vp]),
     "vqcpc_linear_tc": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
+    "vqcpc_split_planes": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _vp]),
     "vqcpc_layernorm_relu_f32": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _vp]),
     "vqcpc_vq_lookup": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp]),
     "vqcpc_encoder_workspace_bytes": (_sz, [_i32, _i32, _i32]),
     "vqcpc_encoder_forward": (C.c_int, [C.POINTER(EncoderWeights), _vp, _i32, _i32, _vp, _sz, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "vqcpc_encoder_workspace_bytes_ex": (_sz, [_i32, _i32, _i32, _i32]),
+    "vqcpc_encoder_forward_ex": (C.c_int, [C.POINTER(EncoderWeights), _vp, _i32, _i32, _vp, _sz, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
     "vqcpc_lstm_workspace_bytes": (_sz, [_i32, _i32]),
     "vqcpc_lstm_forward": (C.c_int, [C.POINTER(EncoderWeights), _vp, _i32, _i32, _vp, _sz, _vp, _vp]),
     "vqcpc_vocoder_pack": (C.c_int, [C.POINTER(VocoderWeights), _vp, _vp]),

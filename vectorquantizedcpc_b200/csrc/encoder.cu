@@ -2,6 +2,8 @@
 //   conv (implicit-im2col GEMM) -> LN+ReLU -> 4x[Linear -> LN+ReLU] -> Linear(C,64)+b -> VQ lookup -> LSTM.
 // This file: LayerNorm+ReLU rows, the exact fp32 VQ nearest-code search + gather, the persistent LSTM
 // (LL exchange between 32-CTA groups, W_hh resident in registers) and the host-side orchestration.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -61,6 +63,99 @@ int layernorm_relu(float* x, const float* w, const float* b, int64_t rows, int C
     VQ_CUDA(cudaGetLastError());
     count_launch(1);
     return VQCPC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Tensor-core mode helpers: the A operand of the next tcgen05 GEMM is a pair of bf16 planes [hi | lo].
+//   ln_relu_split : relu(LayerNorm(y)) of an fp32 row -> planes (and, optionally, the fp32 row itself)
+//   im2col_split  : the conv's implicit im2col rows (K = 320) -> planes
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void split_store4(float4 o, __nv_bfloat16* hi, __nv_bfloat16* lo) {
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(o.x), h1 = __float2bfloat16_rn(o.y), h2 = __float2bfloat16_rn(o.z),
+                        h3 = __float2bfloat16_rn(o.w);
+    reinterpret_cast<__nv_bfloat162*>(hi)[0] = __halves2bfloat162(h0, h1);
+    reinterpret_cast<__nv_bfloat162*>(hi)[1] = __halves2bfloat162(h2, h3);
+    reinterpret_cast<__nv_bfloat162*>(lo)[0] = __halves2bfloat162(__float2bfloat16_rn(o.x - __bfloat162float(h0)),
+                                                                   __float2bfloat16_rn(o.y - __bfloat162float(h1)));
+    reinterpret_cast<__nv_bfloat162*>(lo)[1] = __halves2bfloat162(__float2bfloat16_rn(o.z - __bfloat162float(h2)),
+                                                                   __float2bfloat16_rn(o.w - __bfloat162float(h3)));
+}
+
+template <int N4>
+__global__ void __launch_bounds__(256) ln_relu_split_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                            const float* __restrict__ b, __nv_bfloat16* __restrict__ planes,
+                                                            float* __restrict__ out_f32, int64_t rows) {
+    constexpr int C = N4 * 128;
+    const int lane = threadIdx.x & 31;
+    const int64_t row = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const float4* p = reinterpret_cast<const float4*>(x + row * C);
+    float4 v[N4];
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < N4; ++j) {
+        v[j] = p[j * 32 + lane];
+        s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+    }
+    const float mean = warp_sum(s) * (1.0f / C);
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < N4; ++j) {
+        v[j].x -= mean; v[j].y -= mean; v[j].z -= mean; v[j].w -= mean;
+        q += (v[j].x * v[j].x + v[j].y * v[j].y) + (v[j].z * v[j].z + v[j].w * v[j].w);
+    }
+    const float rstd = 1.0f / sqrtf(warp_sum(q) * (1.0f / C) + 1e-5f);
+    __nv_bfloat16* prow = planes + row * 2 * C;
+#pragma unroll
+    for (int j = 0; j < N4; ++j) {
+        const float4 ww = __ldg(reinterpret_cast<const float4*>(w) + j * 32 + lane);
+        const float4 bb = __ldg(reinterpret_cast<const float4*>(b) + j * 32 + lane);
+        float4 o;
+        o.x = fmaxf(fmaf(v[j].x * rstd, ww.x, bb.x), 0.f);
+        o.y = fmaxf(fmaf(v[j].y * rstd, ww.y, bb.y), 0.f);
+        o.z = fmaxf(fmaf(v[j].z * rstd, ww.z, bb.z), 0.f);
+        o.w = fmaxf(fmaf(v[j].w * rstd, ww.w, bb.w), 0.f);
+        const int col = (j * 32 + lane) * 4;
+        split_store4(o, prow + col, prow + C + col);
+        if (out_f32 != nullptr) reinterpret_cast<float4*>(out_f32 + row * C)[j * 32 + lane] = o;
+    }
+}
+
+static int layernorm_relu_split(const float* x, const float* w, const float* b, void* planes, float* out_f32,
+                                int64_t rows, int C, cudaStream_t stream) {
+    if (rows == 0) return VQCPC_OK;
+    VQ_ARG(C % 128 == 0 && C >= 128 && C <= 1024, "layernorm: C=%d must be a multiple of 128 in [128,1024]", C);
+    const unsigned grid = static_cast<unsigned>((rows + 7) / 8);
+    __nv_bfloat16* pl = static_cast<__nv_bfloat16*>(planes);
+    switch (C / 128) {
+#define LN_CASE(n) case n: ln_relu_split_kernel<n><<<grid, 256, 0, stream>>>(x, w, b, pl, out_f32, rows); break;
+        LN_CASE(1) LN_CASE(2) LN_CASE(3) LN_CASE(4) LN_CASE(5) LN_CASE(6) LN_CASE(7) LN_CASE(8)
+#undef LN_CASE
+    }
+    VQ_CUDA(cudaGetLastError());
+    count_launch(1);
+    return VQCPC_OK;
+}
+
+// one thread per (row m = b*Tp + t, input channel i): the 4 taps mel[b, i, 2t-1 .. 2t+2] (zero padded)
+__global__ void im2col_split_kernel(const float* __restrict__ mel, __nv_bfloat16* __restrict__ planes, int B, int T, int Tp,
+                                    int Cin) {
+    const int K = Cin * 4;
+    const int64_t total = static_cast<int64_t>(B) * Tp * Cin;
+    for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int i = static_cast<int>(idx % Cin);
+        const int64_t m = idx / Cin;
+        const int b = static_cast<int>(m / Tp), t = static_cast<int>(m - static_cast<int64_t>(b) * Tp);
+        const float* p = mel + (static_cast<int64_t>(b) * Cin + i) * T + 2 * t - 1;
+        float4 v;
+        v.x = (t > 0) ? __ldg(p) : 0.0f;
+        v.y = __ldg(p + 1);
+        v.z = (2 * t + 1 < T) ? __ldg(p + 2) : 0.0f;
+        v.w = (2 * t + 2 < T) ? __ldg(p + 3) : 0.0f;
+        __nv_bfloat16* row = planes + m * 2 * K;
+        split_store4(v, row + 4 * i, row + K + 4 * i);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -393,7 +488,7 @@ static size_t lstm_ws_bytes() {
 }
 
 int lstm_forward(const vqcpc_encoder_weights* w, const int64_t* idx, int B, int Tp, void* ws, size_t ws_bytes,
-                 float* out_c, cudaStream_t stream) {
+                 float* out_c, cudaStream_t stream, bool reset_status = true) {
     VQ_ARG(w && idx && ws && out_c, "lstm: null pointer");
     VQ_ARG(w->n_embeddings == VQ_M && w->z_dim == VQ_D && w->c_dim == LSTM_H,
            "lstm: only 512 codes x 64 -> 256 is supported");
@@ -403,7 +498,7 @@ int lstm_forward(const vqcpc_encoder_weights* w, const int64_t* idx, int B, int 
     WorkspaceHeader* hdr = reinterpret_cast<WorkspaceHeader*>(base);
     float* table = reinterpret_cast<float*>(base + sizeof(WorkspaceHeader));
     void* ll = base + sizeof(WorkspaceHeader) + align_up(sizeof(float) * VQ_M * LSTM_G, 256);
-    VQ_CUDA(cudaMemsetAsync(hdr, 0, sizeof(WorkspaceHeader), stream));
+    if (reset_status) VQ_CUDA(cudaMemsetAsync(hdr, 0, sizeof(WorkspaceHeader), stream));
     int rc = gemm_dense(w->codebook, VQ_D, w->lstm_w_ih, VQ_D, w->lstm_b, table, LSTM_G, VQ_M, LSTM_G, VQ_D, stream);
     if (rc) return rc;
     LstmParams prm{};
@@ -424,48 +519,76 @@ int lstm_forward(const vqcpc_encoder_weights* w, const int64_t* idx, int B, int 
 // Orchestration of Encoder.encode.
 // workspace: [lstm workspace][act0 M*C][act1 M*C][z_pre M*64]
 // ------------------------------------------------------------------------------------------------
-static size_t encoder_ws_bytes(int B, int T, int C) {
+static size_t encoder_ws_bytes(int B, int T, int C, int mode) {
     const int Tp = T >= 2 ? (T - 2) / 2 + 1 : 0;
     const size_t M = static_cast<size_t>(B) * Tp;
-    return align_up(lstm_ws_bytes(), 256) + 2 * align_up(M * C * sizeof(float), 256) +
-           align_up(M * VQ_D * sizeof(float), 256);
+    size_t n = align_up(lstm_ws_bytes(), 256) + 2 * align_up(M * C * sizeof(float), 256) +
+               align_up(M * VQ_D * sizeof(float), 256);
+    if (mode == VQCPC_GEMM_BF16X3) n += align_up(M * 2 * (C > 320 ? C : 320) * 2, 256);   // bf16 planes of the A operand
+    return n;
 }
 
 int encoder_forward(const vqcpc_encoder_weights* w, const float* mel, int B, int T, void* ws, size_t ws_bytes,
-                    float* out_z, float* out_c, int64_t* out_idx, float* out_prevq, float* out_hidden,
+                    float* out_z, float* out_c, int64_t* out_idx, float* out_prevq, float* out_hidden, int mode,
                     cudaStream_t stream) {
     if (B == 0) return VQCPC_OK;
     VQ_ARG(w && mel && ws && out_z && out_c && out_idx, "encoder: null pointer");
     VQ_ARG(B >= 0 && T >= 2, "encoder: bad shape B=%d T=%d (T must be >= 2)", B, T);
+    VQ_ARG(mode == VQCPC_GEMM_FP32 || mode == VQCPC_GEMM_BF16X3, "encoder: unknown gemm_mode %d", mode);
     const int C = w->channels;
     VQ_ARG(w->in_channels == 80, "encoder: in_channels must be 80");
     VQ_ARG(C % 128 == 0 && C >= 128 && C <= 1024, "encoder: channels=%d must be a multiple of 128 in [128,1024]", C);
-    VQ_ARG(ws_bytes >= encoder_ws_bytes(B, T, C), "encoder: workspace too small");
-    if (B == 0) return VQCPC_OK;
+    VQ_ARG(ws_bytes >= encoder_ws_bytes(B, T, C, mode), "encoder: workspace too small");
     const int Tp = (T - 2) / 2 + 1;
     const int64_t M = static_cast<int64_t>(B) * Tp;
     unsigned char* base = static_cast<unsigned char*>(ws);
     void* lstm_ws = base;
+    WorkspaceHeader* hdr = reinterpret_cast<WorkspaceHeader*>(base);
     size_t off = align_up(lstm_ws_bytes(), 256);
     float* act[2];
     act[0] = reinterpret_cast<float*>(base + off); off += align_up(M * C * sizeof(float), 256);
     act[1] = reinterpret_cast<float*>(base + off); off += align_up(M * C * sizeof(float), 256);
-    float* zpre = out_prevq ? out_prevq : reinterpret_cast<float*>(base + off);
+    float* zpre_ws = reinterpret_cast<float*>(base + off); off += align_up(M * VQ_D * sizeof(float), 256);
+    float* zpre = out_prevq ? out_prevq : zpre_ws;
 
     int rc;
-    if ((rc = gemm_conv(mel, B, T, 80, w->conv_w, act[0], C, stream))) return rc;
-    if ((rc = layernorm_relu(act[0], w->ln_w[0], w->ln_b[0], M, C, stream))) return rc;
-    int cur = 0;
-    for (int j = 0; j < 4; ++j) {
-        if ((rc = gemm_dense(act[cur], C, w->fc_w[j], C, nullptr, act[cur ^ 1], C, M, C, C, stream))) return rc;
-        cur ^= 1;
-        if ((rc = layernorm_relu(act[cur], w->ln_w[j + 1], w->ln_b[j + 1], M, C, stream))) return rc;
+    if (mode == VQCPC_GEMM_FP32) {
+        if ((rc = gemm_conv(mel, B, T, 80, w->conv_w, act[0], C, stream))) return rc;
+        if ((rc = layernorm_relu(act[0], w->ln_w[0], w->ln_b[0], M, C, stream))) return rc;
+        int cur = 0;
+        for (int j = 0; j < 4; ++j) {
+            if ((rc = gemm_dense(act[cur], C, w->fc_w[j], C, nullptr, act[cur ^ 1], C, M, C, C, stream))) return rc;
+            cur ^= 1;
+            if ((rc = layernorm_relu(act[cur], w->ln_w[j + 1], w->ln_b[j + 1], M, C, stream))) return rc;
+        }
+        if (out_hidden)
+            VQ_CUDA(cudaMemcpyAsync(out_hidden, act[cur], M * C * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+        if ((rc = gemm_dense(act[cur], C, w->proj_w, C, w->proj_b, zpre, VQ_D, M, VQ_D, C, stream))) return rc;
+    } else {
+        // tensor-core mode: every GEMM is tcgen05 over bf16 hi/lo planes; LN+ReLU re-splits its output for the next one
+        VQ_ARG(w->conv_wp && w->fc_wp[0] && w->fc_wp[1] && w->fc_wp[2] && w->fc_wp[3] && w->proj_wp,
+               "encoder: weight planes missing (vqcpc_split_planes) for VQCPC_GEMM_BF16X3");
+        VQ_ARG(M < (1LL << 31), "encoder: too many frames for the tensor-core mode");
+        void* planes = base + off;
+        VQ_CUDA(cudaMemsetAsync(hdr, 0, sizeof(WorkspaceHeader), stream));
+        {
+            const int64_t total = M * 80;
+            const unsigned grid = static_cast<unsigned>((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+            im2col_split_kernel<<<grid, 256, 0, stream>>>(mel, static_cast<__nv_bfloat16*>(planes), B, T, Tp, 80);
+            VQ_CUDA(cudaGetLastError());
+            count_launch(1);
+        }
+        if ((rc = gemm_tc(planes, w->conv_wp, nullptr, act[0], C, static_cast<int>(M), C, 320, 3, &hdr->status, stream))) return rc;
+        if ((rc = layernorm_relu_split(act[0], w->ln_w[0], w->ln_b[0], planes, nullptr, M, C, stream))) return rc;
+        for (int j = 0; j < 4; ++j) {
+            if ((rc = gemm_tc(planes, w->fc_wp[j], nullptr, act[0], C, static_cast<int>(M), C, C, 3, &hdr->status, stream))) return rc;
+            if ((rc = layernorm_relu_split(act[0], w->ln_w[j + 1], w->ln_b[j + 1], planes, j == 3 ? out_hidden : nullptr, M, C,
+                                           stream))) return rc;
+        }
+        if ((rc = gemm_tc(planes, w->proj_wp, w->proj_b, zpre, VQ_D, static_cast<int>(M), VQ_D, C, 3, &hdr->status, stream))) return rc;
     }
-    if (out_hidden)
-        VQ_CUDA(cudaMemcpyAsync(out_hidden, act[cur], M * C * sizeof(float), cudaMemcpyDeviceToDevice, stream));
-    if ((rc = gemm_dense(act[cur], C, w->proj_w, C, w->proj_b, zpre, VQ_D, M, VQ_D, C, stream))) return rc;
     if ((rc = vq_lookup(zpre, w->codebook, M, VQ_M, VQ_D, out_z, out_idx, stream))) return rc;
-    return lstm_forward(w, out_idx, B, Tp, lstm_ws, lstm_ws_bytes(), out_c, stream);
+    return lstm_forward(w, out_idx, B, Tp, lstm_ws, lstm_ws_bytes(), out_c, stream, mode == VQCPC_GEMM_FP32);
 }
 
 }  // namespace vqcpc
@@ -480,13 +603,23 @@ extern "C" int vqcpc_vq_lookup(const float* x, const float* codebook, int64_t n_
     return vqcpc::vq_lookup(x, codebook, n_frames, n_codes, dim, out_q, out_idx, static_cast<cudaStream_t>(stream));
 }
 extern "C" size_t vqcpc_encoder_workspace_bytes(int32_t B, int32_t T, int32_t channels) {
-    return vqcpc::encoder_ws_bytes(B, T, channels);
+    return vqcpc::encoder_ws_bytes(B, T, channels, VQCPC_GEMM_FP32);
+}
+extern "C" size_t vqcpc_encoder_workspace_bytes_ex(int32_t B, int32_t T, int32_t channels, int32_t gemm_mode) {
+    return vqcpc::encoder_ws_bytes(B, T, channels, gemm_mode);
+}
+extern "C" int vqcpc_encoder_forward_ex(const vqcpc_encoder_weights* w, const float* mel, int32_t B, int32_t T,
+                                        void* workspace, size_t workspace_bytes, float* out_z, float* out_c,
+                                        int64_t* out_idx, float* out_prevq, float* out_hidden, int32_t gemm_mode,
+                                        void* stream) {
+    return vqcpc::encoder_forward(w, mel, B, T, workspace, workspace_bytes, out_z, out_c, out_idx, out_prevq,
+                                  out_hidden, gemm_mode, static_cast<cudaStream_t>(stream));
 }
 extern "C" int vqcpc_encoder_forward(const vqcpc_encoder_weights* w, const float* mel, int32_t B, int32_t T,
                                      void* workspace, size_t workspace_bytes, float* out_z, float* out_c,
                                      int64_t* out_idx, float* out_prevq, float* out_hidden, void* stream) {
     return vqcpc::encoder_forward(w, mel, B, T, workspace, workspace_bytes, out_z, out_c, out_idx, out_prevq,
-                                  out_hidden, static_cast<cudaStream_t>(stream));
+                                  out_hidden, VQCPC_GEMM_FP32, static_cast<cudaStream_t>(stream));
 }
 extern "C" size_t vqcpc_lstm_workspace_bytes(int32_t B, int32_t Tp) {
     (void)B; (void)Tp;

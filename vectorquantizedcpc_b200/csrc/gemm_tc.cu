@@ -342,6 +342,9 @@ int split_planes(const float* x, long long ld, void* out, long long rows, int K,
 }  // namespace vqcpc
 
 // ---------------------------------------------------------------------------------------------- C ABI
+extern "C" int vqcpc_split_planes(const float* x, int64_t ld, void* out_planes, int64_t rows, int32_t K, void* stream) {
+    return vqcpc::split_planes(x, ld, out_planes, rows, K, static_cast<cudaStream_t>(stream));
+}
 // C = A . W^T (+bias) through the tensor-core path; A (M x K) and W (N x K) fp32 in, split on the fly into the
 // caller-provided plane buffers (a_planes: M x 2K bf16, w_planes: N x 2K bf16).  mode 3 = hi/lo split (fp32-grade),
 // mode 1 = plain bf16.

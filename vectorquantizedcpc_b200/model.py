@@ -104,6 +104,19 @@ class Encoder(nn.Module):
         self.rnn = nn.LSTM(conf.z_dim, conf.c_dim, batch_first=True)
         self._packed = None
         self._packed_key = None
+        # GEMM arithmetic: "fp32" = CUDA-core FMA (exact-order parity path), "bf16x3" = tcgen05 tensor cores with a
+        # bf16 hi/lo split (fp32-grade: ~2^-16 relative per product), "auto" = bf16x3 once B*T' >= AUTO_TC_ROWS.
+        self.gemm_mode = "auto"
+
+    AUTO_TC_ROWS = 4096
+
+    def _resolve_mode(self, rows: int) -> int:
+        mode = self.gemm_mode
+        if mode == "auto":
+            mode = "bf16x3" if rows >= self.AUTO_TC_ROWS else "fp32"
+        if mode not in ("fp32", "bf16x3"):
+            raise ValueError(f"gemm_mode must be 'auto', 'fp32' or 'bf16x3', got {self.gemm_mode!r}")
+        return _lib.GEMM_BF16X3 if mode == "bf16x3" else _lib.GEMM_FP32
 
     # -------------------------------------------------------------------------------- weights
     def _weight_tensors(self):
@@ -136,6 +149,23 @@ class Encoder(nn.Module):
             w.fc_w[i] = t.data_ptr()
         w.proj_w, w.proj_b, w.codebook = pw.data_ptr(), pb.data_ptr(), cb.data_ptr()
         w.lstm_w_ih, w.lstm_w_hh, w.lstm_b = wih.data_ptr(), whh.data_ptr(), lstm_b.data_ptr()
+        # bf16 hi/lo planes of the GEMM weights for the tensor-core mode
+        lib = _lib.lib()
+        dev = conv_w.device
+
+        def planes(t2d):
+            rows, K = t2d.shape
+            out = torch.empty(rows, 2 * K, dtype=torch.bfloat16, device=dev)
+            with torch.cuda.device(dev):
+                _lib.check(lib.vqcpc_split_planes(t2d.data_ptr(), K, out.data_ptr(), rows, K, _lib.current_stream_ptr()),
+                           "Encoder.pack_weights")
+            keep.append(out)
+            return out.data_ptr()
+
+        w.conv_wp = planes(conv_w.view(conv_w.shape[0], -1))
+        for i, t in enumerate((f0, f1, f2, f3)):
+            w.fc_wp[i] = planes(t)
+        w.proj_wp = planes(pw)
         self._packed, self._packed_key = (w, keep), key
         return self._packed
 
@@ -168,15 +198,16 @@ class Encoder(nn.Module):
         idx = torch.empty(B, Tp, dtype=torch.int64, device=dev)
         prevq = torch.empty(B, Tp, self.conf.z_dim, device=dev) if want_aux else None
         hidden = torch.empty(B, Tp, self.conf.channels, device=dev) if want_aux else None
-        ws_bytes = lib.vqcpc_encoder_workspace_bytes(B, T, self.conf.channels)
+        mode = self._resolve_mode(B * Tp)
+        ws_bytes = lib.vqcpc_encoder_workspace_bytes_ex(B, T, self.conf.channels, mode)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
-            st = lib.vqcpc_encoder_forward(C.byref(w), _lib.ptr(mel), B, T, _lib.ptr(ws), ws_bytes, _lib.ptr(z),
-                                           _lib.ptr(c), _lib.ptr(idx), _lib.ptr(prevq), _lib.ptr(hidden),
-                                           _lib.current_stream_ptr())
+            st = lib.vqcpc_encoder_forward_ex(C.byref(w), _lib.ptr(mel), B, T, _lib.ptr(ws), ws_bytes, _lib.ptr(z),
+                                              _lib.ptr(c), _lib.ptr(idx), _lib.ptr(prevq), _lib.ptr(hidden), mode,
+                                              _lib.current_stream_ptr())
             _lib.check(st, "Encoder.encode")
             if B > 0:
-                _lib.check(lib.vqcpc_check_status(_lib.ptr(ws), _lib.current_stream_ptr()), "Encoder.encode (LSTM)")
+                _lib.check(lib.vqcpc_check_status(_lib.ptr(ws), _lib.current_stream_ptr()), "Encoder.encode (persistent kernels)")
         if want_aux:
             last = self.encoder[-1]
             for hook in list(last._forward_hooks.values()):
