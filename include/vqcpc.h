@@ -59,6 +59,7 @@ typedef struct {
     const void* conv_wp;      /* (C, 2*320) */
     const void* fc_wp[4];     /* (C, 2*C) */
     const void* proj_wp;      /* (64, 2*C) */
+    const void* lstm_whh_p;   /* (1024, 2*256): planes of rnn.weight_hh_l0 for the batched (B >= 64) LSTM */
 } vqcpc_encoder_weights;
 
 /* GEMM arithmetic of Encoder.encode */

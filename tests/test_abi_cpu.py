@@ -34,7 +34,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layout_matches_header():
     import ctypes as C
     # 6 int32 + 21 pointers each
-    assert C.sizeof(_lib.EncoderWeights) == 24 + 8 * 27
+    assert C.sizeof(_lib.EncoderWeights) == 24 + 8 * 28
     assert C.sizeof(_lib.VocoderWeights) == 24 + 8 * 21
 
 

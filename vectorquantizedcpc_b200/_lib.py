@@ -25,7 +25,7 @@ class EncoderWeights(C.Structure):
         ("ln_w", C.c_void_p * 5), ("ln_b", C.c_void_p * 5), ("fc_w", C.c_void_p * 4),
         ("proj_w", C.c_void_p), ("proj_b", C.c_void_p), ("codebook", C.c_void_p),
         ("lstm_w_ih", C.c_void_p), ("lstm_w_hh", C.c_void_p), ("lstm_b", C.c_void_p),
-        ("conv_wp", C.c_void_p), ("fc_wp", C.c_void_p * 4), ("proj_wp", C.c_void_p),
+        ("conv_wp", C.c_void_p), ("fc_wp", C.c_void_p * 4), ("proj_wp", C.c_void_p), ("lstm_whh_p", C.c_void_p),
     ]
 
 

@@ -481,18 +481,64 @@ static int lstm_launch(LstmParams prm, void* ll_mem, cudaStream_t stream) {
     return VQCPC_OK;
 }
 
-// workspace: [header][table 512x1024][ll]
-static size_t lstm_ws_bytes() {
+// ------------------------------------------------------------------------------------------------
+// Large batches run the LSTM time-major instead: per step ONE batched product  gates = H_{t-1} . W_hh^T
+// (B x 1024, K = 256; tcgen05 over bf16 hi/lo planes of h, or the fp32 GEMM) followed by this fused gate kernel,
+// which adds the gathered input projection table[idx[b, t]], applies the gate non-linearities, updates the cell
+// state, writes h_t into the output sequence and re-splits it into the planes the next step's GEMM reads.
+// ------------------------------------------------------------------------------------------------
+constexpr int LSTM_BATCHED_MIN_B = 64;
+
+__global__ void lstm_gate_kernel(const float* __restrict__ gates, const float* __restrict__ table,
+                                 const int64_t* __restrict__ idx, int t, int Tp, float* __restrict__ cstate,
+                                 float* __restrict__ out, __nv_bfloat16* __restrict__ hplanes, int B) {
+    const int64_t total = static_cast<int64_t>(B) * (LSTM_H / 4);
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int b = static_cast<int>(i / (LSTM_H / 4)), q = static_cast<int>(i % (LSTM_H / 4));
+        const float4* trow = reinterpret_cast<const float4*>(table + idx[static_cast<int64_t>(b) * Tp + t] * LSTM_G);
+        float4 g[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            g[k] = __ldg(trow + k * (LSTM_H / 4) + q);
+            if (gates != nullptr) {
+                const float4 r = reinterpret_cast<const float4*>(gates + static_cast<int64_t>(b) * LSTM_G)[k * (LSTM_H / 4) + q];
+                g[k].x += r.x; g[k].y += r.y; g[k].z += r.z; g[k].w += r.w;
+            }
+        }
+        float4 c = (t == 0) ? make_float4(0.f, 0.f, 0.f, 0.f) : reinterpret_cast<float4*>(cstate)[i];
+        float4 h;
+#define LSTM_CELL(e)                                                                        \
+        c.e = sigmoid_fast(g[1].e) * c.e + sigmoid_fast(g[0].e) * tanh_fast(g[2].e);         \
+        h.e = sigmoid_fast(g[3].e) * tanh_fast(c.e);
+        LSTM_CELL(x) LSTM_CELL(y) LSTM_CELL(z) LSTM_CELL(w)
+#undef LSTM_CELL
+        reinterpret_cast<float4*>(cstate)[i] = c;
+        reinterpret_cast<float4*>(out + (static_cast<int64_t>(b) * Tp + t) * LSTM_H)[q] = h;
+        if (hplanes != nullptr) {
+            __nv_bfloat16* row = hplanes + static_cast<int64_t>(b) * 2 * LSTM_H;
+            split_store4(h, row + 4 * q, row + LSTM_H + 4 * q);
+        }
+    }
+}
+
+// workspace: [header][table 512x1024][ll][gates B x 1024][cstate B x 256][h planes B x 512 bf16]
+static size_t lstm_batched_bytes(int B) {
+    if (B < LSTM_BATCHED_MIN_B) return 0;
+    return align_up(sizeof(float) * B * LSTM_G, 256) + align_up(sizeof(float) * B * LSTM_H, 256) +
+           align_up(2 * static_cast<size_t>(B) * 2 * LSTM_H, 256);
+}
+static size_t lstm_ws_bytes(int B) {
     return sizeof(WorkspaceHeader) + align_up(sizeof(float) * VQ_M * LSTM_G, 256) +
-           lstm_ll_bytes(LSTM_MAX_GROUPS, LSTM_MAX_NB);
+           lstm_ll_bytes(LSTM_MAX_GROUPS, LSTM_MAX_NB) + lstm_batched_bytes(B);
 }
 
 int lstm_forward(const vqcpc_encoder_weights* w, const int64_t* idx, int B, int Tp, void* ws, size_t ws_bytes,
-                 float* out_c, cudaStream_t stream, bool reset_status = true) {
+                 float* out_c, cudaStream_t stream, bool reset_status = true, int mode = VQCPC_GEMM_FP32) {
     VQ_ARG(w && idx && ws && out_c, "lstm: null pointer");
     VQ_ARG(w->n_embeddings == VQ_M && w->z_dim == VQ_D && w->c_dim == LSTM_H,
            "lstm: only 512 codes x 64 -> 256 is supported");
-    VQ_ARG(ws_bytes >= lstm_ws_bytes(), "lstm: workspace too small (%zu < %zu)", ws_bytes, lstm_ws_bytes());
+    VQ_ARG(ws_bytes >= lstm_ws_bytes(B), "lstm: workspace too small (%zu < %zu)", ws_bytes, lstm_ws_bytes(B));
     if (B == 0 || Tp == 0) return VQCPC_OK;
     unsigned char* base = static_cast<unsigned char*>(ws);
     WorkspaceHeader* hdr = reinterpret_cast<WorkspaceHeader*>(base);
@@ -501,6 +547,31 @@ int lstm_forward(const vqcpc_encoder_weights* w, const int64_t* idx, int B, int 
     if (reset_status) VQ_CUDA(cudaMemsetAsync(hdr, 0, sizeof(WorkspaceHeader), stream));
     int rc = gemm_dense(w->codebook, VQ_D, w->lstm_w_ih, VQ_D, w->lstm_b, table, LSTM_G, VQ_M, LSTM_G, VQ_D, stream);
     if (rc) return rc;
+    if (B >= LSTM_BATCHED_MIN_B) {
+        unsigned char* bb = static_cast<unsigned char*>(ll) + lstm_ll_bytes(LSTM_MAX_GROUPS, LSTM_MAX_NB);
+        float* gates = reinterpret_cast<float*>(bb); bb += align_up(sizeof(float) * B * LSTM_G, 256);
+        float* cstate = reinterpret_cast<float*>(bb); bb += align_up(sizeof(float) * B * LSTM_H, 256);
+        __nv_bfloat16* hplanes = reinterpret_cast<__nv_bfloat16*>(bb);
+        const bool tc = (mode == VQCPC_GEMM_BF16X3) && (w->lstm_whh_p != nullptr);
+        TcPlan plan;
+        if (tc && (rc = gemm_tc_plan(&plan, hplanes, w->lstm_whh_p, nullptr, gates, LSTM_G, B, LSTM_G, LSTM_H, 3, &hdr->status)))
+            return rc;
+        const int64_t total = static_cast<int64_t>(B) * (LSTM_H / 4);
+        const unsigned grid = static_cast<unsigned>((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
+        for (int t = 0; t < Tp; ++t) {
+            if (t > 0) {
+                if (tc) rc = gemm_tc_run(&plan, stream);
+                else rc = gemm_dense(out_c + static_cast<int64_t>(t - 1) * LSTM_H, static_cast<int64_t>(Tp) * LSTM_H, w->lstm_w_hh,
+                                     LSTM_H, nullptr, gates, LSTM_G, B, LSTM_G, LSTM_H, stream);
+                if (rc) return rc;
+            }
+            lstm_gate_kernel<<<grid, 256, 0, stream>>>(t > 0 ? gates : nullptr, table, idx, t, Tp, cstate, out_c,
+                                                       tc ? hplanes : nullptr, B);
+            VQ_CUDA(cudaGetLastError());
+            count_launch(1);
+        }
+        return VQCPC_OK;
+    }
     LstmParams prm{};
     prm.table = table;
     prm.idx = idx;
@@ -522,7 +593,7 @@ int lstm_forward(const vqcpc_encoder_weights* w, const int64_t* idx, int B, int 
 static size_t encoder_ws_bytes(int B, int T, int C, int mode) {
     const int Tp = T >= 2 ? (T - 2) / 2 + 1 : 0;
     const size_t M = static_cast<size_t>(B) * Tp;
-    size_t n = align_up(lstm_ws_bytes(), 256) + 2 * align_up(M * C * sizeof(float), 256) +
+    size_t n = align_up(lstm_ws_bytes(B), 256) + 2 * align_up(M * C * sizeof(float), 256) +
                align_up(M * VQ_D * sizeof(float), 256);
     if (mode == VQCPC_GEMM_BF16X3) n += align_up(M * 2 * (C > 320 ? C : 320) * 2, 256);   // bf16 planes of the A operand
     return n;
@@ -544,7 +615,7 @@ int encoder_forward(const vqcpc_encoder_weights* w, const float* mel, int B, int
     unsigned char* base = static_cast<unsigned char*>(ws);
     void* lstm_ws = base;
     WorkspaceHeader* hdr = reinterpret_cast<WorkspaceHeader*>(base);
-    size_t off = align_up(lstm_ws_bytes(), 256);
+    size_t off = align_up(lstm_ws_bytes(B), 256);
     float* act[2];
     act[0] = reinterpret_cast<float*>(base + off); off += align_up(M * C * sizeof(float), 256);
     act[1] = reinterpret_cast<float*>(base + off); off += align_up(M * C * sizeof(float), 256);
@@ -588,7 +659,7 @@ int encoder_forward(const vqcpc_encoder_weights* w, const float* mel, int B, int
         if ((rc = gemm_tc(planes, w->proj_wp, w->proj_b, zpre, VQ_D, static_cast<int>(M), VQ_D, C, 3, &hdr->status, stream))) return rc;
     }
     if ((rc = vq_lookup(zpre, w->codebook, M, VQ_M, VQ_D, out_z, out_idx, stream))) return rc;
-    return lstm_forward(w, out_idx, B, Tp, lstm_ws, lstm_ws_bytes(), out_c, stream, mode == VQCPC_GEMM_FP32);
+    return lstm_forward(w, out_idx, B, Tp, lstm_ws, lstm_ws_bytes(B), out_c, stream, mode == VQCPC_GEMM_FP32, mode);
 }
 
 }  // namespace vqcpc
@@ -622,8 +693,8 @@ extern "C" int vqcpc_encoder_forward(const vqcpc_encoder_weights* w, const float
                                   out_hidden, VQCPC_GEMM_FP32, static_cast<cudaStream_t>(stream));
 }
 extern "C" size_t vqcpc_lstm_workspace_bytes(int32_t B, int32_t Tp) {
-    (void)B; (void)Tp;
-    return vqcpc::lstm_ws_bytes();
+    (void)Tp;
+    return vqcpc::lstm_ws_bytes(B);
 }
 extern "C" int vqcpc_lstm_forward(const vqcpc_encoder_weights* w, const int64_t* idx, int32_t B, int32_t Tp,
                                   void* workspace, size_t workspace_bytes, float* out_c, void* stream) {

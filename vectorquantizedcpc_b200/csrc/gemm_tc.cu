@@ -284,24 +284,44 @@ static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mw, const TcParam
 }
 
 // A planes (M x nplanes*K) bf16, W planes (N x nplanes*K) bf16 with nplanes = (nseg == 3 ? 2 : 1).
-int gemm_tc(const void* a_planes, const void* w_planes, const float* bias, float* C, long long ldc, int M, int N, int K,
-            int nseg, int* err_flag, cudaStream_t stream) {
-    if (M == 0) return VQCPC_OK;
-    VQ_ARG(a_planes && w_planes && C && err_flag, "gemm_tc: null pointer");
+// A plan holds the two tensor maps so that a GEMM repeated on the same buffers (the LSTM's per-step product)
+// encodes them once.
+int gemm_tc_plan(TcPlan* plan, const void* a_planes, const void* w_planes, const float* bias, float* C, long long ldc, int M,
+                 int N, int K, int nseg, int* err_flag) {
+    VQ_ARG(plan && a_planes && w_planes && C && err_flag, "gemm_tc: null pointer");
+    VQ_ARG(M > 0, "gemm_tc: empty problem");
     VQ_ARG(nseg == 1 || nseg == 3, "gemm_tc: nseg must be 1 or 3");
     VQ_ARG(K % TC_BK == 0 && K > 0, "gemm_tc: K=%d must be a multiple of %d", K, TC_BK);
     VQ_ARG(N % 64 == 0 && ldc % 4 == 0, "gemm_tc: N=%d must be a multiple of 64", N);
+    static_assert(sizeof(CUtensorMap) == sizeof(plan->map_a), "TcPlan map storage");
     const int planes = nseg == 3 ? 2 : 1;
-    const int BN = (N % 256 == 0) ? 256 : (N % 128 == 0 ? 128 : 64);
-    CUtensorMap ma, mw;
-    int rc = make_map(&ma, a_planes, M, static_cast<long long>(planes) * K, static_cast<long long>(planes) * K, TC_BM);
+    plan->bn = (N % 256 == 0) ? 256 : (N % 128 == 0 ? 128 : 64);
+    int rc = make_map(reinterpret_cast<CUtensorMap*>(plan->map_a), a_planes, M, static_cast<long long>(planes) * K,
+                      static_cast<long long>(planes) * K, TC_BM);
     if (rc) return rc;
-    rc = make_map(&mw, w_planes, N, static_cast<long long>(planes) * K, static_cast<long long>(planes) * K, BN);
+    rc = make_map(reinterpret_cast<CUtensorMap*>(plan->map_w), w_planes, N, static_cast<long long>(planes) * K,
+                  static_cast<long long>(planes) * K, plan->bn);
     if (rc) return rc;
-    TcParams p{C, bias, err_flag, ldc, M, N, K, nseg};
-    if (BN == 256) return launch_tc<256>(ma, mw, p, stream);
-    if (BN == 128) return launch_tc<128>(ma, mw, p, stream);
+    plan->C = C; plan->bias = bias; plan->err = err_flag; plan->ldc = ldc; plan->M = M; plan->N = N; plan->K = K; plan->nseg = nseg;
+    return VQCPC_OK;
+}
+
+int gemm_tc_run(const TcPlan* plan, cudaStream_t stream) {
+    const CUtensorMap& ma = *reinterpret_cast<const CUtensorMap*>(plan->map_a);
+    const CUtensorMap& mw = *reinterpret_cast<const CUtensorMap*>(plan->map_w);
+    TcParams p{plan->C, plan->bias, plan->err, plan->ldc, plan->M, plan->N, plan->K, plan->nseg};
+    if (plan->bn == 256) return launch_tc<256>(ma, mw, p, stream);
+    if (plan->bn == 128) return launch_tc<128>(ma, mw, p, stream);
     return launch_tc<64>(ma, mw, p, stream);
+}
+
+int gemm_tc(const void* a_planes, const void* w_planes, const float* bias, float* C, long long ldc, int M, int N, int K,
+            int nseg, int* err_flag, cudaStream_t stream) {
+    if (M == 0) return VQCPC_OK;
+    TcPlan plan;
+    int rc = gemm_tc_plan(&plan, a_planes, w_planes, bias, C, ldc, M, N, K, nseg, err_flag);
+    if (rc) return rc;
+    return gemm_tc_run(&plan, stream);
 }
 
 // ---------------------------------------------------------------------------------------------- bf16 hi/lo planes

@@ -13,6 +13,14 @@ int gemm_conv(const float* mel, int B, int T, int Cin, const float* W, float* C,
 // gemm_tc.cu  (tcgen05 / TMEM / TMA)
 int gemm_tc(const void* a_planes, const void* w_planes, const float* bias, float* C, long long ldc, int M, int N, int K,
             int nseg, int* err_flag, cudaStream_t stream);
+struct TcPlan {                      // a tcgen05 GEMM bound to fixed operand buffers (tensor maps encoded once)
+    alignas(64) unsigned char map_a[128];
+    alignas(64) unsigned char map_w[128];
+    float* C; const float* bias; int* err; long long ldc; int M, N, K, nseg, bn;
+};
+int gemm_tc_plan(TcPlan* plan, const void* a_planes, const void* w_planes, const float* bias, float* C, long long ldc, int M,
+                 int N, int K, int nseg, int* err_flag);
+int gemm_tc_run(const TcPlan* plan, cudaStream_t stream);
 int split_planes(const float* x, long long ld, void* out, long long rows, int K, cudaStream_t stream);
 
 // encoder.cu

@@ -166,6 +166,7 @@ class Encoder(nn.Module):
         for i, t in enumerate((f0, f1, f2, f3)):
             w.fc_wp[i] = planes(t)
         w.proj_wp = planes(pw)
+        w.lstm_whh_p = planes(whh)
         self._packed, self._packed_key = (w, keep), key
         return self._packed
 
