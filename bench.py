@@ -333,16 +333,28 @@ def main():
             mel = fixtures.synthetic_mel(1, 200, seed=0).to(dev)
             with torch.no_grad():
                 ms = timed(lambda: enc.encode(mel), 20, 3) / 20
-            extra[f"encode_1utt_2s_c{Cc}"] = {"ms": ms, "frames_per_s": 100 / (ms * 1e-3)}
+            extra[f"encode_1utt_2s_c{Cc}"] = {"ms": ms, "frames_per_s": 100 / (ms * 1e-3), "gemm_mode": "fp32"}
             if Cc == 768:
-                # configs[3] (per-GPU share at 8 GPUs = 512 utterances x 3 s): batched encode throughput
-                melb = fixtures.synthetic_mel(512, 300, seed=0).to(dev)
-                with torch.no_grad():
-                    ms = timed(lambda: enc.encode(melb), 3, 3) / 3
-                frames = 512 * 150
-                extra["encode_batch_512x3s_c768"] = {"ms": ms, "frames_per_s": frames / (ms * 1e-3),
-                                                     "tflops_fp32": frames * 6.029e6 / (ms * 1e-3) / 1e12}
-                del melb
+                # configs[3]: batched encode, 512 utterances x 3 s (the per-GPU share at 8 GPUs) and all 4096 on one GPU;
+                # tcgen05 bf16 hi/lo-split GEMMs ("bf16x3", fp32-grade) and the fp32 CUDA-core parity path
+                for Bb in (512, 4096):
+                    melb = fixtures.synthetic_mel(Bb, 300, seed=0).to(dev)
+                    for gm in ("bf16x3", "fp32"):
+                        if gm == "fp32" and Bb == 4096:
+                            continue
+                        enc.gemm_mode = gm
+                        with torch.no_grad():
+                            ms = timed(lambda: enc.encode(melb), 3, 3) / 3
+                        frames = Bb * 150
+                        extra[f"encode_batch_{Bb}x3s_c768_{gm}"] = {
+                            "ms": ms, "frames_per_s": frames / (ms * 1e-3),
+                            "tflops_fp32_equivalent": frames * 6.029e6 / (ms * 1e-3) / 1e12,
+                            "roofline": {"bound": "tensor", "unit": "TFLOP/s",
+                                         "achieved": frames * 6.029e6 * (3 if gm == "bf16x3" else 1) / (ms * 1e-3) / 1e12,
+                                         "peak": peaks["bf16_tflops_sustained"] if gm == "bf16x3" else None,
+                                         "note": "whole encode (GEMMs + LN + VQ + LSTM); bf16x3 issues 3 MMA terms per product"}}
+                    del melb
+                enc.gemm_mode = "auto"
         line["extra"] = extra
 
     # ---- CPU baseline (rank 0, N = 1): the restated reference loop on the host cores, bounded sample
