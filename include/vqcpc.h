@@ -116,6 +116,10 @@ int vqcpc_layernorm_relu_f32(float* x, const float* w, const float* b, int64_t r
  * |e|^2 - 2 x.e (fp32; the |x|^2 term of model.py:107-110 is argmin-invariant and is not added). */
 int vqcpc_vq_lookup(const float* x, const float* codebook, int64_t n_frames, int32_t n_codes, int32_t dim,
                     float* out_q, int64_t* out_idx, void* stream);
+/* For n_frames >= 8192 the search runs on the tensor cores (tcgen05 coarse pass over bf16 hi/lo planes, exact fp32
+ * re-decision of every frame whose best two candidates are within the coarse error bound), with identical results.
+ * vqcpc_vq_check_status synchronises `stream` and returns VQCPC_ERR_TIMEOUT if that pipeline ever timed out. */
+int vqcpc_vq_check_status(void* stream);
 
 /* ------------------------------------------------------------------ Encoder.encode -- model.py:59-70
  * mel (B, 80, T) fp32 -> out_z (B, T', 64) quantised, out_c (B, T', 256), out_idx (B, T') int64,

@@ -141,6 +141,28 @@ def test_vq_lookup_matches_oracle_and_golden(golden_dir, kind):
     print(f"[vq {kind}] vs oracle {rep} | vs golden {rep_g} | vs fp64 {rep_t}")
 
 
+@pytest.mark.parametrize("kind", ["init", "trained"])
+def test_vq_tensor_core_path_equals_fp32_path(kind):
+    """n >= 8192 runs the tcgen05 coarse pass + exact recheck; it must reproduce the fp32 kernel's indices exactly
+    (compared by running the same frames in chunks below the threshold), including a ragged tail and exact ties."""
+    n = 50_000 + 37
+    x, cb = fixtures.vq_inputs(n, kind=kind, seed=77)
+    cb[300] = cb[7]                                   # exact duplicate code: ties must go to index 7
+    x[0, :5] = cb[7]
+    vq = VQEmbeddingEMA(512, 64)
+    vq.embedding.copy_(cb)
+    vq = vq.to(dev())
+    xd = x.to(dev())
+    q, idx = vq.encode(xd)
+    parts = [vq.encode(xd[:, i:i + 4096])[1] for i in range(0, n, 4096)]
+    idx_ref = torch.cat(parts, dim=1)
+    nbad = int((idx != idx_ref).sum())
+    print(f"[vq tc vs fp32, {kind}] mismatches {nbad} / {n}")
+    assert nbad == 0
+    assert idx[0, :5].tolist() == [7] * 5
+    assert torch.equal(q, cb.to(dev())[idx])
+
+
 def test_vq_exact_tie_and_ragged_sizes():
     x, cb = fixtures.vq_inputs(16, kind="trained", seed=5)
     cb[300] = cb[7]

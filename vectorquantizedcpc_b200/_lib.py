@@ -55,6 +55,7 @@ SIGNATURES = {
     "vqcpc_split_planes": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _vp]),
     "vqcpc_layernorm_relu_f32": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _vp]),
     "vqcpc_vq_lookup": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp]),
+    "vqcpc_vq_check_status": (C.c_int, [_vp]),
     "vqcpc_encoder_workspace_bytes": (_sz, [_i32, _i32, _i32]),
     "vqcpc_encoder_forward": (C.c_int, [C.POINTER(EncoderWeights), _vp, _i32, _i32, _vp, _sz, _vp, _vp, _vp, _vp, _vp, _vp]),
     "vqcpc_encoder_workspace_bytes_ex": (_sz, [_i32, _i32, _i32, _i32]),

@@ -306,6 +306,13 @@ int vq_lookup(const float* x, const float* codebook, int64_t n, int n_codes, int
     return VQCPC_OK;
 }
 
+int vq_lookup_auto(const float* x, const float* codebook, int64_t n, float* q, int64_t* idx, void* planes_ws, int* err,
+                   cudaStream_t stream) {
+    if (planes_ws != nullptr && err != nullptr && n >= VQ_TC_MIN_FRAMES)
+        return vq_lookup_tc(x, codebook, n, q, idx, planes_ws, err, stream);
+    return vq_lookup(x, codebook, n, VQ_M, VQ_D, q, idx, stream);
+}
+
 // ------------------------------------------------------------------------------------------------
 // LSTM(64 -> 256) over the quantised codes (model.py:57,69).
 //   x-projection: z_q takes only 512 values, so  W_ih z_q[t] + b_ih + b_hh = table[idx[t]]  with
@@ -594,8 +601,8 @@ static size_t encoder_ws_bytes(int B, int T, int C, int mode) {
     const int Tp = T >= 2 ? (T - 2) / 2 + 1 : 0;
     const size_t M = static_cast<size_t>(B) * Tp;
     size_t n = align_up(lstm_ws_bytes(B), 256) + 2 * align_up(M * C * sizeof(float), 256) +
-               align_up(M * VQ_D * sizeof(float), 256);
-    if (mode == VQCPC_GEMM_BF16X3) n += align_up(M * 2 * (C > 320 ? C : 320) * 2, 256);   // bf16 planes of the A operand
+               align_up(M * VQ_D * sizeof(float), 256) + align_up(VQ_TC_PLANES_BYTES, 1024);
+    if (mode == VQCPC_GEMM_BF16X3) n += align_up(M * 2 * (C > 320 ? C : 320) * 2, 256) + 1024;   // bf16 planes of the A operand
     return n;
 }
 
@@ -620,10 +627,13 @@ int encoder_forward(const vqcpc_encoder_weights* w, const float* mel, int B, int
     act[0] = reinterpret_cast<float*>(base + off); off += align_up(M * C * sizeof(float), 256);
     act[1] = reinterpret_cast<float*>(base + off); off += align_up(M * C * sizeof(float), 256);
     float* zpre_ws = reinterpret_cast<float*>(base + off); off += align_up(M * VQ_D * sizeof(float), 256);
+    off = align_up(off, 1024);
+    void* vq_planes = base + off; off += align_up(VQ_TC_PLANES_BYTES, 1024);
     float* zpre = out_prevq ? out_prevq : zpre_ws;
 
     int rc;
     if (mode == VQCPC_GEMM_FP32) {
+        VQ_CUDA(cudaMemsetAsync(hdr, 0, sizeof(WorkspaceHeader), stream));
         if ((rc = gemm_conv(mel, B, T, 80, w->conv_w, act[0], C, stream))) return rc;
         if ((rc = layernorm_relu(act[0], w->ln_w[0], w->ln_b[0], M, C, stream))) return rc;
         int cur = 0;
@@ -658,8 +668,9 @@ int encoder_forward(const vqcpc_encoder_weights* w, const float* mel, int B, int
         }
         if ((rc = gemm_tc(planes, w->proj_wp, w->proj_b, zpre, VQ_D, static_cast<int>(M), VQ_D, C, 3, &hdr->status, stream))) return rc;
     }
-    if ((rc = vq_lookup(zpre, w->codebook, M, VQ_M, VQ_D, out_z, out_idx, stream))) return rc;
-    return lstm_forward(w, out_idx, B, Tp, lstm_ws, lstm_ws_bytes(B), out_c, stream, mode == VQCPC_GEMM_FP32, mode);
+    // the nearest-code search is exact in both modes (tensor-core coarse pass + exact recheck, or the fp32 kernel)
+    if ((rc = vq_lookup_auto(zpre, w->codebook, M, out_z, out_idx, vq_planes, &hdr->status, stream))) return rc;
+    return lstm_forward(w, out_idx, B, Tp, lstm_ws, lstm_ws_bytes(B), out_c, stream, false, mode);
 }
 
 }  // namespace vqcpc
@@ -669,9 +680,35 @@ extern "C" int vqcpc_layernorm_relu_f32(float* x, const float* w, const float* b
                                         void* stream) {
     return vqcpc::layernorm_relu(x, w, b, rows, C, static_cast<cudaStream_t>(stream));
 }
+namespace vqcpc {
+// per-device scratch of the standalone VQ entry point: [status int | pad to 1 KB | codebook planes 128 KB]
+static void* vq_scratch() {
+    static void* buf[64] = {nullptr};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    if (buf[dev] == nullptr) {
+        if (cudaMalloc(&buf[dev], 1024 + VQ_TC_PLANES_BYTES) != cudaSuccess) return nullptr;
+        cudaMemset(buf[dev], 0, 1024);
+    }
+    return buf[dev];
+}
+}  // namespace vqcpc
 extern "C" int vqcpc_vq_lookup(const float* x, const float* codebook, int64_t n_frames, int32_t n_codes, int32_t dim,
                                float* out_q, int64_t* out_idx, void* stream) {
-    return vqcpc::vq_lookup(x, codebook, n_frames, n_codes, dim, out_q, out_idx, static_cast<cudaStream_t>(stream));
+    using namespace vqcpc;
+    if (n_frames == 0) return VQCPC_OK;
+    VQ_ARG(n_codes == VQ_M && dim == VQ_D, "vq_lookup: only a 512x64 codebook is supported (got %dx%d)", n_codes, dim);
+    unsigned char* s = static_cast<unsigned char*>(vq_scratch());
+    if (s == nullptr) return vq_lookup(x, codebook, n_frames, n_codes, dim, out_q, out_idx, static_cast<cudaStream_t>(stream));
+    return vq_lookup_auto(x, codebook, n_frames, out_q, out_idx, s + 1024, reinterpret_cast<int*>(s),
+                          static_cast<cudaStream_t>(stream));
+}
+// status word of the standalone VQ entry point (synchronises the stream): 0 ok, VQCPC_ERR_TIMEOUT if the tensor-core
+// pipeline timed out since the last check.
+extern "C" int vqcpc_vq_check_status(void* stream) {
+    void* s = vqcpc::vq_scratch();
+    if (s == nullptr) return VQCPC_OK;
+    return vqcpc_check_status(s, stream);
 }
 extern "C" size_t vqcpc_encoder_workspace_bytes(int32_t B, int32_t T, int32_t channels) {
     return vqcpc::encoder_ws_bytes(B, T, channels, VQCPC_GEMM_FP32);

@@ -27,6 +27,13 @@ int split_planes(const float* x, long long ld, void* out, long long rows, int K,
 int layernorm_relu(float* x, const float* w, const float* b, int64_t rows, int C, cudaStream_t stream);
 int vq_lookup(const float* x, const float* codebook, int64_t n, int n_codes, int dim, float* q, int64_t* idx,
               cudaStream_t stream);
+// tensor-core search (vq_tc.cu); vq_lookup_auto picks it for n >= VQ_TC_MIN_FRAMES when scratch is provided
+constexpr int64_t VQ_TC_MIN_FRAMES = 8192;
+constexpr size_t VQ_TC_PLANES_BYTES = 512 * 128 * 2;
+int vq_lookup_tc(const float* x, const float* codebook, int64_t n, float* q, int64_t* idx, void* planes_ws, int* err,
+                 cudaStream_t stream);
+int vq_lookup_auto(const float* x, const float* codebook, int64_t n, float* q, int64_t* idx, void* planes_ws, int* err,
+                   cudaStream_t stream);
 
 // persistent-kernel workspace header (first bytes of every workspace handed to a persistent kernel)
 struct WorkspaceHeader {

@@ -1,0 +1,383 @@
+// VQ nearest-code search on the tensor cores (VQEmbeddingEMA.encode, /root/reference/model.py:103-115).
+//
+//   score[n, m] = |e_m|^2 - 2 x_n . e_m      idx[n] = first argmin_m score[n, m]      q[n] = e[idx[n]]
+//
+// HBM-bound by construction: x is read once (256 B/frame), q and idx written once (264 B/frame); the 512 x 64
+// distance contraction never leaves the SM:
+//   * the codebook lives in shared memory for the whole kernel as bf16 hi/lo planes of (-2 e) (128 KB, loaded once
+//     by TMA, SWIZZLE_128B) -- the factor -2 is exact in bf16, so the MMA yields -2 x.e directly;
+//   * converter warps turn each 128-frame tile of fp32 x into bf16 hi/lo planes written straight into the UMMA
+//     K-major SWIZZLE_128B layout (generic-proxy stores + fence.proxy.async), double buffered;
+//   * one thread issues tcgen05.mma (M=128, N=256, K=16): three K-segments (x_hi e_hi + x_hi e_lo + x_lo e_hi) per
+//     256-code half; the two halves of a tile are the two TMEM accumulators, so the MMAs of one half overlap the
+//     argmin epilogue of the other;
+//   * epilogue warps (thread = frame) read the accumulators with tcgen05.ld, add |e|^2 and keep the best two
+//     candidates.  The coarse scores carry an error <= 2^-15 |x| max|e|; a frame whose best two are closer than twice
+//     that is re-decided with exact fp32 scores of both candidates (same arithmetic as the fp32 kernel), ties to
+//     the lower index.  Everything else is exact already, so the result equals the fp32 path's.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace vqcpc {
+
+// PTX wrappers shared with gemm_tc.cu (kept local: both files are self-contained translation units)
+namespace vqtc {
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, int* err) {
+    if (mbar_try_wait(bar, parity)) return true;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) { atomicExch(err, VQCPC_ERR_TIMEOUT); return false; }
+    }
+    return true;
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{ .reg .pred p; setp.ne.b32 p, %4, 0; tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p; }"
+                 ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3fff);
+    d |= static_cast<uint64_t>(1) << 16;
+    d |= static_cast<uint64_t>(1024 >> 4) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(2) << 61;
+    return d;
+}
+}  // namespace vqtc
+using namespace vqtc;
+
+constexpr int VT_D = 64, VT_M = 512, VT_TF = 128;
+constexpr int VT_MMA_WARP = 0, VT_CONV_WARP0 = 1, VT_EPI_WARP0 = 5, VT_THREADS = 9 * 32;
+constexpr uint32_t VT_CB_HALF = 256 * 128;                 // bytes of one (plane, half) block of the codebook: 256 rows x 128 B
+constexpr uint32_t VT_CB_BYTES = 4 * VT_CB_HALF;           // hi/lo x two halves = 128 KB
+constexpr uint32_t VT_PLANE = VT_TF * 128;                 // 16 KB: one bf16 plane of an x tile
+constexpr uint32_t VT_XBUF = 2 * VT_PLANE;                 // hi + lo
+constexpr size_t VT_SMEM = VT_CB_BYTES + 2 * VT_XBUF + 1024;
+constexpr uint32_t VT_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(256 >> 3) << 17) |
+                              (static_cast<uint32_t>(128 >> 4) << 24);
+
+struct VqTcParams {
+    const float* x;          // (n, 64)
+    const float* codebook;   // (512, 64) fp32
+    float* out_q;            // (n, 64)
+    int64_t* out_idx;        // (n,)
+    int* err;
+    long long n;
+};
+
+__global__ void __launch_bounds__(VT_THREADS, 1) vq_tc_kernel(const __grid_constant__ CUtensorMap map_cb, VqTcParams p) {
+    extern __shared__ __align__(1024) unsigned char vt_smem[];
+    __shared__ __align__(8) uint64_t cb_bar, xfull_bar[2], xempty_bar[2], tfull_bar[2], tempty_bar[2];
+    __shared__ uint32_t tmem_base_slot;
+    __shared__ float e2s[VT_M];
+    __shared__ float xnorm[2][VT_TF];
+    __shared__ float emax_s;
+
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(vt_smem) + 1023) & ~uintptr_t(1023));
+    unsigned char* cb_s = smem;                       // [plane][half][256 rows][128 B]
+    unsigned char* x_s = smem + VT_CB_BYTES;          // [buf][plane][128 rows][128 B]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        mbar_init(&cb_bar, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&xfull_bar[i], 4);              // one arrival per converter warp
+            mbar_init(&xempty_bar[i], 1);             // tcgen05.commit
+            mbar_init(&tfull_bar[i], 1);              // tcgen05.commit
+            mbar_init(&tempty_bar[i], 4);             // one arrival per epilogue warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == VT_MMA_WARP) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(512)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    // |e_m|^2 with the fp32 kernel's arithmetic (sequential FMA over k) and max |e_m|
+    for (int m = threadIdx.x; m < VT_M; m += VT_THREADS) {
+        const float* e = p.codebook + m * VT_D;
+        float s = 0.f;
+#pragma unroll 8
+        for (int k = 0; k < VT_D; ++k) s = fmaf(__ldg(e + k), __ldg(e + k), s);
+        e2s[m] = s;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (threadIdx.x < 32) {
+        float mx = 0.f;
+        for (int m = lane; m < VT_M; m += 32) mx = fmaxf(mx, e2s[m]);
+        mx = warp_max(mx);
+        if (lane == 0) emax_s = sqrtf(mx);
+    }
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(&cb_bar, VT_CB_BYTES);
+        for (int plane = 0; plane < 2; ++plane)
+            for (int half = 0; half < 2; ++half)
+                tma_load_2d(cb_s + (plane * 2 + half) * VT_CB_HALF, &map_cb, plane * VT_D, half * 256, &cb_bar);
+    }
+    __syncthreads();
+    const uint32_t tmem_base = tmem_base_slot;
+    const long long n_tiles = (p.n + VT_TF - 1) / VT_TF;
+
+    if (warp == VT_MMA_WARP) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            bool ok = mbar_wait(&cb_bar, 0, p.err);
+            uint32_t xphase[2] = {0, 0}, tphase[2] = {0, 0};
+            int it = 0;
+            for (long long tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x, ++it) {
+                const int buf = it & 1;
+                ok = mbar_wait(&xfull_bar[buf], xphase[buf], p.err);       // planes of this tile are in shared memory
+                if (!ok) break;
+                xphase[buf] ^= 1;
+                tc_fence_after();
+                const uint32_t xa = smem_u32(x_s + buf * VT_XBUF);
+                const uint64_t a_hi = umma_desc_sw128(xa), a_lo = umma_desc_sw128(xa + VT_PLANE);
+                for (int half = 0; half < 2 && ok; ++half) {
+                    ok = mbar_wait(&tempty_bar[half], tphase[half] ^ 1, p.err);   // epilogue drained this accumulator
+                    if (!ok) break;
+                    tc_fence_after();
+                    const uint32_t cb = smem_u32(cb_s);
+                    const uint64_t b_hi = umma_desc_sw128(cb + (0 * 2 + half) * VT_CB_HALF);
+                    const uint64_t b_lo = umma_desc_sw128(cb + (1 * 2 + half) * VT_CB_HALF);
+                    const uint32_t d = tmem_base + half * 256;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) tc_mma_f16(d, a_hi + 2 * k, b_hi + 2 * k, VT_IDESC, k > 0 ? 1u : 0u);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) tc_mma_f16(d, a_hi + 2 * k, b_lo + 2 * k, VT_IDESC, 1u);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) tc_mma_f16(d, a_lo + 2 * k, b_hi + 2 * k, VT_IDESC, 1u);
+                    tc_commit(&tfull_bar[half]);
+                    tphase[half] ^= 1;
+                }
+                tc_commit(&xempty_bar[buf]);                               // planes buffer reusable
+            }
+        }
+    } else if (warp < VT_EPI_WARP0) {
+        // ------------------------------------------------------------------ converters: fp32 x -> bf16 hi/lo planes
+        // item (row r, 16-byte chunk c): thread t of the 128 handles c = t & 7, rows r = (t >> 3) + 16 j, j < 8.
+        const int t = threadIdx.x - 32 * VT_CONV_WARP0;
+        const int c = t & 7, r0 = t >> 3;
+        uint32_t ephase[2] = {0, 0};
+        bool ok = true;
+        int it = 0;
+        float4 cur[8][2];
+        auto load_tile = [&](long long tile, float4 (&dst)[8][2]) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const long long fr = tile * VT_TF + r0 + 16 * j;
+                if (fr < p.n) {
+                    const float4* src = reinterpret_cast<const float4*>(p.x + fr * VT_D + 8 * c);
+                    dst[j][0] = __ldg(src); dst[j][1] = __ldg(src + 1);
+                } else {
+                    dst[j][0] = make_float4(0.f, 0.f, 0.f, 0.f); dst[j][1] = dst[j][0];
+                }
+            }
+        };
+        if (blockIdx.x < n_tiles) load_tile(blockIdx.x, cur);
+        for (long long tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x, ++it) {
+            const int buf = it & 1;
+            ok = mbar_wait(&xempty_bar[buf], ephase[buf] ^ 1, p.err);      // MMAs of the tile two iterations ago are done
+            ok = __all_sync(0xffffffffu, ok);
+            if (!ok) break;
+            ephase[buf] ^= 1;
+            unsigned char* hi = x_s + buf * VT_XBUF;
+            unsigned char* lo = hi + VT_PLANE;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int r = r0 + 16 * j;
+                const float v[8] = {cur[j][0].x, cur[j][0].y, cur[j][0].z, cur[j][0].w, cur[j][1].x, cur[j][1].y, cur[j][1].z, cur[j][1].w};
+                __nv_bfloat162 h2[4], l2[4];
+                float ss = 0.f;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const __nv_bfloat16 ha = __float2bfloat16_rn(v[2 * q]), hb = __float2bfloat16_rn(v[2 * q + 1]);
+                    h2[q] = __halves2bfloat162(ha, hb);
+                    l2[q] = __halves2bfloat162(__float2bfloat16_rn(v[2 * q] - __bfloat162float(ha)),
+                                               __float2bfloat16_rn(v[2 * q + 1] - __bfloat162float(hb)));
+                    ss = fmaf(v[2 * q], v[2 * q], ss);
+                    ss = fmaf(v[2 * q + 1], v[2 * q + 1], ss);
+                }
+                // SWIZZLE_128B: 16-byte chunk c of row r lives at chunk (c ^ (r & 7)) of that row's 128 bytes
+                const uint32_t off = r * 128 + ((c ^ (r & 7)) << 4);
+                *reinterpret_cast<uint4*>(hi + off) = *reinterpret_cast<const uint4*>(h2);
+                *reinterpret_cast<uint4*>(lo + off) = *reinterpret_cast<const uint4*>(l2);
+                ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+                ss += __shfl_xor_sync(0xffffffffu, ss, 2);
+                ss += __shfl_xor_sync(0xffffffffu, ss, 4);
+                if (c == 0) xnorm[buf][r] = sqrtf(ss);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic-proxy stores -> visible to tcgen05.mma
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&xfull_bar[buf]);
+            if (tile + gridDim.x < n_tiles) load_tile(tile + gridDim.x, cur);   // prefetch the next tile's rows
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue: top-2 argmin, exact recheck, gather
+        const int quarter = warp & 3;
+        const int row = quarter * 32 + lane;
+        uint32_t tphase[2] = {0, 0};
+        bool ok = true;
+        int it = 0;
+        const float emax = emax_s;
+        for (long long tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x, ++it) {
+            const int buf = it & 1;
+            float b1 = INFINITY, b2 = INFINITY, xn = 0.f;
+            int i1 = 0, i2 = 0;
+            for (int half = 0; half < 2 && ok; ++half) {
+                ok = mbar_wait(&tfull_bar[half], tphase[half], p.err);
+                ok = __all_sync(0xffffffffu, ok);
+                if (!ok) break;
+                tphase[half] ^= 1;
+                tc_fence_after();
+                if (half == 0) xn = xnorm[buf][row];      // read now: the converters may refill this slot two tiles later
+#pragma unroll 1
+                for (int c0 = 0; c0 < 256; c0 += 32) {
+                    uint32_t v[32];
+                    tc_ld32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + half * 256 + c0, v);
+                    tc_wait_ld();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int m = half * 256 + c0 + j;
+                        const float s = e2s[m] + __uint_as_float(v[j]);      // |e|^2 + (-2 x.e)
+                        if (s < b1) { b2 = b1; i2 = i1; b1 = s; i1 = m; }
+                        else if (s < b2) { b2 = s; i2 = m; }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty_bar[half]);
+            }
+            if (!ok) break;
+            const long long fr = tile * VT_TF + row;
+            if (fr < p.n) {
+                const float margin = 6.2e-5f * xn * emax;      // 2 x (2^-15 |x| max|e|)
+                if (b2 - b1 <= margin) {
+                    // exact fp32 scores of both candidates (arithmetic of the fp32 kernel); ties -> lower index
+                    const float* xr = p.x + fr * VT_D;
+                    const float* ea = p.codebook + i1 * VT_D;
+                    const float* eb = p.codebook + i2 * VT_D;
+                    float da = 0.f, db = 0.f;
+#pragma unroll 8
+                    for (int k = 0; k < VT_D; ++k) {
+                        const float xv = __ldg(xr + k);
+                        da = fmaf(xv, __ldg(ea + k), da);
+                        db = fmaf(xv, __ldg(eb + k), db);
+                    }
+                    const float sa = fmaf(-2.0f, da, e2s[i1]), sb = fmaf(-2.0f, db, e2s[i2]);
+                    if (sb < sa || (sb == sa && i2 < i1)) i1 = i2;
+                }
+                p.out_idx[fr] = i1;
+                const float4* src = reinterpret_cast<const float4*>(p.codebook + i1 * VT_D);
+                float4* dst = reinterpret_cast<float4*>(p.out_q + fr * VT_D);
+#pragma unroll
+                for (int k = 0; k < VT_D / 4; ++k) dst[k] = __ldg(src + k);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == VT_MMA_WARP) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
+// scaled split: planes of (scale * x)
+__global__ void split_scaled_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int rows, int K, float scale) {
+    const int total = rows * K;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int r = i / K, k = i % K;
+        const float v = scale * x[i];
+        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+        out[r * 2 * K + k] = h;
+        out[r * 2 * K + K + k] = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
+}
+
+typedef CUresult (*PFN_encodeTiled2)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// planes_ws: 128 KB device scratch for the codebook planes; err: device int
+int vq_lookup_tc(const float* x, const float* codebook, int64_t n, float* q, int64_t* idx, void* planes_ws, int* err,
+                 cudaStream_t stream) {
+    if (n == 0) return VQCPC_OK;
+    VQ_ARG(x && codebook && q && idx && planes_ws && err, "vq_lookup_tc: null pointer");
+    static PFN_encodeTiled2 fn = nullptr;
+    if (fn == nullptr) {
+        void* fp = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &qr) != cudaSuccess ||
+            qr != cudaDriverEntryPointSuccess) {
+            set_error("vq_lookup_tc: cuTensorMapEncodeTiled is unavailable");
+            return VQCPC_ERR_CUDA;
+        }
+        fn = reinterpret_cast<PFN_encodeTiled2>(fp);
+    }
+    split_scaled_kernel<<<64, 256, 0, stream>>>(codebook, static_cast<__nv_bfloat16*>(planes_ws), VT_M, VT_D, -2.0f);
+    VQ_CUDA(cudaGetLastError());
+    count_launch(1);
+    CUtensorMap map;
+    cuuint64_t gdim[2] = {2 * VT_D, VT_M};
+    cuuint64_t gstr[1] = {2 * VT_D * 2};
+    cuuint32_t box[2] = {VT_D, 256};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, planes_ws, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("vq_lookup_tc: cuTensorMapEncodeTiled failed (%d)", static_cast<int>(r)); return VQCPC_ERR_CUDA; }
+    static bool attr_set = false;
+    if (!attr_set) {
+        VQ_CUDA(cudaFuncSetAttribute(vq_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(VT_SMEM)));
+        attr_set = true;
+    }
+    const long long n_tiles = (n + VT_TF - 1) / VT_TF;
+    const int sms = device_sm_count();
+    VqTcParams p{x, codebook, q, idx, err, static_cast<long long>(n)};
+    vq_tc_kernel<<<static_cast<unsigned>(n_tiles < sms ? n_tiles : sms), VT_THREADS, VT_SMEM, stream>>>(map, p);
+    VQ_CUDA(cudaGetLastError());
+    count_launch(1);
+    return VQCPC_OK;
+}
+
+}  // namespace vqcpc

@@ -69,7 +69,9 @@ class VQEmbeddingEMA(nn.Module):
         with torch.cuda.device(xf.device):
             st = _lib.lib().vqcpc_vq_lookup(_lib.ptr(xf), _lib.ptr(cb), B * T, cb.shape[0], D, _lib.ptr(q),
                                             _lib.ptr(idx), _lib.current_stream_ptr())
-        _lib.check(st, "VQEmbeddingEMA.encode")
+            _lib.check(st, "VQEmbeddingEMA.encode")
+            if B * T >= 8192:       # tensor-core pipeline: surface a device-side timeout instead of returning garbage
+                _lib.check(_lib.lib().vqcpc_vq_check_status(_lib.current_stream_ptr()), "VQEmbeddingEMA.encode")
         return q, idx
 
     def forward(self, x):
