@@ -270,7 +270,8 @@ def main():
     # algorithmic HBM bytes of one launch: weights read once + E' + G + uniforms in + wav out
     ar_bytes = 4 * (2688 * 896 + 256 * 896 + 256 * 256 + 2688 + 512 + 256 * 2688 + 2 * Tc * 2688 + 2 * L + 256)
     roofline = {"kernel": "ar_kernel", "bound": "hbm", "achieved": ar_bytes / (t_ar_ms * 1e-3) / 1e9,
-                "peak": peaks["hbm_gbs"], "unit": "GB/s", "traffic": None,
+                "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "traffic": 14.87e6 if (B == 1 and L == 16000) else None,   # ncu dram read+write per launch, profiles/r01_ncu_ar_summary.txt
                 "note": "latency-bound persistent kernel: see latency.us_per_step vs the exchange floor (DESIGN.md)",
                 "peak_source": peaks["source"]}
     roofline["frac"] = roofline["achieved"] / roofline["peak"]
@@ -320,9 +321,12 @@ def main():
             xd = x.to(dev)
             ms = timed(lambda: vq.encode(xd), 5, 3) / 5
             extra[f"vq_lookup_1M_{kind}"] = {"frames_per_s": 1e6 / (ms * 1e-3), "ms": ms,
-                                            "roofline": {"bound": "hbm", "achieved": 520e6 / (ms * 1e-3) / 1e9,
+                                            "roofline": {"kernel": "vq_tc_kernel", "bound": "hbm",
+                                                         "achieved": 520e6 / (ms * 1e-3) / 1e9,
                                                          "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                                                         "frac": 520e6 / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"]}}
+                                                         "frac": 520e6 / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                                                         "traffic": 470.2e6,   # ncu, profiles/r01_ncu_vq_tc_summary.txt
+                                                         "note": "timed through VQEmbeddingEMA.encode (includes the status sync)"}}
             del xd
         # configs[0]: Encoder.encode on one 2 s utterance (latency), C = 768 and 512
         for Cc in (768, 512):

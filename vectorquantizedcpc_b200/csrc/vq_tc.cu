@@ -17,6 +17,7 @@
 //     the lower index.  Everything else is exact already, so the result equals the fp32 path's.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "kernels.cuh"
@@ -82,11 +83,16 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
     d |= static_cast<uint64_t>(2) << 61;
     return d;
 }
+__device__ __forceinline__ float fmin3(float a, float b, float c) {
+    float d;
+    asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));     // FMNMX3
+    return d;
+}
 }  // namespace vqtc
 using namespace vqtc;
 
 constexpr int VT_D = 64, VT_M = 512, VT_TF = 128;
-constexpr int VT_MMA_WARP = 0, VT_CONV_WARP0 = 1, VT_EPI_WARP0 = 5, VT_THREADS = 9 * 32;
+constexpr int VT_MMA_WARP = 0, VT_CONV_WARP0 = 1, VT_EPI_WARP0 = 5, VT_EPI_WARPS = 8, VT_THREADS = (5 + VT_EPI_WARPS) * 32;
 constexpr uint32_t VT_CB_HALF = 256 * 128;                 // bytes of one (plane, half) block of the codebook: 256 rows x 128 B
 constexpr uint32_t VT_CB_BYTES = 4 * VT_CB_HALF;           // hi/lo x two halves = 128 KB
 constexpr uint32_t VT_PLANE = VT_TF * 128;                 // 16 KB: one bf16 plane of an x tile
@@ -102,15 +108,17 @@ struct VqTcParams {
     int64_t* out_idx;        // (n,)
     int* err;
     long long n;
+    int debug;               // bit 0: skip the argmin math, bit 1: skip the gather/output, bit 2: converters skip the x loads
 };
 
 __global__ void __launch_bounds__(VT_THREADS, 1) vq_tc_kernel(const __grid_constant__ CUtensorMap map_cb, VqTcParams p) {
     extern __shared__ __align__(1024) unsigned char vt_smem[];
     __shared__ __align__(8) uint64_t cb_bar, xfull_bar[2], xempty_bar[2], tfull_bar[2], tempty_bar[2];
     __shared__ uint32_t tmem_base_slot;
-    __shared__ float e2s[VT_M];
+    __shared__ __align__(16) float e2s[VT_M];
     __shared__ float xnorm[2][VT_TF];
     __shared__ float emax_s;
+    __shared__ float2 part[2][2][VT_TF];              // [tile parity][column half][row]: top-2 keys (double buffered)
 
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(vt_smem) + 1023) & ~uintptr_t(1023));
     unsigned char* cb_s = smem;                       // [plane][half][256 rows][128 B]
@@ -123,7 +131,7 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vq_tc_kernel(const __grid_const
             mbar_init(&xfull_bar[i], 4);              // one arrival per converter warp
             mbar_init(&xempty_bar[i], 1);             // tcgen05.commit
             mbar_init(&tfull_bar[i], 1);              // tcgen05.commit
-            mbar_init(&tempty_bar[i], 4);             // one arrival per epilogue warp
+            mbar_init(&tempty_bar[i], VT_EPI_WARPS);  // one arrival per epilogue warp
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -181,12 +189,16 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vq_tc_kernel(const __grid_const
                     const uint64_t b_hi = umma_desc_sw128(cb + (0 * 2 + half) * VT_CB_HALF);
                     const uint64_t b_lo = umma_desc_sw128(cb + (1 * 2 + half) * VT_CB_HALF);
                     const uint32_t d = tmem_base + half * 256;
+                    if (!(p.debug & 8)) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k) tc_mma_f16(d, a_hi + 2 * k, b_hi + 2 * k, VT_IDESC, k > 0 ? 1u : 0u);
+                    if (!(p.debug & 32)) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k) tc_mma_f16(d, a_hi + 2 * k, b_lo + 2 * k, VT_IDESC, 1u);
 #pragma unroll
                     for (int k = 0; k < 4; ++k) tc_mma_f16(d, a_lo + 2 * k, b_hi + 2 * k, VT_IDESC, 1u);
+                    }
+                    }
                     tc_commit(&tfull_bar[half]);
                     tphase[half] ^= 1;
                 }
@@ -206,7 +218,7 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vq_tc_kernel(const __grid_const
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const long long fr = tile * VT_TF + r0 + 16 * j;
-                if (fr < p.n) {
+                if (fr < p.n && !(p.debug & 4)) {
                     const float4* src = reinterpret_cast<const float4*>(p.x + fr * VT_D + 8 * c);
                     dst[j][0] = __ldg(src); dst[j][1] = __ldg(src + 1);
                 } else {
@@ -223,29 +235,39 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vq_tc_kernel(const __grid_const
             ephase[buf] ^= 1;
             unsigned char* hi = x_s + buf * VT_XBUF;
             unsigned char* lo = hi + VT_PLANE;
+            float ssq[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
+                if (p.debug & 16) break;
                 const int r = r0 + 16 * j;
                 const float v[8] = {cur[j][0].x, cur[j][0].y, cur[j][0].z, cur[j][0].w, cur[j][1].x, cur[j][1].y, cur[j][1].z, cur[j][1].w};
                 __nv_bfloat162 h2[4], l2[4];
                 float ss = 0.f;
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    const __nv_bfloat16 ha = __float2bfloat16_rn(v[2 * q]), hb = __float2bfloat16_rn(v[2 * q + 1]);
-                    h2[q] = __halves2bfloat162(ha, hb);
-                    l2[q] = __halves2bfloat162(__float2bfloat16_rn(v[2 * q] - __bfloat162float(ha)),
-                                               __float2bfloat16_rn(v[2 * q + 1] - __bfloat162float(hb)));
-                    ss = fmaf(v[2 * q], v[2 * q], ss);
-                    ss = fmaf(v[2 * q + 1], v[2 * q + 1], ss);
+                    const float a = v[2 * q], b = v[2 * q + 1];
+                    h2[q] = __floats2bfloat162_rn(a, b);                                  // one cvt.rn.bf16x2.f32
+                    const uint32_t hb = *reinterpret_cast<const uint32_t*>(&h2[q]);
+                    const float ha = __uint_as_float(hb << 16), hbv = __uint_as_float(hb & 0xffff0000u);
+                    l2[q] = __floats2bfloat162_rn(a - ha, b - hbv);
+                    ss = fmaf(a, a, ss);
+                    ss = fmaf(b, b, ss);
                 }
+                ssq[j] = ss;
                 // SWIZZLE_128B: 16-byte chunk c of row r lives at chunk (c ^ (r & 7)) of that row's 128 bytes
                 const uint32_t off = r * 128 + ((c ^ (r & 7)) << 4);
                 *reinterpret_cast<uint4*>(hi + off) = *reinterpret_cast<const uint4*>(h2);
                 *reinterpret_cast<uint4*>(lo + off) = *reinterpret_cast<const uint4*>(l2);
-                ss += __shfl_xor_sync(0xffffffffu, ss, 1);
-                ss += __shfl_xor_sync(0xffffffffu, ss, 2);
-                ss += __shfl_xor_sync(0xffffffffu, ss, 4);
-                if (c == 0) xnorm[buf][r] = sqrtf(ss);
+            }
+            // row norms: the 8 lanes of a row reduce their partial sums (all 8 rows' butterflies interleaved)
+#pragma unroll
+            for (int o = 1; o < 8; o <<= 1) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) ssq[j] += __shfl_xor_sync(0xffffffffu, ssq[j], o);
+            }
+            if (c == 0) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) xnorm[buf][r0 + 16 * j] = sqrtf(ssq[j]);
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic-proxy stores -> visible to tcgen05.mma
             __syncwarp();
@@ -254,7 +276,11 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vq_tc_kernel(const __grid_const
         }
     } else {
         // ------------------------------------------------------------------ epilogue: top-2 argmin, exact recheck, gather
-        const int quarter = warp & 3;
+        // 8 warps: warp e handles TMEM lanes 32*(warp & 3) (its frame rows) and columns [128*ch, 128*ch + 128) of each
+        // 256-code accumulator, ch = e >> 2.  The code index is packed into the 9 low mantissa bits of the score, so
+        // tracking the best two (value, index) pairs is three FMNMX per element; two independent chains per thread.
+        // The packing perturbs a score by <= 2^-14 relative, which is added to the recheck margin.
+        const int e = warp - VT_EPI_WARP0, quarter = warp & 3, ch = e >> 2;
         const int row = quarter * 32 + lane;
         uint32_t tphase[2] = {0, 0};
         bool ok = true;
@@ -262,8 +288,7 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vq_tc_kernel(const __grid_const
         const float emax = emax_s;
         for (long long tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x, ++it) {
             const int buf = it & 1;
-            float b1 = INFINITY, b2 = INFINITY, xn = 0.f;
-            int i1 = 0, i2 = 0;
+            float b1a = INFINITY, b2a = INFINITY, b1b = INFINITY, b2b = INFINITY, xn = 0.f;
             for (int half = 0; half < 2 && ok; ++half) {
                 ok = mbar_wait(&tfull_bar[half], tphase[half], p.err);
                 ok = __all_sync(0xffffffffu, ok);
@@ -271,17 +296,33 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vq_tc_kernel(const __grid_const
                 tphase[half] ^= 1;
                 tc_fence_after();
                 if (half == 0) xn = xnorm[buf][row];      // read now: the converters may refill this slot two tiles later
-#pragma unroll 1
-                for (int c0 = 0; c0 < 256; c0 += 32) {
-                    uint32_t v[32];
-                    tc_ld32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + half * 256 + c0, v);
-                    tc_wait_ld();
+                // software-pipelined TMEM reads: the load of chunk c+1 is in flight while chunk c is reduced
+                const uint32_t tbase = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + half * 256 + ch * 128;
+                uint32_t va[32], vb[32];
+                tc_ld32(tbase, va);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int m = half * 256 + c0 + j;
-                        const float s = e2s[m] + __uint_as_float(v[j]);      // |e|^2 + (-2 x.e)
-                        if (s < b1) { b2 = b1; i2 = i1; b1 = s; i1 = m; }
-                        else if (s < b2) { b2 = s; i2 = m; }
+                for (int cc = 0; cc < 4; ++cc) {
+                    if (p.debug & 1) { tc_wait_ld(); break; }
+                    uint32_t (&v)[32] = (cc & 1) ? vb : va;
+                    uint32_t (&vn)[32] = (cc & 1) ? va : vb;
+                    tc_wait_ld();
+                    if (cc + 1 < 4) tc_ld32(tbase + 32 * (cc + 1), vn);
+                    const int col = half * 256 + ch * 128 + 32 * cc;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 e4 = *reinterpret_cast<const float4*>(&e2s[col + j]);    // broadcast LDS.128
+                        const float ev[4] = {e4.x, e4.y, e4.z, e4.w};
+                        float k[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const float sc = ev[q] + __uint_as_float(v[j + q]);               // |e|^2 + (-2 x.e)
+                            k[q] = __uint_as_float((__float_as_uint(sc) & 0xfffffe00u) | static_cast<uint32_t>(col + j + q));
+                        }
+                        // merge the pair (lo <= hi) into the running (b1 <= b2): 5 ops per 2 elements
+                        const float lo0 = fminf(k[0], k[1]), hi0 = fmaxf(k[0], k[1]);
+                        b2a = fmin3(fmaxf(b1a, lo0), b2a, hi0); b1a = fminf(b1a, lo0);
+                        const float lo1 = fminf(k[2], k[3]), hi1 = fmaxf(k[2], k[3]);
+                        b2b = fmin3(fmaxf(b1b, lo1), b2b, hi1); b1b = fminf(b1b, lo1);
                     }
                 }
                 tc_fence_before();
@@ -289,9 +330,23 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vq_tc_kernel(const __grid_const
                 if (lane == 0) mbar_arrive(&tempty_bar[half]);
             }
             if (!ok) break;
+            // merge the two chains, then the two column halves: both warps of a row publish their pair, both read the
+            // other's, so both know the row's best two candidates and each takes half of the output work.
+            float b1 = fminf(b1a, b1b), b2 = fminf(fmaxf(b1a, b1b), fminf(b2a, b2b));
+            part[buf][ch][row] = make_float2(b1, b2);
+            bar_sync(1, VT_EPI_WARPS * 32);
+            {
+                const float2 o = part[buf][ch ^ 1][row];
+                const float n1 = fminf(b1, o.x), n2 = fminf(fmaxf(b1, o.x), fminf(b2, o.y));
+                b1 = n1; b2 = n2;
+            }
+            int i1 = static_cast<int>(__float_as_uint(b1) & 511u);
             const long long fr = tile * VT_TF + row;
-            if (fr < p.n) {
-                const float margin = 6.2e-5f * xn * emax;      // 2 x (2^-15 |x| max|e|)
+            // warp (quarter, ch) finishes rows quarter*32 + ch*16 + [0, 16): lanes ch*16 .. ch*16+15 own them
+            if ((lane >> 4) == ch && fr < p.n && !(p.debug & 2)) {
+                const int i2 = static_cast<int>(__float_as_uint(b2) & 511u);
+                // 2 x (coarse MMA error 2^-15 |x| max|e|  +  index-packing error 2^-14 |score|)
+                const float margin = 6.2e-5f * xn * emax + 1.3e-4f * fmaxf(fabsf(b1), fabsf(b2));
                 if (b2 - b1 <= margin) {
                     // exact fp32 scores of both candidates (arithmetic of the fp32 kernel); ties -> lower index
                     const float* xr = p.x + fr * VT_D;
@@ -308,10 +363,20 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vq_tc_kernel(const __grid_const
                     if (sb < sa || (sb == sa && i2 < i1)) i1 = i2;
                 }
                 p.out_idx[fr] = i1;
-                const float4* src = reinterpret_cast<const float4*>(p.codebook + i1 * VT_D);
-                float4* dst = reinterpret_cast<float4*>(p.out_q + fr * VT_D);
+            }
+            __syncwarp();
+            if (!(p.debug & 2)) {
+                // cooperative gather: per instruction two rows, 16 lanes x 16 B each = one fully coalesced 256-byte row
+                const long long fr0 = tile * VT_TF + quarter * 32 + ch * 16;
 #pragma unroll
-                for (int k = 0; k < VT_D / 4; ++k) dst[k] = __ldg(src + k);
+                for (int k = 0; k < 8; ++k) {
+                    const int r = 2 * k + (lane >> 4);                       // row within this warp's 16
+                    const int code = __shfl_sync(0xffffffffu, i1, ch * 16 + r);
+                    if (fr0 + r < p.n) {
+                        const float4 v = __ldg(reinterpret_cast<const float4*>(p.codebook + code * VT_D) + (lane & 15));
+                        reinterpret_cast<float4*>(p.out_q + (fr0 + r) * VT_D)[lane & 15] = v;
+                    }
+                }
             }
         }
     }
@@ -373,7 +438,9 @@ int vq_lookup_tc(const float* x, const float* codebook, int64_t n, float* q, int
     }
     const long long n_tiles = (n + VT_TF - 1) / VT_TF;
     const int sms = device_sm_count();
-    VqTcParams p{x, codebook, q, idx, err, static_cast<long long>(n)};
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("VQCPC_VQ_DEBUG"); dbg = e ? atoi(e) : 0; }
+    VqTcParams p{x, codebook, q, idx, err, static_cast<long long>(n), dbg};
     vq_tc_kernel<<<static_cast<unsigned>(n_tiles < sms ? n_tiles : sms), VT_THREADS, VT_SMEM, stream>>>(map, p);
     VQ_CUDA(cudaGetLastError());
     count_launch(1);
