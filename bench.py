@@ -137,6 +137,141 @@ def reference_arm(args):
     return 0
 
 
+
+def run_other_workload(args, world, rank, local, dev, timed, peaks, lib):
+    """BASELINE configs[3] (batched encode, 4096 x 3 s, STRONG scaling over the ranks) and configs[4] (end-to-end
+    convert: encode + generate, 64 x 3 s per GPU, weak scaling).  One JSON line, same contract as the headline."""
+    import torch
+    import torch.distributed as dist
+    from oracle import encoder as oenc
+    from oracle import fixtures
+    from oracle import vocoder as ovoc
+    from vectorquantizedcpc_b200 import ConfEncoder, Encoder, Vocoder
+    from vectorquantizedcpc_b200 import dist as vdist
+
+    sd = fixtures.encoder_init_state(768, seed=13)
+    enc = Encoder(ConfEncoder(channels=768))
+    enc.load_state_dict(sd)
+    enc = enc.to(dev).eval()
+    sampler = ClockSampler(local)
+    n0 = lib.vqcpc_launch_count()
+    if args.workload == "encode_4096":
+        n_total, T = 4096, 300
+        lo, hi = vdist.shard_range(n_total, rank, world)
+        mel_h = fixtures.synthetic_mel(n_total, T, seed=0)[lo:hi].contiguous().pin_memory()
+        mel_d = mel_h.to(dev)
+        idx_h = torch.empty(hi - lo, 150, dtype=torch.int64).pin_memory()
+
+        def gather_idx(idx):
+            if world > 1:
+                vdist.gather_utterances(idx, n_total, dst=0)
+
+        def step_resident():
+            with torch.no_grad():
+                _, _, idx = enc.encode(mel_d)
+            gather_idx(idx)
+
+        def step_e2e():
+            with torch.no_grad():
+                _, _, idx = enc.encode(mel_h.to(dev, non_blocking=True))
+                gather_idx(idx)
+                idx_h.copy_(idx, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+
+        if rank == 0:
+            sampler.start()
+        t_ms = timed(step_resident, args.steps, args.warmup)
+        launches = (lib.vqcpc_launch_count() - n0) * args.steps // (args.steps + args.warmup)
+        t_e2e = timed(step_e2e, args.steps, args.warmup)
+        clocks = sampler.stop() if rank == 0 else {}
+        frames = n_total * 150
+        value, e2e_v = frames * args.steps / (t_ms * 1e-3), frames * args.steps / (t_e2e * 1e-3)
+        flops = frames * 6.029e6 * 3           # bf16x3: three MMA terms per product
+        line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": t_ms / args.steps, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "bf16x3 (bf16 hi/lo split, fp32 accumulate)", "data": "synthetic",
+                "config": {"workload": "encode_4096x3s (BASELINE configs[3])", "utterances": n_total, "mel_frames": T,
+                           "channels": 768, "parallelism": f"utterances sharded over {world} GPU(s), NCCL gather of indices",
+                           "timing": "CUDA events per step, L2 flushed between steps"},
+                "e2e": {"value": e2e_v, "unit": "frames/s", "h2d_bytes_per_step": int(mel_h.numel() * 4 * world),
+                        "d2h_bytes_per_step": int(idx_h.numel() * 8 * world), "ms_per_step": t_e2e / args.steps},
+                "gpu_launches": int(launches), "clocks": clocks,
+                "roofline": {"kernel": "gemm_tc_kernel", "bound": "tensor", "unit": "TFLOP/s",
+                             "achieved": flops * args.steps / (t_ms * 1e-3) / 1e12 / world, "peak": peaks["bf16_tflops_sustained"],
+                             "frac": flops * args.steps / (t_ms * 1e-3) / 1e12 / world / peaks["bf16_tflops_sustained"],
+                             "traffic": None, "note": "per GPU, whole encode step (GEMMs + LN + VQ + LSTM) against the sustained "
+                             "cuBLAS bf16 peak; the GEMM kernel alone: profiles/r01_ncu_gemm_tc_summary.txt (0.84)"}}
+        if rank == 0 and world == 1 and not args.no_cpu:
+            t0 = time.perf_counter()
+            with torch.no_grad():
+                oenc.encode(sd, fixtures.synthetic_mel(64, T, seed=0))
+            dt = time.perf_counter() - t0
+            line["cpu_baseline"] = {"value": 64 * 150 / dt, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
+                                    "sample": "one chunk of 64 utterances x 3 s through oracle/encoder.py (fp32)"}
+        return line
+
+    # ---- convert_b64: encode + generate, 64 utterances x 3 s per GPU
+    B, T = 64, 300
+    voc = Vocoder()
+    vsd = ovoc.init_state_dict(seed=13)
+    voc.load_state_dict(vsd)
+    voc = voc.to(dev).eval()
+    mel_h = fixtures.synthetic_mel(B, T, seed=rank).pin_memory()
+    mel_d = mel_h.to(dev)
+    g = torch.Generator().manual_seed(rank)
+    spk_h = torch.randint(0, 102, (B,), generator=g).pin_memory()
+    spk_d = spk_h.to(dev)
+    gen = torch.Generator(device=dev).manual_seed(7 + rank)
+    L = 320 * 150
+    wav_h = torch.empty(B, L).pin_memory()
+
+    def convert(mel, spk):
+        with torch.no_grad():
+            _, _, idx = enc.encode(mel)
+            wav = voc.generate(idx, spk, generator=gen)
+        if world > 1:
+            vdist.gather_utterances(wav, B * world, dst=0)
+        return wav
+
+    def step_e2e():
+        wav = convert(mel_h.to(dev, non_blocking=True), spk_h.to(dev, non_blocking=True))
+        wav_h.copy_(wav, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    steps, warm = min(args.steps, 3), 1
+    if rank == 0:
+        sampler.start()
+    t_ms = timed(lambda: convert(mel_d, spk_d), steps, warm)
+    launches = (lib.vqcpc_launch_count() - n0) * steps // (steps + warm)
+    t_e2e = timed(step_e2e, steps, warm)
+    clocks = sampler.stop() if rank == 0 else {}
+    samples = B * L * world
+    value, e2e_v = samples * steps / (t_ms * 1e-3), samples * steps / (t_e2e * 1e-3)
+    line = {"metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": steps, "warmup": warm,
+            "ms_per_step": t_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "x_realtime": value / SR,
+            "config": {"workload": "convert_b64x3s (BASELINE configs[4]): Encoder.encode + Vocoder.generate", "batch_per_gpu": B,
+                       "mel_frames": T, "samples_per_utterance": L,
+                       "parallelism": f"utterances sharded over {world} GPU(s), NCCL gather of waveforms"},
+            "e2e": {"value": e2e_v, "unit": "samples/s", "x_realtime": e2e_v / SR, "h2d_bytes_per_step": int(mel_h.numel() * 4 + B * 8),
+                    "d2h_bytes_per_step": int(B * L * 4), "ms_per_step": t_e2e / steps},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": {"kernel": "ar_kernel", "bound": "hbm", "achieved": None, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": None, "traffic": None, "note": "latency-bound persistent kernel, see the headline workload"}}
+    if rank == 0 and world == 1 and not args.no_cpu:
+        # reference CPU: oracle encode of the 64 utterances + restated generate at B=64 truncated to 200 steps, extrapolated
+        codes, spk, u = fixtures.vocoder_inputs(B, 150, seed=0, n_steps=200)
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            oenc.encode(sd, mel_h)
+            ovoc.generate(vsd, codes, spk, u, n_steps=200)
+        dt = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": B * 200 / dt, "unit": "samples/s", "x_realtime": B * 200 / dt / SR,
+                                "cores": torch.get_num_threads(), "kind": "port",
+                                "sample": "oracle encode of 64 x 3 s + restated generate at B=64 truncated to 200 of 48000 steps"}
+    return line
+
+
 # ------------------------------------------------------------------------------------------------ our arm
 def main():
     ap = argparse.ArgumentParser()
@@ -144,7 +279,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="generate_b1", choices=["generate_b1", "convert_b64"])
+    ap.add_argument("--workload", default="generate_b1", choices=["generate_b1", "encode_4096", "convert_b64"],
+                    help="generate_b1 = BASELINE configs[2] (headline); encode_4096 = configs[3]; convert_b64 = configs[4]")
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary configs (VQ / encoder)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     args = ap.parse_args()
@@ -202,6 +338,14 @@ def main():
             evs.append((a, b))
         barrier()
         return max_over_ranks(sum(a.elapsed_time(b) for a, b in evs))
+
+    if args.workload != "generate_b1":
+        line = run_other_workload(args, world, rank, local, dev, timed, peaks, lib)
+        if rank == 0:
+            print(json.dumps(line))
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
 
     # ---- model + inputs (random-init weights, seed 13; synthetic inputs per SURVEY.md 8d)
     vsd = ovoc.init_state_dict(seed=13)
