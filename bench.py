@@ -448,8 +448,9 @@ def main():
     # ---- the other BASELINE configs, measured in the same run on rank 0's GPU (N = 1 only)
     if not args.no_extra and world == 1:
         extra = {}
-        # interleaved-utterance throughput of the sample loop (B = 4: one launch; B = 16: four launches), 1 s each
-        for Bb in (4, 16):
+        # sample-loop throughput beyond B = 1: B = 4 (one interleaved launch of the latency kernel) and B = 64 (the
+        # grid-barrier batched kernel, 64 utterance slots per launch), 1 s each
+        for Bb in (4, 64):
             cb, sb, _ = fixtures.vocoder_inputs(Bb, 50, seed=100 + Bb)
             cbd, sbd = cb.to(dev), sb.to(dev)
             with torch.no_grad():

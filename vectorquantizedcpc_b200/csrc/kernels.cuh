@@ -35,6 +35,9 @@ int vq_lookup_tc(const float* x, const float* codebook, int64_t n, float* q, int
 int vq_lookup_auto(const float* x, const float* codebook, int64_t n, float* q, int64_t* idx, void* planes_ws, int* err,
                    cudaStream_t stream);
 
+// vocoder_batch.cu: batched sample loop (up to 64 utterances per launch, grid-barrier phases)
+size_t ar_batch_workspace_bytes();
+
 // persistent-kernel workspace header (first bytes of every workspace handed to a persistent kernel)
 struct WorkspaceHeader {
     int status;       // 0 ok, else VQCPC_ERR_*

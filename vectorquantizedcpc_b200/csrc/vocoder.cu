@@ -542,14 +542,20 @@ __global__ void __launch_bounds__(32, 1) exchange_floor_kernel(ll_word* buf, int
 }
 
 // ------------------------------------------------------------------------------------------------ host
+int ar_batch_run(const vqcpc_vocoder_weights* w, const float* G, const float* uniforms, const int64_t* x_in, int B, int T2,
+                 int L, void* ws, int* status, float* out_wav, int32_t* out_codes, float* out_logits, cudaStream_t stream);
+constexpr int AR_BATCH_MIN_B = 8;     // from this many utterances on, the grid-barrier batched kernel wins
+static size_t ar_ws_bytes() {
+    const size_t ll = align_up(sizeof(ll_word) * AR_LL_WORDS, 256), ab = ar_batch_workspace_bytes();
+    return sizeof(WorkspaceHeader) + (ll > ab ? ll : ab);
+}
+
 // workspace layout: [header][u B*2Tc*128][xproj B*2Tc*768][p0 B*2Tc*256][p1 B*2Tc*256][ll words]
 static size_t vocoder_ws_bytes(int B, int Tc) {
     const size_t rows = static_cast<size_t>(B) * 2 * Tc;
     return sizeof(WorkspaceHeader) + align_up(rows * 128 * 4, 256) + align_up(rows * 768 * 4, 256) +
-           2 * align_up(rows * 256 * 4, 256) + align_up(sizeof(ll_word) * AR_LL_WORDS, 256);
+           2 * align_up(rows * 256 * 4, 256) + ar_ws_bytes();
 }
-static size_t ar_ws_bytes() { return sizeof(WorkspaceHeader) + align_up(sizeof(ll_word) * AR_LL_WORDS, 256); }
-
 static int check_vocoder_dims(const vqcpc_vocoder_weights* w) {
     VQ_ARG(w != nullptr, "vocoder: null weights");
     VQ_ARG(w->dim_code + w->dim_speaker == 128 && w->dim_code % 4 == 0 && w->dim_speaker % 4 == 0,
@@ -607,6 +613,7 @@ int vocoder_condition(const vqcpc_vocoder_weights* w, const int64_t* codes, cons
 
 static int g_poll_gap = 400;     // bits 0..11: first-poll delay, bits 12..23: backoff (cycles); see vqcpc_debug_set_ar_poll_gap
 static int g_nb_cap = AR_NB_MAX;
+static int g_batch_min_b = AR_BATCH_MIN_B;
 struct ArTrace { long long* buf; int cta, t0, n; };
 static ArTrace g_trace = {nullptr, 0, 0, 0};
 
@@ -646,6 +653,9 @@ static int ar_run(const vqcpc_vocoder_weights* w, const float* G, const float* u
     WorkspaceHeader* hdr = reinterpret_cast<WorkspaceHeader*>(base);
     ll_word* ll = reinterpret_cast<ll_word*>(base + sizeof(WorkspaceHeader));
     VQ_CUDA(cudaMemsetAsync(hdr, 0, sizeof(WorkspaceHeader), stream));
+    if (B >= g_batch_min_b)
+        return ar_batch_run(w, G, uniforms, x_in, B, T2, L, base + sizeof(WorkspaceHeader), &hdr->status, out_wav, out_codes,
+                            out_logits, stream);
     // groups of up to NB utterances share one persistent launch (their steps are interleaved inside the kernel)
     for (int b = 0; b < B;) {
         int nb = B - b < g_nb_cap ? B - b : g_nb_cap;
@@ -708,10 +718,13 @@ extern "C" int vqcpc_debug_set_ar_poll_gap(int32_t packed) {
     vqcpc::g_poll_gap = packed < 0 ? 0 : (packed & 0xffffff);
     const int cap = (packed >> 24) & 0xf;          // bits 24..27: cap on utterances per launch (0 = default)
     vqcpc::g_nb_cap = (cap >= 1 && cap <= vqcpc::AR_NB_MAX) ? cap : vqcpc::AR_NB_MAX;
+    vqcpc::g_batch_min_b = ((packed >> 28) & 1) ? (1 << 30) : vqcpc::AR_BATCH_MIN_B;   // bit 28: disable the batched kernel
     return VQCPC_OK;
 }
+namespace vqcpc { extern long long* g_ab_trace; extern int g_ab_trace_cta, g_ab_trace_t0, g_ab_trace_n; }
 extern "C" int vqcpc_debug_set_ar_trace(long long* device_buf, int32_t cta, int32_t first_step, int32_t n_steps) {
     vqcpc::g_trace = vqcpc::ArTrace{device_buf, cta, first_step, n_steps};
+    vqcpc::g_ab_trace = device_buf; vqcpc::g_ab_trace_cta = cta; vqcpc::g_ab_trace_t0 = first_step; vqcpc::g_ab_trace_n = n_steps;
     return VQCPC_OK;
 }
 extern "C" int vqcpc_vocoder_pack(const vqcpc_vocoder_weights* w, float* eprime_out, void* stream) {
