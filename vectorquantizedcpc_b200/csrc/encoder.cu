@@ -419,7 +419,8 @@ __global__ void __launch_bounds__(256) lstm_kernel(LstmParams p) {
                 const float og = sigmoid_fast(mine[3] + xp[3]);
                 cst = fg * cst + ig * gg;
                 const float hn = og * tanh_fast(cst);
-                ll_store(ll + (static_cast<size_t>(cur) * NB + lane) * LSTM_H + unit, hn, tag);
+                // every producer CTA owns one contiguous slot [NB][8] (64 B at NB = 1): a line is written by one CTA only
+                ll_store(ll + ((static_cast<size_t>(cur) * LSTM_GROUP + cta) * NB + lane) * 8 + warp, hn, tag);
             }
 #pragma unroll
             for (int g = 0; g < 4; ++g) xp[g] = xn[g];
@@ -427,13 +428,14 @@ __global__ void __launch_bounds__(256) lstm_kernel(LstmParams p) {
             // gather all 256 hidden values of every slot: thread tid polls column tid
             float got[NB];
             {
-                const ll_word* src = ll + static_cast<size_t>(cur) * NB * LSTM_H + tid;
+                const ll_word* src = ll + ((static_cast<size_t>(cur) * LSTM_GROUP + (tid >> 3)) * NB) * 8 + (tid & 7);
                 const long long t0 = clock64();
+                while (clock64() - t0 < 300) {}          // the earliest a remote value can be visible (~770-cycle one-way)
                 bool done = false;
                 while (!done) {
                     ll_word wv[NB];
 #pragma unroll
-                    for (int nb = 0; nb < NB; ++nb) wv[nb] = ll_load(src + nb * LSTM_H);
+                    for (int nb = 0; nb < NB; ++nb) wv[nb] = ll_load(src + nb * 8);
                     done = true;
 #pragma unroll
                     for (int nb = 0; nb < NB; ++nb) {

@@ -39,7 +39,7 @@ struct AbParams {
     const float* uniforms;   // (B, L)   generate mode
     const int64_t* x_in;     // (B, L)   teacher-forced mode
     float* out_wav; int32_t* out_codes; float* out_logits;
-    float* hT;               // [896][64]
+    float* hT;               // [2][896][64]  double buffered by step parity
     float* rT;               // [256][64]
     float* oT;               // [256][64]
     int* xs;                 // [64]
@@ -97,6 +97,82 @@ __device__ __forceinline__ bool ab_grid_sync(ll_word* flags, uint32_t tag, volat
     return *abort_flag == 0;
 }
 
+// split barrier: signal = publish this CTA's arrival (after a fence), wait = poll all 128 arrivals.  Work placed
+// between the two hides the ~4000-cycle barrier latency.
+__device__ __forceinline__ void ab_signal(ll_word* flags, uint32_t tag) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        ll_store(flags + blockIdx.x * 16, 0.f, tag);
+    }
+}
+__device__ __forceinline__ bool ab_wait(ll_word* flags, uint32_t tag, volatile int* abort_flag, int* status) {
+    if (threadIdx.x < 32) {
+        const long long t0 = clock64();
+        for (;;) {
+            bool ok = true;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t seen = ll_tag(ll_load(flags + (32 * k + threadIdx.x) * 16));
+                ok = ok && (static_cast<int32_t>(seen - tag) >= 0);
+            }
+            if (__all_sync(0xffffffffu, ok)) break;
+            if (clock64() - t0 > LL_TIMEOUT_CYCLES) {
+                *abort_flag = 1;
+                if (threadIdx.x == 0) atomicExch(status, VQCPC_ERR_TIMEOUT);
+                break;
+            }
+        }
+        __threadfence();
+    }
+    __syncthreads();
+    return *abort_flag == 0;
+}
+
+// Stream column groups [c4_begin, c4_end) of this warp's 112-column chunk of h_t from L2 and accumulate rows
+// R0 .. R0+NR-1 of the CTA's weight slice for this lane's two utterances (slots lane, lane + 32).
+// hcol -> hT[chunk column 0][lane]; wg -> weight groups of the chunk ([c4][23 rows] float4, shared memory).
+template <int R0, int NR, int PF>
+__device__ __forceinline__ void ab_stream(const float* hcol, const float4* wg, int c4_begin, int c4_end, float (&acc0)[NR],
+                                          float (&acc1)[NR]) {
+    float ha[PF][4], hb[PF][4];
+#pragma unroll
+    for (int s = 0; s < PF - 1; ++s) {
+        if (c4_begin + s < c4_end) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                ha[s][i] = ld_strong(hcol + (4 * (c4_begin + s) + i) * AB_B);
+                hb[s][i] = ld_strong(hcol + (4 * (c4_begin + s) + i) * AB_B + 32);
+            }
+        }
+    }
+    for (int base = c4_begin; base < c4_end; base += PF) {
+#pragma unroll
+        for (int s = 0; s < PF; ++s) {
+            const int c4 = base + s;
+            if (c4 < c4_end) {
+                constexpr int dummy = 0; (void)dummy;
+                const int nxt = (s + PF - 1) % PF;
+                if (c4 + PF - 1 < c4_end) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        ha[nxt][i] = ld_strong(hcol + (4 * (c4 + PF - 1) + i) * AB_B);
+                        hb[nxt][i] = ld_strong(hcol + (4 * (c4 + PF - 1) + i) * AB_B + 32);
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < NR; ++r) {
+                    const float4 w4 = wg[c4 * AB_ROWS + R0 + r];                    // broadcast LDS.128
+                    acc0[r] = fmaf(w4.x, ha[s][0], acc0[r]); acc1[r] = fmaf(w4.x, hb[s][0], acc1[r]);
+                    acc0[r] = fmaf(w4.y, ha[s][1], acc0[r]); acc1[r] = fmaf(w4.y, hb[s][1], acc1[r]);
+                    acc0[r] = fmaf(w4.z, ha[s][2], acc0[r]); acc1[r] = fmaf(w4.z, hb[s][2], acc1[r]);
+                    acc0[r] = fmaf(w4.w, ha[s][3], acc0[r]); acc1[r] = fmaf(w4.w, hb[s][3], acc1[r]);
+                }
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(AB_THREADS, 1) ar_batch_kernel(AbParams p) {
     extern __shared__ __align__(16) float ab_smem[];
     float* Ws = ab_smem;                 // [c4][row][4]
@@ -146,8 +222,12 @@ __global__ void __launch_bounds__(AB_THREADS, 1) ar_batch_kernel(AbParams p) {
     int frame_left = 0, frame = 0;
     const bool tracing = p.trace != nullptr && cta == p.trace_cta && tid == 0;
 #define AB_TRACE(k) if (tracing && t >= p.trace_t0 && t < p.trace_t0 + p.trace_n) p.trace[(t - p.trace_t0) * 8 + (k)] = clock64();
+    constexpr int NIT = AB_CHUNK / 4, S1 = 10, S2 = 19;          // column groups per warp; slices of the W_hh rows
+    const float4* wg = reinterpret_cast<const float4*>(Ws) + static_cast<int64_t>(cc * NIT) * AB_ROWS;
     for (int t = 0; t < L; ++t) {
         AB_TRACE(0)
+        float* hT = p.hT + static_cast<int64_t>(t & 1) * AB_H * AB_B;             // double buffered by step parity
+        const float* hcol = hT + static_cast<int64_t>(cc * AB_CHUNK) * AB_B + lane;
         // ------------------------------------------------------------------ G: conditioning reload, gates, h_t
         if (frame_left == 0) {
             for (int i = tid; i < AB_GC; i += AB_THREADS) {
@@ -167,84 +247,59 @@ __global__ void __launch_bounds__(AB_THREADS, 1) ar_batch_kernel(AbParams p) {
             const float n = tanh_fast(__fmaf_rn(r, hh[(3 * u + 2) * AB_B + b], __fadd_rn(e[2], Gc[(3 * u + 2) * AB_B + b])));
             const float hn = __fmaf_rn(z, __fsub_rn(hown[i], n), n);
             hown[i] = hn;
-            p.hT[(cta * AB_U + u) * AB_B + b] = hn;
+            hT[(cta * AB_U + u) * AB_B + b] = hn;
         }
         AB_TRACE(1)
-        if (!ab_grid_sync(p.flags, ++tag, &abort_flag, p.status)) return;
+        ab_signal(p.flags, ++tag);
+        if (!ab_wait(p.flags, tag, &abort_flag, p.status)) return;                  // barrier 1: h_t complete
         AB_TRACE(2)
 
-        // ------------------------------------------------------------------ P2: stream h_t; 23 rows x this lane's TWO utterances
-        // (two utterances per lane: one broadcast LDS.128 of weights feeds 8 FMAs, which keeps the shared-memory
-        //  return path -- 4 cycles per warp-wide LDS.128 -- below the FMA pipe)
+        // ------------------------------------------------------------------ P2a: the two fc1 rows first (critical path)
         {
-            float acc0[AB_ROWS], acc1[AB_ROWS];
+            float f0[AB_R] = {0.f, 0.f}, f1[AB_R] = {0.f, 0.f};
+            ab_stream<AB_NROW, AB_R, 7>(hcol, wg, 0, NIT, f0, f1);
 #pragma unroll
-            for (int r = 0; r < AB_ROWS; ++r) { acc0[r] = 0.f; acc1[r] = 0.f; }
-            const float* hcol = p.hT + static_cast<int64_t>(cc * AB_CHUNK) * AB_B + lane;
-            const float4* wg = reinterpret_cast<const float4*>(Ws) + static_cast<int64_t>(cc * (AB_CHUNK / 4)) * AB_ROWS;
-            constexpr int PF = 3, NIT = AB_CHUNK / 4;        // register ring of column groups
-            float ha[PF][4], hb[PF][4];
-#pragma unroll
-            for (int s = 0; s < PF - 1; ++s)
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    ha[s][i] = ld_strong(hcol + (4 * s + i) * AB_B);
-                    hb[s][i] = ld_strong(hcol + (4 * s + i) * AB_B + 32);
-                }
-#pragma unroll 3
-            for (int c4 = 0; c4 < NIT; ++c4) {
-                const int cur = c4 % PF, nxt = (c4 + PF - 1) % PF;
-                if (c4 + PF - 1 < NIT) {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        ha[nxt][i] = ld_strong(hcol + (4 * (c4 + PF - 1) + i) * AB_B);
-                        hb[nxt][i] = ld_strong(hcol + (4 * (c4 + PF - 1) + i) * AB_B + 32);
-                    }
-                }
-#pragma unroll
-                for (int r = 0; r < AB_ROWS; ++r) {
-                    const float4 w4 = wg[c4 * AB_ROWS + r];                         // broadcast LDS.128
-                    acc0[r] = fmaf(w4.x, ha[cur][0], acc0[r]); acc1[r] = fmaf(w4.x, hb[cur][0], acc1[r]);
-                    acc0[r] = fmaf(w4.y, ha[cur][1], acc0[r]); acc1[r] = fmaf(w4.y, hb[cur][1], acc1[r]);
-                    acc0[r] = fmaf(w4.z, ha[cur][2], acc0[r]); acc1[r] = fmaf(w4.z, hb[cur][2], acc1[r]);
-                    acc0[r] = fmaf(w4.w, ha[cur][3], acc0[r]); acc1[r] = fmaf(w4.w, hb[cur][3], acc1[r]);
-                }
-            }
-#pragma unroll
-            for (int r = 0; r < AB_ROWS; ++r) {
-                part[(cc * AB_ROWS + r) * AB_B + lane] = acc0[r];
-                part[(cc * AB_ROWS + r) * AB_B + lane + 32] = acc1[r];
+            for (int r = 0; r < AB_R; ++r) {
+                part[(cc * AB_R + r) * AB_B + lane] = f0[r];
+                part[(cc * AB_R + r) * AB_B + lane + 32] = f1[r];
             }
         }
         __syncthreads();
-        for (int i = tid; i < AB_ROWS * AB_B; i += AB_THREADS) {
-            const int row = i / AB_B, b = i % AB_B;
-            float s = 0.f;
+        if (tid < AB_R * AB_B) {
+            const int r = tid / AB_B, b = tid % AB_B;
+            float sum = 0.f;
 #pragma unroll
-            for (int c = 0; c < AB_CC; ++c) s += part[(c * AB_ROWS + row) * AB_B + b];
-            if (row < AB_NROW) hh[i] = s + bhh_s[row];
-            else p.rT[(cta * AB_R + row - AB_NROW) * AB_B + b] = fmaxf(s + b1_s[row - AB_NROW], 0.f);
+            for (int c = 0; c < AB_CC; ++c) sum += part[(c * AB_R + r) * AB_B + b];
+            p.rT[(cta * AB_R + r) * AB_B + b] = fmaxf(sum + b1_s[r], 0.f);
         }
         AB_TRACE(3)
-        if (!ab_grid_sync(p.flags, ++tag, &abort_flag, p.status)) return;
+        ab_signal(p.flags, ++tag);                                                  // barrier 2 (r complete) ...
+        // ------------------------------------------------------------------ P2b: W_hh rows for the NEXT step, in three
+        // slices that run while barriers 2, 3 and 4 are in flight
+        float acc0[AB_NROW], acc1[AB_NROW];
+#pragma unroll
+        for (int r = 0; r < AB_NROW; ++r) { acc0[r] = 0.f; acc1[r] = 0.f; }
+        ab_stream<0, AB_NROW, 3>(hcol, wg, 0, S1, acc0, acc1);
+        if (!ab_wait(p.flags, tag, &abort_flag, p.status)) return;                  // ... barrier 2 wait
         AB_TRACE(4)
 
         // ------------------------------------------------------------------ P3: fc2 rows over relu(fc1 h_t)
         {
             float a0 = 0.f, a1 = 0.f;
             const float* rcol = p.rT + static_cast<int64_t>(cc3 * 64) * AB_B + slot;
-            const float4* wg = reinterpret_cast<const float4*>(W2s) + static_cast<int64_t>(cc3 * 16) * AB_R;
+            const float4* w2g = reinterpret_cast<const float4*>(W2s) + static_cast<int64_t>(cc3 * 16) * AB_R;
             float rv[64];
 #pragma unroll
             for (int i = 0; i < 64; ++i) rv[i] = ld_strong(rcol + i * AB_B);       // all 64 loads in flight at once
 #pragma unroll
             for (int c4 = 0; c4 < 16; ++c4) {
-                const float4 w0 = wg[c4 * AB_R], w1 = wg[c4 * AB_R + 1];
+                const float4 w0 = w2g[c4 * AB_R], w1 = w2g[c4 * AB_R + 1];
                 a0 = fmaf(w0.x, rv[4 * c4], a0); a0 = fmaf(w0.y, rv[4 * c4 + 1], a0);
                 a0 = fmaf(w0.z, rv[4 * c4 + 2], a0); a0 = fmaf(w0.w, rv[4 * c4 + 3], a0);
                 a1 = fmaf(w1.x, rv[4 * c4], a1); a1 = fmaf(w1.y, rv[4 * c4 + 1], a1);
                 a1 = fmaf(w1.z, rv[4 * c4 + 2], a1); a1 = fmaf(w1.w, rv[4 * c4 + 3], a1);
             }
+            __syncthreads();                                                        // fc1 partials in `part` fully consumed
             part[(cc3 * AB_R + 0) * AB_B + slot] = a0;
             part[(cc3 * AB_R + 1) * AB_B + slot] = a1;
         }
@@ -257,63 +312,88 @@ __global__ void __launch_bounds__(AB_THREADS, 1) ar_batch_kernel(AbParams p) {
             if (p.out_logits != nullptr && b < nb)
                 p.out_logits[(static_cast<int64_t>(b) * L + t) * AB_Q + cta * AB_R + r] = o;
         }
-        if (teacher) { __syncthreads(); continue; }     // codes are given: no logits exchange, no sampling
         AB_TRACE(5)
-        if (!ab_grid_sync(p.flags, ++tag, &abort_flag, p.status)) return;
-        AB_TRACE(6)
-
-        // ------------------------------------------------------------------ P4: CTA b samples utterance b
-        if (warp == 0 && cta < nb) {
-            const int b = cta;
-            float ov[8];
+        if (!teacher) {
+            ab_signal(p.flags, ++tag);                                              // barrier 3 (logits complete) ...
+            ab_stream<0, AB_NROW, 3>(hcol, wg, S1, S2, acc0, acc1);
+            if (!ab_wait(p.flags, tag, &abort_flag, p.status)) return;
+            AB_TRACE(6)
+            // -------------------------------------------------------------- P4: CTA b samples utterance b
+            if (warp == 0 && cta < nb) {
+                const int b = cta;
+                float ov[8];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) ov[k] = ld_strong(p.oT + (8 * lane + k) * AB_B + b);
-            float m = ov[0];
+                for (int k = 0; k < 8; ++k) ov[k] = ld_strong(p.oT + (8 * lane + k) * AB_B + b);
+                float m = ov[0];
 #pragma unroll
-            for (int k = 1; k < 8; ++k) m = fmaxf(m, ov[k]);
-            m = warp_max(m);
-            float c[8];
-            float run = 0.f;
+                for (int k = 1; k < 8; ++k) m = fmaxf(m, ov[k]);
+                m = warp_max(m);
+                float c[8];
+                float run = 0.f;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) { run += __expf(ov[k] - m); c[k] = run; }
-            float incl = run;
+                for (int k = 0; k < 8; ++k) { run += __expf(ov[k] - m); c[k] = run; }
+                float incl = run;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const float v = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += v;
+                for (int o = 1; o < 32; o <<= 1) {
+                    const float v = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += v;
+                }
+                const float excl = incl - run;
+                const float S = __shfl_sync(0xffffffffu, incl, 31);
+                const float thr = __ldg(p.uniforms + static_cast<int64_t>(b) * L + t) * S;
+                int loc = 8;
+#pragma unroll
+                for (int k = 7; k >= 0; --k) if (excl + c[k] > thr) loc = k;
+                const unsigned hit = __ballot_sync(0xffffffffu, loc < 8);
+                int x = AB_Q - 1;
+                if (hit != 0u) {
+                    const int src = __ffs(hit) - 1;
+                    x = 8 * src + __shfl_sync(0xffffffffu, loc, src);
+                }
+                if (lane == 0) {
+                    p.xs[b] = x;
+                    if (p.out_wav) p.out_wav[static_cast<int64_t>(b) * L + t] = __ldg(p.lut + x);
+                    if (p.out_codes) p.out_codes[static_cast<int64_t>(b) * L + t] = x;
+                }
             }
-            const float excl = incl - run;
-            const float S = __shfl_sync(0xffffffffu, incl, 31);
-            const float thr = __ldg(p.uniforms + static_cast<int64_t>(b) * L + t) * S;
-            int loc = 8;
-#pragma unroll
-            for (int k = 7; k >= 0; --k) if (excl + c[k] > thr) loc = k;
-            const unsigned hit = __ballot_sync(0xffffffffu, loc < 8);
-            int x = AB_Q - 1;
-            if (hit != 0u) {
-                const int src = __ffs(hit) - 1;
-                x = 8 * src + __shfl_sync(0xffffffffu, loc, src);
-            }
-            if (lane == 0) {
-                p.xs[b] = x;
-                if (p.out_wav) p.out_wav[static_cast<int64_t>(b) * L + t] = __ldg(p.lut + x);
-                if (p.out_codes) p.out_codes[static_cast<int64_t>(b) * L + t] = x;
-            }
+            AB_TRACE(7)
+            ab_signal(p.flags, ++tag);                                              // barrier 4 (codes complete) ...
+            ab_stream<0, AB_NROW, 3>(hcol, wg, S2, NIT, acc0, acc1);
+        } else {
+            ab_stream<0, AB_NROW, 3>(hcol, wg, S1, NIT, acc0, acc1);
+            __syncthreads();                                                        // fc2 partials in `part` consumed
         }
-        AB_TRACE(7)
-        if (!ab_grid_sync(p.flags, ++tag, &abort_flag, p.status)) return;
-        if (tid < AB_B) {
-            int xv = 0;
-            if (tid < nb) asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(xv) : "l"(p.xs + tid) : "memory");
-            xcur[tid] = xv;
+        // W_hh partials of the eight column chunks meet in shared memory
+#pragma unroll
+        for (int r = 0; r < AB_NROW; ++r) {
+            part[(cc * AB_ROWS + r) * AB_B + lane] = acc0[r];
+            part[(cc * AB_ROWS + r) * AB_B + lane + 32] = acc1[r];
         }
-        // (the __syncthreads at the top of the next step orders xcur before the gates)
+        if (!teacher) {
+            if (!ab_wait(p.flags, tag, &abort_flag, p.status)) return;              // ... barrier 4 wait (ends in __syncthreads)
+            if (tid < AB_B) {
+                int xv = 0;
+                if (tid < nb) asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(xv) : "l"(p.xs + tid) : "memory");
+                xcur[tid] = xv;
+            }
+        } else {
+            __syncthreads();
+        }
+        for (int i = tid; i < AB_NROW * AB_B; i += AB_THREADS) {
+            const int row = i / AB_B, b = i % AB_B;
+            float sum = 0.f;
+#pragma unroll
+            for (int c = 0; c < AB_CC; ++c) sum += part[(c * AB_ROWS + row) * AB_B + b];
+            hh[i] = sum + bhh_s[row];
+        }
+        // (the __syncthreads at the top of the next step orders hh / xcur before the gates)
     }
+#undef AB_TRACE
 }
 
-// workspace of one launch: [hT 896x64][rT 256x64][oT 256x64][xs 64][pad][flags 128x16 words]
+// workspace of one launch: [hT 2x896x64][rT 256x64][oT 256x64][xs 64][pad][flags 128x16 words]
 static size_t ab_ws_bytes() {
-    return sizeof(float) * (AB_H + 2 * AB_FC) * AB_B + 256 + sizeof(ll_word) * AB_CTAS * 16;
+    return sizeof(float) * (2 * AB_H + 2 * AB_FC) * AB_B + 256 + sizeof(ll_word) * AB_CTAS * 16;
 }
 size_t ar_batch_workspace_bytes() { return align_up(ab_ws_bytes(), 256); }
 
@@ -342,10 +422,10 @@ int ar_batch_run(const vqcpc_vocoder_weights* w, const float* G, const float* un
         p.out_codes = out_codes ? out_codes + static_cast<int64_t>(b0) * L : nullptr;
         p.out_logits = out_logits ? out_logits + static_cast<int64_t>(b0) * L * AB_Q : nullptr;
         p.hT = reinterpret_cast<float*>(base);
-        p.rT = p.hT + AB_H * AB_B;
+        p.rT = p.hT + 2 * AB_H * AB_B;
         p.oT = p.rT + AB_FC * AB_B;
         p.xs = reinterpret_cast<int*>(p.oT + AB_FC * AB_B);
-        p.flags = reinterpret_cast<ll_word*>(base + sizeof(float) * (AB_H + 2 * AB_FC) * AB_B + 256);
+        p.flags = reinterpret_cast<ll_word*>(base + sizeof(float) * (2 * AB_H + 2 * AB_FC) * AB_B + 256);
         p.status = status;
         p.L = L; p.upsample = w->upsample_t; p.nb = nb;
         p.trace = g_ab_trace; p.trace_cta = g_ab_trace_cta; p.trace_t0 = g_ab_trace_t0; p.trace_n = g_ab_trace_n;
