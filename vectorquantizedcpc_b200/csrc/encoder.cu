@@ -604,7 +604,8 @@ static size_t encoder_ws_bytes(int B, int T, int C, int mode) {
     const size_t M = static_cast<size_t>(B) * Tp;
     size_t n = align_up(lstm_ws_bytes(B), 256) + 2 * align_up(M * C * sizeof(float), 256) +
                align_up(M * VQ_D * sizeof(float), 256) + align_up(VQ_TC_PLANES_BYTES, 1024);
-    if (mode == VQCPC_GEMM_BF16X3) n += align_up(M * 2 * (C > 320 ? C : 320) * 2, 256) + 1024;   // bf16 planes of the A operand
+    if (mode == VQCPC_GEMM_BF16X3)        // two bf16 plane buffers (ping-pong A operands) + the fused-LN kernel's scratch rows
+        n += 2 * (align_up(M * 2 * (C > 320 ? C : 320) * 2, 256) + 1024) + align_up(gemm_tc_ln_scratch_bytes(C), 256);
     return n;
 }
 
@@ -652,7 +653,11 @@ int encoder_forward(const vqcpc_encoder_weights* w, const float* mel, int B, int
         VQ_ARG(w->conv_wp && w->fc_wp[0] && w->fc_wp[1] && w->fc_wp[2] && w->fc_wp[3] && w->proj_wp,
                "encoder: weight planes missing (vqcpc_split_planes) for VQCPC_GEMM_BF16X3");
         VQ_ARG(M < (1LL << 31), "encoder: too many frames for the tensor-core mode");
-        void* planes = base + off;
+        const size_t plane_bytes = align_up(M * 2 * (C > 320 ? C : 320) * 2, 256) + 1024;
+        void* planes = base + off; off += plane_bytes;
+        void* planes2 = base + off; off += plane_bytes;
+        void* ln_scratch = base + off;
+        const bool fused = gemm_tc_ln_supported(C);
         VQ_CUDA(cudaMemsetAsync(hdr, 0, sizeof(WorkspaceHeader), stream));
         {
             const int64_t total = M * 80;
@@ -661,12 +666,26 @@ int encoder_forward(const vqcpc_encoder_weights* w, const float* mel, int B, int
             VQ_CUDA(cudaGetLastError());
             count_launch(1);
         }
-        if ((rc = gemm_tc(planes, w->conv_wp, nullptr, act[0], C, static_cast<int>(M), C, 320, 3, &hdr->status, stream))) return rc;
-        if ((rc = layernorm_relu_split(act[0], w->ln_w[0], w->ln_b[0], planes, nullptr, M, C, stream))) return rc;
-        for (int j = 0; j < 4; ++j) {
-            if ((rc = gemm_tc(planes, w->fc_wp[j], nullptr, act[0], C, static_cast<int>(M), C, C, 3, &hdr->status, stream))) return rc;
-            if ((rc = layernorm_relu_split(act[0], w->ln_w[j + 1], w->ln_b[j + 1], planes, j == 3 ? out_hidden : nullptr, M, C,
-                                           stream))) return rc;
+        if (fused) {
+            // every GEMM writes relu(LN(.)) straight as the next GEMM's planes (ping-pong between the two plane buffers)
+            void* cur = planes;
+            void* nxt = planes2;
+            if ((rc = gemm_tc_ln(cur, w->conv_wp, w->ln_w[0], w->ln_b[0], nxt, nullptr, ln_scratch, static_cast<int>(M), C, 320, 3,
+                                 &hdr->status, stream))) return rc;
+            for (int j = 0; j < 4; ++j) {
+                void* t = cur; cur = nxt; nxt = t;
+                if ((rc = gemm_tc_ln(cur, w->fc_wp[j], w->ln_w[j + 1], w->ln_b[j + 1], nxt, j == 3 ? out_hidden : nullptr, ln_scratch,
+                                     static_cast<int>(M), C, C, 3, &hdr->status, stream))) return rc;
+            }
+            planes = nxt;
+        } else {
+            if ((rc = gemm_tc(planes, w->conv_wp, nullptr, act[0], C, static_cast<int>(M), C, 320, 3, &hdr->status, stream))) return rc;
+            if ((rc = layernorm_relu_split(act[0], w->ln_w[0], w->ln_b[0], planes, nullptr, M, C, stream))) return rc;
+            for (int j = 0; j < 4; ++j) {
+                if ((rc = gemm_tc(planes, w->fc_wp[j], nullptr, act[0], C, static_cast<int>(M), C, C, 3, &hdr->status, stream))) return rc;
+                if ((rc = layernorm_relu_split(act[0], w->ln_w[j + 1], w->ln_b[j + 1], planes, j == 3 ? out_hidden : nullptr, M, C,
+                                               stream))) return rc;
+            }
         }
         if ((rc = gemm_tc(planes, w->proj_wp, w->proj_b, zpre, VQ_D, static_cast<int>(M), VQ_D, C, 3, &hdr->status, stream))) return rc;
     }

@@ -15,6 +15,7 @@
 // Every mbarrier wait is bounded; on timeout the kernel raises a device-side error flag and drains.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "kernels.cuh"
@@ -235,6 +236,225 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
 }
 
+// ----------------------------------------------------------------------------------------------
+// GEMM with a fused LayerNorm + ReLU + hi/lo-split epilogue:   planes = split(relu(LN(A' . W'^T)))
+// (nn.Linear(C, C, bias=False) -> nn.LayerNorm(C) -> nn.ReLU of /root/reference/model.py:50-52, and the conv ->
+// LN -> ReLU head, model.py:43-48).  N = NT * 256 <= 768: a CTA owns a whole 128-row block and walks its NT
+// column tiles through the two TMEM accumulators, so an epilogue thread (= one row) sees the complete row:
+//   pass A (per tile, overlapped with the next tile's MMAs): tcgen05.ld -> stash raw y in an L2-resident
+//          per-CTA scratch row, accumulate shifted sums  s1 = sum(y - K), s2 = sum((y - K)^2),  K = y[row][0];
+//   pass B (after the last tile, overlapped with the next row block's MMAs): mean = K + s1/N,
+//          var = s2/N - (s1/N)^2 (biased, eps 1e-5), re-read the row, affine, ReLU, and write it straight as the
+//          bf16 hi/lo planes the next tcgen05 GEMM consumes (optionally also as fp32).
+// The fp32 activation never makes a round trip through a separate LayerNorm kernel.
+// ----------------------------------------------------------------------------------------------
+struct TcLnParams {
+    const float* ln_w; const float* ln_b;
+    __nv_bfloat16* out_planes;   // (M, 2N): [hi | lo]
+    float* out_f32;              // (M, N) or null
+    float* scratch;              // gridDim.x * 128 * N floats
+    int* err;
+    int M, N, K, nseg;
+    int debug;                   // bit 0: skip the scratch stores of pass A, bit 1: skip pass B (timing experiments)
+};
+
+template <int NT>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_ln_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, TcLnParams p) {
+    constexpr int BN = 256;
+    constexpr uint32_t A_BYTES = TC_BM * TC_BK * 2, W_BYTES = BN * TC_BK * 2, STAGE_BYTES = A_BYTES + W_BYTES;
+    constexpr uint32_t TMEM_COLS = 512;
+    constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(BN >> 3) << 17) |
+                               (static_cast<uint32_t>(TC_BM >> 4) << 24);
+    constexpr int N = NT * BN;
+
+    extern __shared__ __align__(1024) unsigned char tc_smem[];
+    __shared__ __align__(8) uint64_t full_bar[TC_STAGES], empty_bar[TC_STAGES], tfull_bar[2], tempty_bar[2];
+    __shared__ uint32_t tmem_base_slot;
+    __shared__ float ep_tile[4][32 * 33];                 // per epilogue warp: 32 x 32 transpose tile (padded)
+
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tc_smem) + 1023) & ~uintptr_t(1023));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                     "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_slot;
+
+    const int n_blocks = (p.M + TC_BM - 1) / TC_BM;
+    const int kb_per_seg = p.K / TC_BK;
+    const int n_kb = kb_per_seg * p.nseg;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            bool ok = true;
+            for (int rb = blockIdx.x; rb < n_blocks && ok; rb += gridDim.x) {
+                for (int tn = 0; tn < NT && ok; ++tn) {
+                    for (int kb = 0; kb < n_kb && ok; ++kb) {
+                        ok = mbar_wait(&empty_bar[stage], phase ^ 1, p.err);
+                        if (!ok) break;
+                        const int seg = kb / kb_per_seg, kk = (kb - seg * kb_per_seg) * TC_BK;
+                        const int a_col = (seg == 2 ? p.K : 0) + kk, w_col = (seg == 1 ? p.K : 0) + kk;
+                        unsigned char* sa = smem + stage * STAGE_BYTES;
+                        mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+                        tma_load_2d(sa, &map_a, a_col, rb * TC_BM, &full_bar[stage]);
+                        tma_load_2d(sa + A_BYTES, &map_w, w_col, tn * BN, &full_bar[stage]);
+                        if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase[2] = {0, 0};
+            bool ok = true;
+            for (int rb = blockIdx.x; rb < n_blocks && ok; rb += gridDim.x) {
+                for (int tn = 0; tn < NT && ok; ++tn) {
+                    ok = mbar_wait(&tempty_bar[acc], acc_phase[acc] ^ 1, p.err);
+                    if (!ok) break;
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + acc * BN;
+                    for (int kb = 0; kb < n_kb && ok; ++kb) {
+                        ok = mbar_wait(&full_bar[stage], phase, p.err);
+                        if (!ok) break;
+                        tc_fence_after();
+                        const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+                        const uint64_t adesc = umma_desc_sw128(sa), bdesc = umma_desc_sw128(sa + A_BYTES);
+#pragma unroll
+                        for (int k = 0; k < TC_BK / 16; ++k)
+                            tc_mma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, IDESC, (kb > 0 || k > 0) ? 1u : 0u);
+                        tc_commit(&empty_bar[stage]);
+                        if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+                    }
+                    tc_commit(&tfull_bar[acc]);
+                    acc_phase[acc] ^= 1;
+                    acc ^= 1;
+                }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue
+        // pass A: thread = row (TMEM lane).  Each 32 x 32 chunk goes through a padded shared tile so that the raw y
+        //         lands in the per-CTA scratch with fully coalesced 128-byte row segments.
+        // pass B: warp walks its 32 rows; the whole warp reads one row (coalesced), lane l owns columns
+        //         {128 j + 4 l .. +3}; the row's mean / rstd come from the lane that owns the row (shuffle).
+        const int quarter = warp & 3;
+        int acc = 0;
+        uint32_t acc_phase[2] = {0, 0};
+        bool ok = true;
+        float* tile = &ep_tile[quarter][0];
+        float* sblk = p.scratch + static_cast<size_t>(blockIdx.x) * TC_BM * N;       // this CTA's 128 scratch rows
+        constexpr int NJ = N / 128;
+        float4 lw[NJ], lb[NJ];
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            lw[j] = __ldg(reinterpret_cast<const float4*>(p.ln_w + 128 * j) + lane);
+            lb[j] = __ldg(reinterpret_cast<const float4*>(p.ln_b + 128 * j) + lane);
+        }
+        for (int rb = blockIdx.x; rb < n_blocks && ok; rb += gridDim.x) {
+            float shift = 0.f, s1 = 0.f, s2 = 0.f;
+            for (int tn = 0; tn < NT && ok; ++tn) {
+                ok = mbar_wait(&tfull_bar[acc], acc_phase[acc], p.err);
+                ok = __all_sync(0xffffffffu, ok);
+                if (!ok) break;
+                tc_fence_after();
+#pragma unroll 1
+                for (int c0 = 0; c0 < BN; c0 += 32) {
+                    uint32_t v[32];
+                    tc_ld32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + c0, v);
+                    tc_wait_ld();
+                    if (tn == 0 && c0 == 0) shift = __uint_as_float(v[0]);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float y = __uint_as_float(v[j]);
+                        const float d = y - shift;
+                        s1 += d;
+                        s2 = fmaf(d, d, s2);
+                        tile[lane * 33 + j] = y;                    // [row = lane][col j], padded: conflict free
+                    }
+                    __syncwarp();
+                    if (!(p.debug & 1))
+#pragma unroll 8
+                    for (int r = 0; r < 32; ++r)                   // row r of the chunk: 32 consecutive floats, one line
+                        sblk[static_cast<size_t>(quarter * 32 + r) * N + tn * BN + c0 + lane] = tile[r * 33 + lane];
+                    __syncwarp();
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+                acc_phase[acc] ^= 1;
+                acc ^= 1;
+            }
+            if (!ok) break;
+            // per-row statistics live in the lane that owns the row
+            const float m1 = s1 * (1.0f / N);
+            const float mean_own = shift + m1;
+            const float rstd_own = 1.0f / sqrtf(fmaxf(s2 * (1.0f / N) - m1 * m1, 0.f) + 1e-5f);
+            __syncwarp();                                          // this warp's scratch rows are complete (same-warp writes)
+            // software pipelined over rows: the loads of row r+1 are issued before row r is normalised and stored
+            // (the scratch loads may not be reordered across the plane stores by the compiler, so do it by hand)
+            const float* src0 = sblk + static_cast<size_t>(quarter * 32) * N;
+            float4 ycur[NJ], ynext[NJ];
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) ycur[j] = *(reinterpret_cast<const float4*>(src0 + 128 * j) + lane);
+#pragma unroll 1
+            for (int r = 0; r < ((p.debug & 2) ? 0 : 32); ++r) {
+                const float mean = __shfl_sync(0xffffffffu, mean_own, r), rstd = __shfl_sync(0xffffffffu, rstd_own, r);
+                const int row = rb * TC_BM + quarter * 32 + r;
+                if (row >= p.M) break;                             // warp-uniform
+                if (r + 1 < 32) {
+#pragma unroll
+                    for (int j = 0; j < NJ; ++j) ynext[j] = *(reinterpret_cast<const float4*>(src0 + static_cast<size_t>(r + 1) * N + 128 * j) + lane);
+                }
+                __nv_bfloat16* prow = p.out_planes + static_cast<size_t>(row) * 2 * N;
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) {
+                    const float4 y = ycur[j];
+                    float4 o;
+                    o.x = fmaxf(fmaf((y.x - mean) * rstd, lw[j].x, lb[j].x), 0.f);
+                    o.y = fmaxf(fmaf((y.y - mean) * rstd, lw[j].y, lb[j].y), 0.f);
+                    o.z = fmaxf(fmaf((y.z - mean) * rstd, lw[j].z, lb[j].z), 0.f);
+                    o.w = fmaxf(fmaf((y.w - mean) * rstd, lw[j].w, lb[j].w), 0.f);
+                    const __nv_bfloat162 h0 = __floats2bfloat162_rn(o.x, o.y), h1 = __floats2bfloat162_rn(o.z, o.w);
+                    const uint32_t hb0 = *reinterpret_cast<const uint32_t*>(&h0), hb1 = *reinterpret_cast<const uint32_t*>(&h1);
+                    const __nv_bfloat162 l0 = __floats2bfloat162_rn(o.x - __uint_as_float(hb0 << 16), o.y - __uint_as_float(hb0 & 0xffff0000u));
+                    const __nv_bfloat162 l1 = __floats2bfloat162_rn(o.z - __uint_as_float(hb1 << 16), o.w - __uint_as_float(hb1 & 0xffff0000u));
+                    uint2 hv, lv;
+                    hv.x = hb0; hv.y = hb1;
+                    lv.x = *reinterpret_cast<const uint32_t*>(&l0); lv.y = *reinterpret_cast<const uint32_t*>(&l1);
+                    *(reinterpret_cast<uint2*>(prow + 128 * j) + lane) = hv;              // 256 B coalesced per warp
+                    *(reinterpret_cast<uint2*>(prow + N + 128 * j) + lane) = lv;
+                    if (p.out_f32 != nullptr) *(reinterpret_cast<float4*>(p.out_f32 + static_cast<size_t>(row) * N + 128 * j) + lane) = o;
+                }
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) ycur[j] = ynext[j];
+            }
+            __syncwarp();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- host side
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -322,6 +542,47 @@ int gemm_tc(const void* a_planes, const void* w_planes, const float* bias, float
     int rc = gemm_tc_plan(&plan, a_planes, w_planes, bias, C, ldc, M, N, K, nseg, err_flag);
     if (rc) return rc;
     return gemm_tc_run(&plan, stream);
+}
+
+
+// relu(LayerNorm(A . W^T)) written as bf16 hi/lo planes (and optionally fp32): N must be 512 or 768.
+// scratch: gemm_tc_ln_scratch_bytes(N) bytes of device memory.
+size_t gemm_tc_ln_scratch_bytes(int N) { return static_cast<size_t>(148) * TC_BM * N * sizeof(float); }
+bool gemm_tc_ln_supported(int N) { return N == 512 || N == 768; }
+
+template <int NT>
+static int launch_tc_ln(const CUtensorMap& ma, const CUtensorMap& mw, const TcLnParams& p, cudaStream_t stream) {
+    constexpr size_t smem = TC_STAGES * (TC_BM * TC_BK * 2 + 256 * TC_BK * 2) + 1024;
+    static bool attr_set = false;
+    if (!attr_set) {
+        VQ_CUDA(cudaFuncSetAttribute(gemm_tc_ln_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        attr_set = true;
+    }
+    const int blocks = (p.M + TC_BM - 1) / TC_BM;
+    int sms = device_sm_count();
+    if (sms > 148) sms = 148;
+    gemm_tc_ln_kernel<NT><<<blocks < sms ? blocks : sms, TC_THREADS, smem, stream>>>(ma, mw, p);
+    VQ_CUDA(cudaGetLastError());
+    count_launch(1);
+    return VQCPC_OK;
+}
+
+int gemm_tc_ln(const void* a_planes, const void* w_planes, const float* ln_w, const float* ln_b, void* out_planes,
+               float* out_f32, void* scratch, int M, int N, int K, int nseg, int* err_flag, cudaStream_t stream) {
+    if (M == 0) return VQCPC_OK;
+    VQ_ARG(a_planes && w_planes && ln_w && ln_b && out_planes && scratch && err_flag, "gemm_tc_ln: null pointer");
+    VQ_ARG(gemm_tc_ln_supported(N), "gemm_tc_ln: N=%d must be 512 or 768", N);
+    VQ_ARG(K % TC_BK == 0 && K > 0 && (nseg == 1 || nseg == 3), "gemm_tc_ln: bad K / nseg");
+    const int planes = nseg == 3 ? 2 : 1;
+    CUtensorMap ma, mw;
+    int rc = make_map(&ma, a_planes, M, static_cast<long long>(planes) * K, static_cast<long long>(planes) * K, TC_BM);
+    if (rc) return rc;
+    rc = make_map(&mw, w_planes, N, static_cast<long long>(planes) * K, static_cast<long long>(planes) * K, 256);
+    if (rc) return rc;
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("VQCPC_LN_DEBUG"); dbg = e ? atoi(e) : 0; }
+    TcLnParams p{ln_w, ln_b, static_cast<__nv_bfloat16*>(out_planes), out_f32, static_cast<float*>(scratch), err_flag, M, N, K, nseg, dbg};
+    return N == 768 ? launch_tc_ln<3>(ma, mw, p, stream) : launch_tc_ln<2>(ma, mw, p, stream);
 }
 
 // ---------------------------------------------------------------------------------------------- bf16 hi/lo planes

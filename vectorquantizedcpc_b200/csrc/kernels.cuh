@@ -21,6 +21,10 @@ struct TcPlan {                      // a tcgen05 GEMM bound to fixed operand bu
 int gemm_tc_plan(TcPlan* plan, const void* a_planes, const void* w_planes, const float* bias, float* C, long long ldc, int M,
                  int N, int K, int nseg, int* err_flag);
 int gemm_tc_run(const TcPlan* plan, cudaStream_t stream);
+size_t gemm_tc_ln_scratch_bytes(int N);
+bool gemm_tc_ln_supported(int N);
+int gemm_tc_ln(const void* a_planes, const void* w_planes, const float* ln_w, const float* ln_b, void* out_planes,
+               float* out_f32, void* scratch, int M, int N, int K, int nseg, int* err_flag, cudaStream_t stream);
 int split_planes(const float* x, long long ld, void* out, long long rows, int K, cudaStream_t stream);
 
 // encoder.cu
