@@ -1,25 +1,27 @@
 // Batched sample loop: up to 64 utterances advance together through one persistent cooperative kernel.
 //
 // The single-utterance kernel (vocoder.cu) is bound by three ~1 us grid-wide exchanges per step.  With a batch the
-// same exchanges carry 64 utterances, so the cost per sample falls by the batch size and the fp32 FMA work
-// (2.7 M MAC x 64 per step) becomes the other half of the step.  Layout:
+// same exchanges carry 64 utterances and the per-step contraction  [W_hh ; fc1] (23 x 896 per CTA) x h_t (896 x 64)
+// becomes a small GEMM that runs on the TENSOR CORES:
 //   * 128 CTAs x 256 threads.  CTA j owns hidden units 7j..7j+6 (21 W_hh rows), fc1 rows 2j,2j+1, fc2 rows 2j,2j+1.
-//     Its weight slice lives in SHARED memory as float4 groups of 4 consecutive columns; a warp reads a weight
-//     group with one broadcast LDS.128 and every LANE multiplies it with the h values of ITS OWN utterance
-//     (utterance slots lane and lane + 32), so there are no cross-lane reductions at all.
-//   * warp cc streams 112 of the 896 columns for all 64 utterances (two per lane: one weight LDS.128 feeds 8
-//     FMAs, keeping the shared-memory return path below the FMA pipe); the eight chunk partials of a
-//     (row, utterance) meet in shared memory.
-//   * h_t, relu(fc1 h_t), logits and the sampled codes are exchanged through plain global buffers stored
-//     utterance-minor ([row][64]: coalesced for producers and consumers) and separated by grid barriers
-//     (__threadfence + one LL flag per CTA in its own 128-byte slot, polled by one warp): 4 barriers per step
-//     in generate mode, 2 in teacher-forced mode.  h_t is streamed from L2 (229 KB per CTA per step), never
-//     staged: every lane consumes its own utterance's column values straight from coalesced 128-byte loads.
-//   * step phases:  G  gates -> h_t                                  | barrier |
-//                   P2 W_hh h_t (for the next step) + fc1 rows -> r  | barrier |
-//                   P3 fc2 rows -> logits                            | barrier |
-//                   P4 CTA b samples utterance b (softmax + inverse CDF), writes code + waveform | barrier |
-// Arithmetic is fp32 FMA throughout (same definitions as vocoder.cu; summation order differs).
+//   * warp cc owns 112 of the 896 columns.  Its slice of the 23 weight rows (padded to 2 x 16) lives in REGISTERS for
+//     the whole kernel as mma.sync m16n8k16 A-fragments, split into bf16 hi/lo planes (112 registers per lane).
+//   * the producers of h_t (the gate phase) publish it already split:  hi = bf16(h), lo = bf16(h - hi), stored in mma
+//     B-fragment order [k-tile][utterance tile][lane][hi0 hi1 lo0 lo1], so a consumer lane fetches the four B registers
+//     of a (16 x 8) tile with ONE 16-byte strong load and a warp reads 512 contiguous bytes.  Three MMAs per (16 x 8 x 16) tile -- hi*hi, hi*lo, lo*hi -- accumulate in fp32
+//     (the dropped lo*lo term is 2^-16 relative; logits stay within 1e-5 of the fp32 kernels).
+//   * the eight column-chunk partials of a (row, utterance) meet in shared memory.
+//   * h planes, relu(fc1 h_t), logits and the sampled codes travel through plain global buffers stored utterance-minor
+//     and separated by grid barriers (__threadfence + one LL flag per CTA in its own 128-byte slot, polled by one
+//     warp; split into signal / wait): 4 barriers per step in generate mode, 2 in teacher-forced mode.
+//   * step:  G   gates -> h_t planes                                         | barrier 1 |
+//            P2a rows 16..31 (W_hh rows 16-20 + the two fc1 rows) -> r       | signal 2  | P2b slice | wait 2 |
+//            P3  fc2 rows -> logits                                          | signal 3  | P2b slice | wait 3 |
+//            P4  CTA b samples utterance b (softmax + inverse CDF)           | signal 4  | P2b slice | wait 4 |
+//     P2b = rows 0..15 (W_hh rows needed only by the NEXT step's gates): it hides behind the barrier waits; the h
+//     planes are double buffered by step parity so a straggler may still be reading while the next gates write.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -39,7 +41,7 @@ struct AbParams {
     const float* uniforms;   // (B, L)   generate mode
     const int64_t* x_in;     // (B, L)   teacher-forced mode
     float* out_wav; int32_t* out_codes; float* out_logits;
-    float* hT;               // [2][896][64]  double buffered by step parity
+    uint32_t* hP;            // [2 parity][k-tile 56][n-tile 8][lane 32][hi0 hi1 lo0 lo1] bf16x2 (mma B-fragment order)
     float* rT;               // [256][64]
     float* oT;               // [256][64]
     int* xs;                 // [64]
@@ -52,14 +54,16 @@ struct AbParams {
 };
 
 // dynamic shared memory layout (floats)
-constexpr int AB_WS = (AB_H / 4) * AB_ROWS * 4;     // weight groups: [224][23][4]
+constexpr int AB_MROWS = 32;                        // 23 weight rows padded to two m16 tiles
 constexpr int AB_W2S = (AB_FC / 4) * AB_R * 4;      // fc2 groups:    [64][2][4]
 constexpr int AB_ES = AB_Q * AB_NROW;
-constexpr int AB_PART = AB_CC * AB_ROWS * AB_B;
+constexpr int AB_PART = AB_CC * AB_MROWS * AB_B;    // [cc][row 0..31][b]
+constexpr int AB_PART2 = 4 * AB_R * AB_B;           // fc2 partials [cc3][r][b]
 constexpr int AB_HH = AB_NROW * AB_B;
 constexpr int AB_HOWN = AB_U * AB_B;
 constexpr int AB_GC = AB_NROW * AB_B;
-constexpr size_t AB_SMEM = sizeof(float) * (AB_WS + AB_W2S + AB_ES + AB_PART + AB_HH + AB_HOWN + AB_GC) + sizeof(int) * AB_B;
+constexpr size_t AB_SMEM = sizeof(float) * (AB_W2S + AB_ES + AB_PART + AB_PART2 + AB_HH + AB_HOWN + AB_GC) + sizeof(int) * AB_B;
+constexpr int AB_PLANE = (AB_H / 2) * AB_B;         // uint32 words of one bf16x2 plane: [448 column pairs][64]
 
 __device__ __forceinline__ float ld_strong(const float* p) {
     float v;
@@ -129,57 +133,70 @@ __device__ __forceinline__ bool ab_wait(ll_word* flags, uint32_t tag, volatile i
     return *abort_flag == 0;
 }
 
-// Stream column groups [c4_begin, c4_end) of this warp's 112-column chunk of h_t from L2 and accumulate rows
-// R0 .. R0+NR-1 of the CTA's weight slice for this lane's two utterances (slots lane, lane + 32).
-// hcol -> hT[chunk column 0][lane]; wg -> weight groups of the chunk ([c4][23 rows] float4, shared memory).
-template <int R0, int NR, int PF>
-__device__ __forceinline__ void ab_stream(const float* hcol, const float4* wg, int c4_begin, int c4_end, float (&acc0)[NR],
-                                          float (&acc1)[NR]) {
-    float ha[PF][4], hb[PF][4];
+__device__ __forceinline__ uint32_t ld_strong_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void split_pair(float x, float y, uint32_t& hi, uint32_t& lo) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(x, y);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(x - __uint_as_float(hi << 16), y - __uint_as_float(hi & 0xffff0000u));
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+// One m16 tile of weight rows x utterance tiles [n_begin, n_end) x this warp's 7 k-tiles (112 columns).
+// hp_hi / hp_lo -> plane word of (column pair of the chunk's first column + lane % 4, utterance lane / 4).
+// B fragment of (k-tile, n-tile): b0 = pair k*8 + lane%4, b1 = pair k*8 + 4 + lane%4, utterance n*8 + lane/4.
+// B fragments of k-tile k for all eight utterance tiles: one 16-byte strong load per tile = {hi0, hi1, lo0, lo1}
+__device__ __forceinline__ void ab_load_b(const uint4* hq, int k, uint32_t (&b)[8][4]) {
 #pragma unroll
-    for (int s = 0; s < PF - 1; ++s) {
-        if (c4_begin + s < c4_end) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                ha[s][i] = ld_strong(hcol + (4 * (c4_begin + s) + i) * AB_B);
-                hb[s][i] = ld_strong(hcol + (4 * (c4_begin + s) + i) * AB_B + 32);
-            }
-        }
+    for (int n = 0; n < 8; ++n) {
+        asm volatile("ld.relaxed.gpu.global.v4.u32 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(b[n][0]), "=r"(b[n][1]), "=r"(b[n][2]), "=r"(b[n][3])
+                     : "l"(hq + (k * 8 + n) * 32) : "memory");
     }
-    for (int base = c4_begin; base < c4_end; base += PF) {
+}
+// consecutive MMAs go to different accumulators (eight independent chains), so the tensor pipe is never waiting on
+// its own previous result
+__device__ __forceinline__ void ab_mma_ktile(const uint32_t (&a_hi)[4], const uint32_t (&a_lo)[4], const uint32_t (&b)[8][4], float (&acc)[8][4]) {
 #pragma unroll
-        for (int s = 0; s < PF; ++s) {
-            const int c4 = base + s;
-            if (c4 < c4_end) {
-                constexpr int dummy = 0; (void)dummy;
-                const int nxt = (s + PF - 1) % PF;
-                if (c4 + PF - 1 < c4_end) {
+    for (int n = 0; n < 8; ++n) mma_bf16(acc[n], a_hi, b[n][0], b[n][1]);
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        ha[nxt][i] = ld_strong(hcol + (4 * (c4 + PF - 1) + i) * AB_B);
-                        hb[nxt][i] = ld_strong(hcol + (4 * (c4 + PF - 1) + i) * AB_B + 32);
-                    }
-                }
+    for (int n = 0; n < 8; ++n) mma_bf16(acc[n], a_hi, b[n][2], b[n][3]);
 #pragma unroll
-                for (int r = 0; r < NR; ++r) {
-                    const float4 w4 = wg[c4 * AB_ROWS + R0 + r];                    // broadcast LDS.128
-                    acc0[r] = fmaf(w4.x, ha[s][0], acc0[r]); acc1[r] = fmaf(w4.x, hb[s][0], acc1[r]);
-                    acc0[r] = fmaf(w4.y, ha[s][1], acc0[r]); acc1[r] = fmaf(w4.y, hb[s][1], acc1[r]);
-                    acc0[r] = fmaf(w4.z, ha[s][2], acc0[r]); acc1[r] = fmaf(w4.z, hb[s][2], acc1[r]);
-                    acc0[r] = fmaf(w4.w, ha[s][3], acc0[r]); acc1[r] = fmaf(w4.w, hb[s][3], acc1[r]);
-                }
-            }
+    for (int n = 0; n < 8; ++n) mma_bf16(acc[n], a_lo, b[n][0], b[n][1]);
+}
+// k-tiles [K0, K1) of this warp's column chunk x all 64 utterances: the B fragments of k-tile k+1 are in flight while
+// k-tile k runs on the tensor cores.
+template <int K0, int K1>
+__device__ __forceinline__ void ab_mma_pass(const uint32_t (&a_hi)[7][4], const uint32_t (&a_lo)[7][4], const uint4* hq,
+                                            float (&acc)[8][4]) {
+    uint32_t b0[8][4], b1[8][4];
+    ab_load_b(hq, K0, b0);
+#pragma unroll
+    for (int k = K0; k < K1; k += 2) {
+        if (k + 1 < K1) ab_load_b(hq, k + 1, b1);
+        ab_mma_ktile(a_hi[k], a_lo[k], b0, acc);
+        if (k + 1 < K1) {
+            if (k + 2 < K1) ab_load_b(hq, k + 2, b0);
+            ab_mma_ktile(a_hi[k + 1], a_lo[k + 1], b1, acc);
         }
     }
 }
 
 __global__ void __launch_bounds__(AB_THREADS, 1) ar_batch_kernel(AbParams p) {
     extern __shared__ __align__(16) float ab_smem[];
-    float* Ws = ab_smem;                 // [c4][row][4]
-    float* W2s = Ws + AB_WS;             // [c4][r][4]
+    float* W2s = ab_smem;                // [c4][r][4]
     float* Es = W2s + AB_W2S;            // [x][21]
-    float* part = Es + AB_ES;            // [cc][row][b]
-    float* hh = part + AB_PART;          // [row][b]   W_hh h + b_hh
+    float* part = Es + AB_ES;            // [cc][row 0..31][b]  column-chunk partials of the weight rows
+    float* part2 = part + AB_PART;       // [cc3][r][b]         fc2 partials
+    float* hh = part2 + AB_PART2;        // [row][b]   W_hh h + b_hh
     float* hown = hh + AB_HH;            // [u][b]
     float* Gc = hown + AB_HOWN;          // [row][b]   conditioning of the current frame
     int* xcur = reinterpret_cast<int*>(Gc + AB_GC);   // [b]
@@ -193,13 +210,29 @@ __global__ void __launch_bounds__(AB_THREADS, 1) ar_batch_kernel(AbParams p) {
     const bool teacher = p.x_in != nullptr;
     const int L = p.L, nb = p.nb;
 
-    // ---- one-time staging of the CTA's weight slice
-    for (int i = tid; i < (AB_H / 4) * AB_ROWS; i += AB_THREADS) {
-        const int c4 = i / AB_ROWS, row = i % AB_ROWS;
-        const float* src = row < AB_NROW
-            ? p.w_hh + static_cast<int64_t>((row % 3) * AB_H + cta * AB_U + row / 3) * AB_H + 4 * c4
-            : p.fc1_w + static_cast<int64_t>(cta * AB_R + (row - AB_NROW)) * AB_H + 4 * c4;
-        reinterpret_cast<float4*>(Ws)[i] = __ldg(reinterpret_cast<const float4*>(src));
+    // ---- one-time: this warp's slice of the 23 weight rows as bf16 hi/lo mma A-fragments (registers)
+    // A fragment of (m-tile m, k-tile k): a[0] = (row m*16 + lane/4, cols k*16 + 2*(lane%4) + {0,1}), a[1] = row + 8,
+    // a[2] = cols + 8, a[3] = row + 8 and cols + 8.  Rows 0..20 = W_hh (3u + g), 21..22 = fc1, 23..31 = zero.
+    uint32_t a_hi[2][7][4], a_lo[2][7][4];
+    {
+        auto wrow = [&](int r) -> const float* {
+            if (r < AB_NROW) return p.w_hh + static_cast<int64_t>((r % 3) * AB_H + cta * AB_U + r / 3) * AB_H;
+            if (r < AB_ROWS) return p.fc1_w + static_cast<int64_t>(cta * AB_R + (r - AB_NROW)) * AB_H;
+            return nullptr;
+        };
+#pragma unroll
+        for (int m = 0; m < 2; ++m)
+#pragma unroll
+            for (int k = 0; k < 7; ++k)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int r = m * 16 + (lane >> 2) + (q & 1) * 8;
+                    const int c = cc * AB_CHUNK + k * 16 + 2 * (lane & 3) + (q >> 1) * 8;
+                    const float* src = wrow(r);
+                    float w0 = 0.f, w1 = 0.f;
+                    if (src != nullptr) { w0 = __ldg(src + c); w1 = __ldg(src + c + 1); }
+                    split_pair(w0, w1, a_hi[m][k][q], a_lo[m][k][q]);
+                }
     }
     for (int i = tid; i < (AB_FC / 4) * AB_R; i += AB_THREADS) {
         const int c4 = i / AB_R, r = i % AB_R;
@@ -222,13 +255,11 @@ __global__ void __launch_bounds__(AB_THREADS, 1) ar_batch_kernel(AbParams p) {
     int frame_left = 0, frame = 0;
     const bool tracing = p.trace != nullptr && cta == p.trace_cta && tid == 0;
 #define AB_TRACE(k) if (tracing && t >= p.trace_t0 && t < p.trace_t0 + p.trace_n) p.trace[(t - p.trace_t0) * 8 + (k)] = clock64();
-    constexpr int NIT = AB_CHUNK / 4, S1 = 10, S2 = 19;          // column groups per warp; slices of the W_hh rows
-    const float4* wg = reinterpret_cast<const float4*>(Ws) + static_cast<int64_t>(cc * NIT) * AB_ROWS;
     for (int t = 0; t < L; ++t) {
         AB_TRACE(0)
-        float* hT = p.hT + static_cast<int64_t>(t & 1) * AB_H * AB_B;             // double buffered by step parity
-        const float* hcol = hT + static_cast<int64_t>(cc * AB_CHUNK) * AB_B + lane;
-        // ------------------------------------------------------------------ G: conditioning reload, gates, h_t
+        uint32_t* hp = p.hP + static_cast<int64_t>(t & 1) * 2 * AB_PLANE;          // planes of h_t, double buffered by parity
+        const uint4* hq = reinterpret_cast<const uint4*>(hp) + (cc * 7 * 8) * 32 + lane;   // this warp's first (k-tile, n-tile)
+        // ------------------------------------------------------------------ G: conditioning reload, gates, h_t planes
         if (frame_left == 0) {
             for (int i = tid; i < AB_GC; i += AB_THREADS) {
                 const int row = i / AB_B, b = i % AB_B;
@@ -247,21 +278,35 @@ __global__ void __launch_bounds__(AB_THREADS, 1) ar_batch_kernel(AbParams p) {
             const float n = tanh_fast(__fmaf_rn(r, hh[(3 * u + 2) * AB_B + b], __fadd_rn(e[2], Gc[(3 * u + 2) * AB_B + b])));
             const float hn = __fmaf_rn(z, __fsub_rn(hown[i], n), n);
             hown[i] = hn;
-            hT[(cta * AB_U + u) * AB_B + b] = hn;
+            // publish h already split for the tensor cores: element (column, utterance) of the hi / lo planes
+            const int col = cta * AB_U + u;
+            const __nv_bfloat16 hb = __float2bfloat16_rn(hn);
+            const __nv_bfloat16 lb = __float2bfloat16_rn(hn - __bfloat162float(hb));
+            // fragment-major layout [k-tile 56][n-tile 8][lane 32][hi0 hi1 lo0 lo1] of bf16x2 words: the consumer lane
+            // (utterance b % 8, column pair % 4) of tile (col / 16, b / 8) finds its four B registers in one 16-byte word
+            const int pr = (col & 15) >> 1;
+            const size_t word = ((static_cast<size_t>(col >> 4) * 8 + (b >> 3)) * 32 + ((b & 7) * 4 + (pr & 3))) * 4 + (pr >> 2);
+            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(hp) + word * 2 + (col & 1);
+            dst[0] = hb;
+            dst[4] = lb;
         }
         AB_TRACE(1)
         ab_signal(p.flags, ++tag);
         if (!ab_wait(p.flags, tag, &abort_flag, p.status)) return;                  // barrier 1: h_t complete
         AB_TRACE(2)
 
-        // ------------------------------------------------------------------ P2a: the two fc1 rows first (critical path)
+        // ------------------------------------------------------------------ P2a: m-tile 1 = W_hh rows 16..20 + the fc1 rows
         {
-            float f0[AB_R] = {0.f, 0.f}, f1[AB_R] = {0.f, 0.f};
-            ab_stream<AB_NROW, AB_R, 7>(hcol, wg, 0, NIT, f0, f1);
+            float acc[8][4];
 #pragma unroll
-            for (int r = 0; r < AB_R; ++r) {
-                part[(cc * AB_R + r) * AB_B + lane] = f0[r];
-                part[(cc * AB_R + r) * AB_B + lane + 32] = f1[r];
+            for (int n = 0; n < 8; ++n) { acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f; }
+            ab_mma_pass<0, 7>(a_hi[1], a_lo[1], hq, acc);
+            // C fragment: c0,c1 = (row lane/4, utts 2*(lane%4) + {0,1}), c2,c3 = row + 8
+#pragma unroll
+            for (int n = 0; n < 8; ++n) {
+                float* d0 = part + (static_cast<size_t>(cc * AB_MROWS + 16 + (lane >> 2))) * AB_B + n * 8 + 2 * (lane & 3);
+                *reinterpret_cast<float2*>(d0) = make_float2(acc[n][0], acc[n][1]);
+                *reinterpret_cast<float2*>(d0 + 8 * AB_B) = make_float2(acc[n][2], acc[n][3]);
             }
         }
         __syncthreads();
@@ -269,17 +314,17 @@ __global__ void __launch_bounds__(AB_THREADS, 1) ar_batch_kernel(AbParams p) {
             const int r = tid / AB_B, b = tid % AB_B;
             float sum = 0.f;
 #pragma unroll
-            for (int c = 0; c < AB_CC; ++c) sum += part[(c * AB_R + r) * AB_B + b];
+            for (int c = 0; c < AB_CC; ++c) sum += part[(c * AB_MROWS + AB_NROW + r) * AB_B + b];
             p.rT[(cta * AB_R + r) * AB_B + b] = fmaxf(sum + b1_s[r], 0.f);
         }
         AB_TRACE(3)
         ab_signal(p.flags, ++tag);                                                  // barrier 2 (r complete) ...
-        // ------------------------------------------------------------------ P2b: W_hh rows for the NEXT step, in three
-        // slices that run while barriers 2, 3 and 4 are in flight
-        float acc0[AB_NROW], acc1[AB_NROW];
+        // ------------------------------------------------------------------ P2b: m-tile 0 = W_hh rows 0..15 for the NEXT
+        // step, in three k-tile slices (3 + 2 + 2) that run while barriers 2, 3 and 4 are in flight
+        float acc0[8][4];
 #pragma unroll
-        for (int r = 0; r < AB_NROW; ++r) { acc0[r] = 0.f; acc1[r] = 0.f; }
-        ab_stream<0, AB_NROW, 3>(hcol, wg, 0, S1, acc0, acc1);
+        for (int n = 0; n < 8; ++n) { acc0[n][0] = acc0[n][1] = acc0[n][2] = acc0[n][3] = 0.f; }
+        ab_mma_pass<0, 3>(a_hi[0], a_lo[0], hq, acc0);
         if (!ab_wait(p.flags, tag, &abort_flag, p.status)) return;                  // ... barrier 2 wait
         AB_TRACE(4)
 
@@ -299,15 +344,14 @@ __global__ void __launch_bounds__(AB_THREADS, 1) ar_batch_kernel(AbParams p) {
                 a1 = fmaf(w1.x, rv[4 * c4], a1); a1 = fmaf(w1.y, rv[4 * c4 + 1], a1);
                 a1 = fmaf(w1.z, rv[4 * c4 + 2], a1); a1 = fmaf(w1.w, rv[4 * c4 + 3], a1);
             }
-            __syncthreads();                                                        // fc1 partials in `part` fully consumed
-            part[(cc3 * AB_R + 0) * AB_B + slot] = a0;
-            part[(cc3 * AB_R + 1) * AB_B + slot] = a1;
+            part2[(cc3 * AB_R + 0) * AB_B + slot] = a0;
+            part2[(cc3 * AB_R + 1) * AB_B + slot] = a1;
         }
         __syncthreads();
         if (tid < AB_R * AB_B) {
             const int r = tid / AB_B, b = tid % AB_B;
-            const float o = (part[(0 * AB_R + r) * AB_B + b] + part[(1 * AB_R + r) * AB_B + b]) +
-                            (part[(2 * AB_R + r) * AB_B + b] + part[(3 * AB_R + r) * AB_B + b]) + b2_s[r];
+            const float o = (part2[(0 * AB_R + r) * AB_B + b] + part2[(1 * AB_R + r) * AB_B + b]) +
+                            (part2[(2 * AB_R + r) * AB_B + b] + part2[(3 * AB_R + r) * AB_B + b]) + b2_s[r];
             p.oT[(cta * AB_R + r) * AB_B + b] = o;
             if (p.out_logits != nullptr && b < nb)
                 p.out_logits[(static_cast<int64_t>(b) * L + t) * AB_Q + cta * AB_R + r] = o;
@@ -315,7 +359,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1) ar_batch_kernel(AbParams p) {
         AB_TRACE(5)
         if (!teacher) {
             ab_signal(p.flags, ++tag);                                              // barrier 3 (logits complete) ...
-            ab_stream<0, AB_NROW, 3>(hcol, wg, S1, S2, acc0, acc1);
+            ab_mma_pass<3, 5>(a_hi[0], a_lo[0], hq, acc0);
             if (!ab_wait(p.flags, tag, &abort_flag, p.status)) return;
             AB_TRACE(6)
             // -------------------------------------------------------------- P4: CTA b samples utterance b
@@ -358,16 +402,16 @@ __global__ void __launch_bounds__(AB_THREADS, 1) ar_batch_kernel(AbParams p) {
             }
             AB_TRACE(7)
             ab_signal(p.flags, ++tag);                                              // barrier 4 (codes complete) ...
-            ab_stream<0, AB_NROW, 3>(hcol, wg, S2, NIT, acc0, acc1);
+            ab_mma_pass<5, 7>(a_hi[0], a_lo[0], hq, acc0);
         } else {
-            ab_stream<0, AB_NROW, 3>(hcol, wg, S1, NIT, acc0, acc1);
-            __syncthreads();                                                        // fc2 partials in `part` consumed
+            ab_mma_pass<3, 7>(a_hi[0], a_lo[0], hq, acc0);
         }
         // W_hh partials of the eight column chunks meet in shared memory
 #pragma unroll
-        for (int r = 0; r < AB_NROW; ++r) {
-            part[(cc * AB_ROWS + r) * AB_B + lane] = acc0[r];
-            part[(cc * AB_ROWS + r) * AB_B + lane + 32] = acc1[r];
+        for (int n = 0; n < 8; ++n) {
+            float* d0 = part + (static_cast<size_t>(cc * AB_MROWS + (lane >> 2))) * AB_B + n * 8 + 2 * (lane & 3);
+            *reinterpret_cast<float2*>(d0) = make_float2(acc0[n][0], acc0[n][1]);
+            *reinterpret_cast<float2*>(d0 + 8 * AB_B) = make_float2(acc0[n][2], acc0[n][3]);
         }
         if (!teacher) {
             if (!ab_wait(p.flags, tag, &abort_flag, p.status)) return;              // ... barrier 4 wait (ends in __syncthreads)
@@ -383,7 +427,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1) ar_batch_kernel(AbParams p) {
             const int row = i / AB_B, b = i % AB_B;
             float sum = 0.f;
 #pragma unroll
-            for (int c = 0; c < AB_CC; ++c) sum += part[(c * AB_ROWS + row) * AB_B + b];
+            for (int c = 0; c < AB_CC; ++c) sum += part[(c * AB_MROWS + row) * AB_B + b];
             hh[i] = sum + bhh_s[row];
         }
         // (the __syncthreads at the top of the next step orders hh / xcur before the gates)
@@ -391,7 +435,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1) ar_batch_kernel(AbParams p) {
 #undef AB_TRACE
 }
 
-// workspace of one launch: [hT 2x896x64][rT 256x64][oT 256x64][xs 64][pad][flags 128x16 words]
+// workspace of one launch: [h planes 2 parity x (hi, lo) x 448x64 words][rT 256x64][oT 256x64][xs 64][pad][flags 128x16 words]
 static size_t ab_ws_bytes() {
     return sizeof(float) * (2 * AB_H + 2 * AB_FC) * AB_B + 256 + sizeof(ll_word) * AB_CTAS * 16;
 }
@@ -421,8 +465,8 @@ int ar_batch_run(const vqcpc_vocoder_weights* w, const float* G, const float* un
         p.out_wav = out_wav ? out_wav + static_cast<int64_t>(b0) * L : nullptr;
         p.out_codes = out_codes ? out_codes + static_cast<int64_t>(b0) * L : nullptr;
         p.out_logits = out_logits ? out_logits + static_cast<int64_t>(b0) * L * AB_Q : nullptr;
-        p.hT = reinterpret_cast<float*>(base);
-        p.rT = p.hT + 2 * AB_H * AB_B;
+        p.hP = reinterpret_cast<uint32_t*>(base);
+        p.rT = reinterpret_cast<float*>(base) + 2 * AB_H * AB_B;
         p.oT = p.rT + AB_FC * AB_B;
         p.xs = reinterpret_cast<int*>(p.oT + AB_FC * AB_B);
         p.flags = reinterpret_cast<ll_word*>(base + sizeof(float) * (2 * AB_H + 2 * AB_FC) * AB_B + 256);
