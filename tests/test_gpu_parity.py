@@ -386,18 +386,24 @@ def test_vocoder_batched_generate_equals_single_utterance_runs():
     assert torch.equal(tf1[0], tf[5])
 
 
-def test_vocoder_large_batch_kernel_matches_oracle():
-    """B >= 8 runs the grid-barrier batched kernel (64 utterance slots per launch): B = 70 -> launches of 64 + 6.
+@pytest.mark.parametrize("B,sel", [
+    (8, [0, 5, 7]),                            # one group of 8 (NT = 4)
+    (21, [0, 10, 11, 20]),                     # two groups 11 + 10 (NT = 4)
+    (64, [0, 31, 32, 63]),                     # two full groups of 32
+    (70, [0, 1, 31, 34, 35, 63, 64, 69]),      # two groups 35 + 35 (NT = 8)
+    (131, [0, 63, 64, 127, 128, 130]),         # launches of 128 (64 + 64) and 3
+])
+def test_vocoder_large_batch_kernel_matches_oracle(B, sel):
+    """B >= 8 runs the grid-barrier batched kernel (two interleaved utterance groups, up to 128 utterances per launch).
     Teacher-forced logits against the oracle, and free-running samples consistent with the oracle's CDF."""
     voc, sd = make_vocoder()
-    B, Tc, L = 70, 1, 200
+    Tc, L = 1, 200
     codes, spk, u = fixtures.vocoder_inputs(B, Tc, seed=9, n_steps=L)
     cd, sdv, ud = codes.to(dev()), spk.to(dev()), u.to(dev())
     wav, x, logits = voc.generate(cd, sdv, uniforms=ud, n_steps=L, return_mulaw=True, return_logits=True)
     wav, x, logits = wav.cpu(), x.cpu(), logits.cpu()
     lut = torch.from_numpy(mulaw.mulaw_decode_lut(8))
     assert torch.equal(wav, lut[x])
-    sel = [0, 1, 31, 32, 63, 64, 69]
     x_in = torch.cat([torch.full((B, 1), 128, dtype=torch.int64), x[:, :-1]], dim=1)
     ref = ovoc.forward_teacher_forced(sd, x_in[sel], codes[sel], spk[sel])
     err = float((logits[sel] - ref).abs().max())

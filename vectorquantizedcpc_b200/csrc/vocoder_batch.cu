@@ -4,18 +4,19 @@
 // same exchanges carry 64 utterances and the per-step contraction  [W_hh ; fc1] (23 x 896 per CTA) x h_t (896 x 64)
 // becomes a small GEMM that runs on the TENSOR CORES:
 //   * 128 CTAs x 256 threads.  CTA j owns hidden units 7j..7j+6 (21 W_hh rows), fc1 rows 2j,2j+1, fc2 rows 2j,2j+1.
-//   * warp cc owns 112 of the 896 columns.  Its slice of the 23 weight rows (padded to 2 x 16) lives in REGISTERS for
-//     the whole kernel as mma.sync m16n8k16 A-fragments, split into bf16 hi/lo planes (112 registers per lane).
+//   * warp cc owns 112 of the 896 columns.  The utterances are the M side of mma.sync m16n8k16 (4 tiles of 16), the
+//     weight rows the N side (23 rows -> 3 tiles of 8, one padding row).  The warp's slice of the weight rows lives in
+//     REGISTERS for the whole kernel as B-fragments, split into bf16 hi/lo planes (84 registers per lane).
 //   * the producers of h_t (the gate phase) publish it already split:  hi = bf16(h), lo = bf16(h - hi), stored in mma
-//     B-fragment order [k-tile][utterance tile][lane][hi0 hi1 lo0 lo1], so a consumer lane fetches the four B registers
-//     of a (16 x 8) tile with ONE 16-byte strong load and a warp reads 512 contiguous bytes.  Three MMAs per (16 x 8 x 16) tile -- hi*hi, hi*lo, lo*hi -- accumulate in fp32
+//     A-fragment order [k-tile][utterance tile][lane][hi a0..a3, lo a0..a3], so a consumer lane fetches the eight A
+//     registers of a (16 x 16) tile with two 16-byte strong loads and a warp reads 1 KB contiguous.  Three MMAs per (16 x 8 x 16) tile -- hi*hi, hi*lo, lo*hi -- accumulate in fp32
 //     (the dropped lo*lo term is 2^-16 relative; logits stay within 1e-5 of the fp32 kernels).
 //   * the eight column-chunk partials of a (row, utterance) meet in shared memory.
 //   * h planes, relu(fc1 h_t), logits and the sampled codes travel through plain global buffers stored utterance-minor
 //     and separated by grid barriers (__threadfence + one LL flag per CTA in its own 128-byte slot, polled by one
 //     warp; split into signal / wait): 4 barriers per step in generate mode, 2 in teacher-forced mode.
 //   * step:  G   gates -> h_t planes                                         | barrier 1 |
-//            P2a rows 16..31 (W_hh rows 16-20 + the two fc1 rows) -> r       | signal 2  | P2b slice | wait 2 |
+//            P2a rows 16..23 (W_hh rows 16-20 + the two fc1 rows) -> r       | signal 2  | P2b slice | wait 2 |
 //            P3  fc2 rows -> logits                                          | signal 3  | P2b slice | wait 3 |
 //            P4  CTA b samples utterance b (softmax + inverse CDF)           | signal 4  | P2b slice | wait 4 |
 //     P2b = rows 0..15 (W_hh rows needed only by the NEXT step's gates): it hides behind the barrier waits; the h
@@ -41,7 +42,7 @@ struct AbParams {
     const float* uniforms;   // (B, L)   generate mode
     const int64_t* x_in;     // (B, L)   teacher-forced mode
     float* out_wav; int32_t* out_codes; float* out_logits;
-    uint32_t* hP;            // [2 parity][k-tile 56][n-tile 8][lane 32][hi0 hi1 lo0 lo1] bf16x2 (mma B-fragment order)
+    uint32_t* hP;            // [2 parity][k-tile 56][m-tile 4][lane 32][hi a0..a3, lo a0..a3] bf16x2 (mma A-fragment order)
     float* rT;               // [256][64]
     float* oT;               // [256][64]
     int* xs;                 // [64]
@@ -54,10 +55,11 @@ struct AbParams {
 };
 
 // dynamic shared memory layout (floats)
-constexpr int AB_MROWS = 32;                        // 23 weight rows padded to two m16 tiles
+constexpr int AB_MROWS = 24;                        // 23 weight rows padded to three n8 tiles
+constexpr int AB_PSTR = 68;                         // utterance stride of a `part` row (conflict-free C-fragment stores)
 constexpr int AB_W2S = (AB_FC / 4) * AB_R * 4;      // fc2 groups:    [64][2][4]
 constexpr int AB_ES = AB_Q * AB_NROW;
-constexpr int AB_PART = AB_CC * AB_MROWS * AB_B;    // [cc][row 0..31][b]
+constexpr int AB_PART = AB_CC * AB_MROWS * AB_PSTR;  // [cc][row 0..23][b (stride 68)]
 constexpr int AB_PART2 = 4 * AB_R * AB_B;           // fc2 partials [cc3][r][b]
 constexpr int AB_HH = AB_NROW * AB_B;
 constexpr int AB_HOWN = AB_U * AB_B;
@@ -153,41 +155,70 @@ __device__ __forceinline__ void split_pair(float x, float y, uint32_t& hi, uint3
 // One m16 tile of weight rows x utterance tiles [n_begin, n_end) x this warp's 7 k-tiles (112 columns).
 // hp_hi / hp_lo -> plane word of (column pair of the chunk's first column + lane % 4, utterance lane / 4).
 // B fragment of (k-tile, n-tile): b0 = pair k*8 + lane%4, b1 = pair k*8 + 4 + lane%4, utterance n*8 + lane/4.
-// B fragments of k-tile k for all eight utterance tiles: one 16-byte strong load per tile = {hi0, hi1, lo0, lo1}
-__device__ __forceinline__ void ab_load_b(const uint4* hq, int k, uint32_t (&b)[8][4]) {
+// A fragments (h) of k-tile k for the four utterance tiles: a[m][0..3] = hi a0..a3, a[m][4..7] = lo a0..a3
+__device__ __forceinline__ void ab_load_a(const uint4* hq, int k, uint32_t (&a)[4][8]) {
 #pragma unroll
-    for (int n = 0; n < 8; ++n) {
+    for (int m = 0; m < 4; ++m) {
+        const uint4* src = hq + ((k * 4 + m) * 32) * 2;
         asm volatile("ld.relaxed.gpu.global.v4.u32 {%0,%1,%2,%3}, [%4];"
-                     : "=r"(b[n][0]), "=r"(b[n][1]), "=r"(b[n][2]), "=r"(b[n][3])
-                     : "l"(hq + (k * 8 + n) * 32) : "memory");
+                     : "=r"(a[m][0]), "=r"(a[m][1]), "=r"(a[m][2]), "=r"(a[m][3]) : "l"(src) : "memory");
+        asm volatile("ld.relaxed.gpu.global.v4.u32 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(a[m][4]), "=r"(a[m][5]), "=r"(a[m][6]), "=r"(a[m][7]) : "l"(src + 1) : "memory");
     }
 }
-// consecutive MMAs go to different accumulators (eight independent chains), so the tensor pipe is never waiting on
-// its own previous result
-__device__ __forceinline__ void ab_mma_ktile(const uint32_t (&a_hi)[4], const uint32_t (&a_lo)[4], const uint32_t (&b)[8][4], float (&acc)[8][4]) {
-#pragma unroll
-    for (int n = 0; n < 8; ++n) mma_bf16(acc[n], a_hi, b[n][0], b[n][1]);
-#pragma unroll
-    for (int n = 0; n < 8; ++n) mma_bf16(acc[n], a_hi, b[n][2], b[n][3]);
-#pragma unroll
-    for (int n = 0; n < 8; ++n) mma_bf16(acc[n], a_lo, b[n][0], b[n][1]);
+__device__ __forceinline__ void mma_bf16_a(float (&d)[4], const uint32_t* a, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
-// k-tiles [K0, K1) of this warp's column chunk x all 64 utterances: the B fragments of k-tile k+1 are in flight while
-// k-tile k runs on the tensor cores.
-template <int K0, int K1>
-__device__ __forceinline__ void ab_mma_pass(const uint32_t (&a_hi)[7][4], const uint32_t (&a_lo)[7][4], const uint4* hq,
-                                            float (&acc)[8][4]) {
-    uint32_t b0[8][4], b1[8][4];
-    ab_load_b(hq, K0, b0);
+// one k-tile x weight-row tiles [N0, N1): consecutive MMAs go to different accumulators
+template <int N0, int N1>
+__device__ __forceinline__ void ab_mma_ktile(const uint32_t (&w_hi)[3][2], const uint32_t (&w_lo)[3][2], const uint32_t (&a)[4][8],
+                                             float (&acc)[4][N1 - N0][4]) {
+#pragma unroll
+    for (int n = N0; n < N1; ++n)
+#pragma unroll
+        for (int m = 0; m < 4; ++m) mma_bf16_a(acc[m][n - N0], &a[m][0], w_hi[n][0], w_hi[n][1]);
+#pragma unroll
+    for (int n = N0; n < N1; ++n)
+#pragma unroll
+        for (int m = 0; m < 4; ++m) mma_bf16_a(acc[m][n - N0], &a[m][4], w_hi[n][0], w_hi[n][1]);
+#pragma unroll
+    for (int n = N0; n < N1; ++n)
+#pragma unroll
+        for (int m = 0; m < 4; ++m) mma_bf16_a(acc[m][n - N0], &a[m][0], w_lo[n][0], w_lo[n][1]);
+}
+// k-tiles [K0, K1) of this warp's column chunk x all 64 utterances x weight-row tiles [N0, N1): the A fragments of
+// k-tile k+1 are in flight while k-tile k runs on the tensor cores.
+template <int K0, int K1, int N0, int N1>
+__device__ __forceinline__ void ab_mma_pass(const uint32_t (&w_hi)[7][3][2], const uint32_t (&w_lo)[7][3][2], const uint4* hq,
+                                            float (&acc)[4][N1 - N0][4]) {
+    uint32_t a0[4][8], a1[4][8];
+    ab_load_a(hq, K0, a0);
 #pragma unroll
     for (int k = K0; k < K1; k += 2) {
-        if (k + 1 < K1) ab_load_b(hq, k + 1, b1);
-        ab_mma_ktile(a_hi[k], a_lo[k], b0, acc);
+        if (k + 1 < K1) ab_load_a(hq, k + 1, a1);
+        ab_mma_ktile<N0, N1>(w_hi[k], w_lo[k], a0, acc);
         if (k + 1 < K1) {
-            if (k + 2 < K1) ab_load_b(hq, k + 2, b0);
-            ab_mma_ktile(a_hi[k + 1], a_lo[k + 1], b1, acc);
+            if (k + 2 < K1) ab_load_a(hq, k + 2, a0);
+            ab_mma_ktile<N0, N1>(w_hi[k + 1], w_lo[k + 1], a1, acc);
         }
     }
+}
+// C fragment of (utterance tile m, weight-row tile n): c0,c1 = (utt m*16 + lane/4, rows n*8 + 2*(lane%4) + {0,1}),
+// c2,c3 = utt + 8
+template <int N0, int N1>
+__device__ __forceinline__ void ab_store_c(float* part_cc, int lane, const float (&acc)[4][N1 - N0][4]) {
+#pragma unroll
+    for (int m = 0; m < 4; ++m)
+#pragma unroll
+        for (int n = N0; n < N1; ++n) {
+            float* d = part_cc + (n * 8 + 2 * (lane & 3)) * AB_PSTR + m * 16 + (lane >> 2);
+            d[0] = acc[m][n - N0][0];
+            d[AB_PSTR] = acc[m][n - N0][1];
+            d[8] = acc[m][n - N0][2];
+            d[AB_PSTR + 8] = acc[m][n - N0][3];
+        }
 }
 
 __global__ void __launch_bounds__(AB_THREADS, 1) ar_batch_kernel(AbParams p) {
@@ -210,10 +241,10 @@ __global__ void __launch_bounds__(AB_THREADS, 1) ar_batch_kernel(AbParams p) {
     const bool teacher = p.x_in != nullptr;
     const int L = p.L, nb = p.nb;
 
-    // ---- one-time: this warp's slice of the 23 weight rows as bf16 hi/lo mma A-fragments (registers)
-    // A fragment of (m-tile m, k-tile k): a[0] = (row m*16 + lane/4, cols k*16 + 2*(lane%4) + {0,1}), a[1] = row + 8,
-    // a[2] = cols + 8, a[3] = row + 8 and cols + 8.  Rows 0..20 = W_hh (3u + g), 21..22 = fc1, 23..31 = zero.
-    uint32_t a_hi[2][7][4], a_lo[2][7][4];
+    // ---- one-time: this warp's slice of the 23 weight rows as bf16 hi/lo mma B-fragments (registers)
+    // B fragment of (k-tile k, row tile n): b[0] = (cols k*16 + 2*(lane%4) + {0,1}, row n*8 + lane/4), b[1] = cols + 8.
+    // Rows 0..20 = W_hh (3u + g), 21..22 = fc1, 23 = zero.
+    uint32_t w_hi[7][3][2], w_lo[7][3][2];
     {
         auto wrow = [&](int r) -> const float* {
             if (r < AB_NROW) return p.w_hh + static_cast<int64_t>((r % 3) * AB_H + cta * AB_U + r / 3) * AB_H;
@@ -221,17 +252,16 @@ __global__ void __launch_bounds__(AB_THREADS, 1) ar_batch_kernel(AbParams p) {
             return nullptr;
         };
 #pragma unroll
-        for (int m = 0; m < 2; ++m)
+        for (int k = 0; k < 7; ++k)
 #pragma unroll
-            for (int k = 0; k < 7; ++k)
+            for (int n = 0; n < 3; ++n)
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int r = m * 16 + (lane >> 2) + (q & 1) * 8;
-                    const int c = cc * AB_CHUNK + k * 16 + 2 * (lane & 3) + (q >> 1) * 8;
-                    const float* src = wrow(r);
+                for (int q = 0; q < 2; ++q) {
+                    const float* src = wrow(n * 8 + (lane >> 2));
+                    const int c = cc * AB_CHUNK + k * 16 + 2 * (lane & 3) + q * 8;
                     float w0 = 0.f, w1 = 0.f;
                     if (src != nullptr) { w0 = __ldg(src + c); w1 = __ldg(src + c + 1); }
-                    split_pair(w0, w1, a_hi[m][k][q], a_lo[m][k][q]);
+                    split_pair(w0, w1, w_hi[k][n][q], w_lo[k][n][q]);
                 }
     }
     for (int i = tid; i < (AB_FC / 4) * AB_R; i += AB_THREADS) {
@@ -258,7 +288,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1) ar_batch_kernel(AbParams p) {
     for (int t = 0; t < L; ++t) {
         AB_TRACE(0)
         uint32_t* hp = p.hP + static_cast<int64_t>(t & 1) * 2 * AB_PLANE;          // planes of h_t, double buffered by parity
-        const uint4* hq = reinterpret_cast<const uint4*>(hp) + (cc * 7 * 8) * 32 + lane;   // this warp's first (k-tile, n-tile)
+        const uint4* hq = reinterpret_cast<const uint4*>(hp) + ((cc * 7 * 4) * 32 + lane) * 2;   // this warp's first (k-tile, utterance tile)
         // ------------------------------------------------------------------ G: conditioning reload, gates, h_t planes
         if (frame_left == 0) {
             for (int i = tid; i < AB_GC; i += AB_THREADS) {
@@ -282,49 +312,48 @@ __global__ void __launch_bounds__(AB_THREADS, 1) ar_batch_kernel(AbParams p) {
             const int col = cta * AB_U + u;
             const __nv_bfloat16 hb = __float2bfloat16_rn(hn);
             const __nv_bfloat16 lb = __float2bfloat16_rn(hn - __bfloat162float(hb));
-            // fragment-major layout [k-tile 56][n-tile 8][lane 32][hi0 hi1 lo0 lo1] of bf16x2 words: the consumer lane
-            // (utterance b % 8, column pair % 4) of tile (col / 16, b / 8) finds its four B registers in one 16-byte word
-            const int pr = (col & 15) >> 1;
-            const size_t word = ((static_cast<size_t>(col >> 4) * 8 + (b >> 3)) * 32 + ((b & 7) * 4 + (pr & 3))) * 4 + (pr >> 2);
+            // fragment-major layout [k-tile 56][utterance tile 4][lane 32][hi a0..a3, lo a0..a3] of bf16x2 words: the
+            // consumer lane (utterance % 8, column pair % 4) of tile (col / 16, b / 16) finds its eight A registers in
+            // 32 contiguous bytes; register a(rsel + 2 csel) holds (utterance + 8 rsel, columns + 8 csel)
+            const int c16 = col & 15, u16 = b & 15;
+            const size_t word = ((static_cast<size_t>(col >> 4) * 4 + (b >> 4)) * 32 + ((u16 & 7) * 4 + ((c16 & 7) >> 1))) * 8 +
+                                (u16 >> 3) + 2 * (c16 >> 3);
             __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(hp) + word * 2 + (col & 1);
             dst[0] = hb;
-            dst[4] = lb;
+            dst[8] = lb;
         }
         AB_TRACE(1)
         ab_signal(p.flags, ++tag);
         if (!ab_wait(p.flags, tag, &abort_flag, p.status)) return;                  // barrier 1: h_t complete
         AB_TRACE(2)
 
-        // ------------------------------------------------------------------ P2a: m-tile 1 = W_hh rows 16..20 + the fc1 rows
+        // ------------------------------------------------------------------ P2a: row tile 2 = W_hh rows 16..20 + the fc1 rows
+        float* part_cc = part + cc * AB_MROWS * AB_PSTR;
         {
-            float acc[8][4];
+            float acc[4][1][4];
 #pragma unroll
-            for (int n = 0; n < 8; ++n) { acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f; }
-            ab_mma_pass<0, 7>(a_hi[1], a_lo[1], hq, acc);
-            // C fragment: c0,c1 = (row lane/4, utts 2*(lane%4) + {0,1}), c2,c3 = row + 8
-#pragma unroll
-            for (int n = 0; n < 8; ++n) {
-                float* d0 = part + (static_cast<size_t>(cc * AB_MROWS + 16 + (lane >> 2))) * AB_B + n * 8 + 2 * (lane & 3);
-                *reinterpret_cast<float2*>(d0) = make_float2(acc[n][0], acc[n][1]);
-                *reinterpret_cast<float2*>(d0 + 8 * AB_B) = make_float2(acc[n][2], acc[n][3]);
-            }
+            for (int m = 0; m < 4; ++m) { acc[m][0][0] = acc[m][0][1] = acc[m][0][2] = acc[m][0][3] = 0.f; }
+            ab_mma_pass<0, 7, 2, 3>(w_hi, w_lo, hq, acc);
+            ab_store_c<2, 3>(part_cc, lane, acc);
         }
         __syncthreads();
         if (tid < AB_R * AB_B) {
             const int r = tid / AB_B, b = tid % AB_B;
             float sum = 0.f;
 #pragma unroll
-            for (int c = 0; c < AB_CC; ++c) sum += part[(c * AB_MROWS + AB_NROW + r) * AB_B + b];
+            for (int c = 0; c < AB_CC; ++c) sum += part[(c * AB_MROWS + AB_NROW + r) * AB_PSTR + b];
             p.rT[(cta * AB_R + r) * AB_B + b] = fmaxf(sum + b1_s[r], 0.f);
         }
         AB_TRACE(3)
         ab_signal(p.flags, ++tag);                                                  // barrier 2 (r complete) ...
-        // ------------------------------------------------------------------ P2b: m-tile 0 = W_hh rows 0..15 for the NEXT
-        // step, in three k-tile slices (3 + 2 + 2) that run while barriers 2, 3 and 4 are in flight
-        float acc0[8][4];
+        // ------------------------------------------------------------------ P2b: row tiles 0, 1 = W_hh rows 0..15 for the
+        // NEXT step, in three k-tile slices (3 + 2 + 2) that run while barriers 2, 3 and 4 are in flight
+        float acc0[4][2][4];
 #pragma unroll
-        for (int n = 0; n < 8; ++n) { acc0[n][0] = acc0[n][1] = acc0[n][2] = acc0[n][3] = 0.f; }
-        ab_mma_pass<0, 3>(a_hi[0], a_lo[0], hq, acc0);
+        for (int m = 0; m < 4; ++m)
+#pragma unroll
+            for (int n = 0; n < 2; ++n) { acc0[m][n][0] = acc0[m][n][1] = acc0[m][n][2] = acc0[m][n][3] = 0.f; }
+        ab_mma_pass<0, 3, 0, 2>(w_hi, w_lo, hq, acc0);
         if (!ab_wait(p.flags, tag, &abort_flag, p.status)) return;                  // ... barrier 2 wait
         AB_TRACE(4)
 
@@ -359,7 +388,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1) ar_batch_kernel(AbParams p) {
         AB_TRACE(5)
         if (!teacher) {
             ab_signal(p.flags, ++tag);                                              // barrier 3 (logits complete) ...
-            ab_mma_pass<3, 5>(a_hi[0], a_lo[0], hq, acc0);
+            ab_mma_pass<3, 5, 0, 2>(w_hi, w_lo, hq, acc0);
             if (!ab_wait(p.flags, tag, &abort_flag, p.status)) return;
             AB_TRACE(6)
             // -------------------------------------------------------------- P4: CTA b samples utterance b
@@ -402,17 +431,12 @@ __global__ void __launch_bounds__(AB_THREADS, 1) ar_batch_kernel(AbParams p) {
             }
             AB_TRACE(7)
             ab_signal(p.flags, ++tag);                                              // barrier 4 (codes complete) ...
-            ab_mma_pass<5, 7>(a_hi[0], a_lo[0], hq, acc0);
+            ab_mma_pass<5, 7, 0, 2>(w_hi, w_lo, hq, acc0);
         } else {
-            ab_mma_pass<3, 7>(a_hi[0], a_lo[0], hq, acc0);
+            ab_mma_pass<3, 7, 0, 2>(w_hi, w_lo, hq, acc0);
         }
         // W_hh partials of the eight column chunks meet in shared memory
-#pragma unroll
-        for (int n = 0; n < 8; ++n) {
-            float* d0 = part + (static_cast<size_t>(cc * AB_MROWS + (lane >> 2))) * AB_B + n * 8 + 2 * (lane & 3);
-            *reinterpret_cast<float2*>(d0) = make_float2(acc0[n][0], acc0[n][1]);
-            *reinterpret_cast<float2*>(d0 + 8 * AB_B) = make_float2(acc0[n][2], acc0[n][3]);
-        }
+        ab_store_c<0, 2>(part_cc, lane, acc0);
         if (!teacher) {
             if (!ab_wait(p.flags, tag, &abort_flag, p.status)) return;              // ... barrier 4 wait (ends in __syncthreads)
             if (tid < AB_B) {
@@ -427,7 +451,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1) ar_batch_kernel(AbParams p) {
             const int row = i / AB_B, b = i % AB_B;
             float sum = 0.f;
 #pragma unroll
-            for (int c = 0; c < AB_CC; ++c) sum += part[(c * AB_MROWS + row) * AB_B + b];
+            for (int c = 0; c < AB_CC; ++c) sum += part[(c * AB_MROWS + row) * AB_PSTR + b];
             hh[i] = sum + bhh_s[row];
         }
         // (the __syncthreads at the top of the next step orders hh / xcur before the gates)
