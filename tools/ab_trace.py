@@ -10,7 +10,7 @@ codes, spk, u = fixtures.vocoder_inputs(B, 10, seed=0)
 lib = _lib.lib()
 cd, sd, ud = codes.to(dev), spk.to(dev), u.to(dev)
 n, t0 = 128, 1000
-names = ["G(gates)", "barrier1", "P2a(fc1)", "signal2+slice1+wait2", "P3(fc2)", "signal3+slice2+wait3", "P4(sample)", "signal4+slice3+wait4+reduce"]
+names = ["G(gates)", "barrier1", "P2a(fc1)", "signal2+slice1+wait2", "P3(fc2)", "logits hop (LL)", "P4(sample)", "codes hop (LL)+reduce"]
 with torch.no_grad():
     voc.generate(cd, sd, uniforms=ud)
     for cta in (0, 77):

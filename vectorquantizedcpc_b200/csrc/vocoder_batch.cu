@@ -12,15 +12,18 @@
 //     registers of a (16 x 16) tile with two 16-byte strong loads and a warp reads 1 KB contiguous.  Three MMAs per (16 x 8 x 16) tile -- hi*hi, hi*lo, lo*hi -- accumulate in fp32
 //     (the dropped lo*lo term is 2^-16 relative; logits stay within 1e-5 of the fp32 kernels).
 //   * the eight column-chunk partials of a (row, utterance) meet in shared memory.
-//   * h planes, relu(fc1 h_t), logits and the sampled codes travel through plain global buffers stored utterance-minor
-//     and separated by grid barriers (__threadfence + one LL flag per CTA in its own 128-byte slot, polled by one
-//     warp; split into signal / wait): 4 barriers per step in generate mode, 2 in teacher-forced mode.
-//   * step:  G   gates -> h_t planes                                         | barrier 1 |
-//            P2a rows 16..23 (W_hh rows 16-20 + the two fc1 rows) -> r       | signal 2  | P2b slice | wait 2 |
-//            P3  fc2 rows -> logits                                          | signal 3  | P2b slice | wait 3 |
-//            P4  CTA b samples utterance b (softmax + inverse CDF)           | signal 4  | P2b slice | wait 4 |
-//     P2b = rows 0..15 (W_hh rows needed only by the NEXT step's gates): it hides behind the barrier waits; the h
-//     planes are double buffered by step parity so a straggler may still be reading while the next gates write.
+//   * h_t and relu(fc1 h_t) travel through plain global buffers separated by grid barriers (__threadfence + one LL
+//     flag per CTA in its own 128-byte slot; split into signal / wait): 2 barriers per step.  The logits (to the 64
+//     sampling CTAs) and the sampled codes (to everyone) travel as LL words -- value and step tag in one 8-byte
+//     store, polled by the reader -- which costs one ~1 us hop instead of a fence + flag + poll round.
+//   * a ninth warp per CTA polls the barriers and does the sampling, so the eight tensor-core warps never wait on it.
+//   * step:  G   gates -> h_t                                               | barrier 1 |
+//            P2a rows 16..23 (W_hh rows 16-20 + the two fc1 rows) -> r       | signal 2  | P2b | wait 2 |
+//            P3  fc2 rows -> logits (LL)
+//            sampler warp of CTA b: wait logits, sample utterance b, publish code (LL);  everyone polls the 64 codes
+//     P2b = rows 0..15 (W_hh rows needed only by the NEXT step's gates): runs while barrier 2 is in flight and, after
+//     P3, while the sampler warp works.
+
 #include <cuda_bf16.h>
 
 #include "common.cuh"
@@ -31,7 +34,8 @@ namespace vqcpc {
 constexpr int AB_H = 896, AB_G = 2688, AB_FC = 256, AB_Q = 256;
 constexpr int AB_CTAS = 128, AB_U = 7, AB_R = 2, AB_NROW = 21, AB_ROWS = AB_NROW + AB_R;   // 23 rows ride the h stream
 constexpr int AB_B = 64;                          // utterance slots per launch
-constexpr int AB_THREADS = 256;
+constexpr int AB_THREADS = 288;                   // 8 tensor-core warps + 1 sampler / barrier-poller warp
+constexpr int AB_SW = 8;                          // index of the sampler warp
 constexpr int AB_CC = 8, AB_CHUNK = AB_H / AB_CC; // 112 columns per warp in the h stream
 constexpr int AB_X_INIT = 128;
 
@@ -44,8 +48,8 @@ struct AbParams {
     float* out_wav; int32_t* out_codes; float* out_logits;
     uint32_t* hP;            // [2 parity][k-tile 56][m-tile 4][lane 32][hi a0..a3, lo a0..a3] bf16x2 (mma A-fragment order)
     float* rT;               // [256][64]
-    float* oT;               // [256][64]
-    int* xs;                 // [64]
+    ll_word* oLL;            // [64][256]  logits as LL words {tag = step + 1, value}, utterance-major
+    ll_word* xLL;            // [64]       sampled codes as LL words
     ll_word* flags;          // [128][16]
     int* status;
     long long g_stride;
@@ -73,38 +77,8 @@ __device__ __forceinline__ float ld_strong(const float* p) {
     return v;
 }
 
-// grid barrier: every CTA publishes `tag` in its own 128-byte slot after a fence; warp 0 polls all 128 slots.
-// Returns false (CTA-uniform) on timeout.
-__device__ __forceinline__ bool ab_grid_sync(ll_word* flags, uint32_t tag, volatile int* abort_flag, int* status) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        ll_store(flags + blockIdx.x * 16, 0.f, tag);
-    }
-    if (threadIdx.x < 32) {
-        const long long t0 = clock64();
-        for (;;) {
-            bool ok = true;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const uint32_t seen = ll_tag(ll_load(flags + (32 * k + threadIdx.x) * 16));
-                ok = ok && (static_cast<int32_t>(seen - tag) >= 0);
-            }
-            if (__all_sync(0xffffffffu, ok)) break;
-            if (clock64() - t0 > LL_TIMEOUT_CYCLES) {
-                *abort_flag = 1;
-                if (threadIdx.x == 0) atomicExch(status, VQCPC_ERR_TIMEOUT);
-                break;
-            }
-        }
-        __threadfence();
-    }
-    __syncthreads();
-    return *abort_flag == 0;
-}
-
-// split barrier: signal = publish this CTA's arrival (after a fence), wait = poll all 128 arrivals.  Work placed
-// between the two hides the ~4000-cycle barrier latency.
+// grid barrier, split: signal = publish this CTA's arrival in its own 128-byte slot (after a fence), wait = the sampler
+// warp polls all 128 arrivals.  Work placed between the two hides the ~4000-cycle barrier latency.
 __device__ __forceinline__ void ab_signal(ll_word* flags, uint32_t tag) {
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -113,19 +87,20 @@ __device__ __forceinline__ void ab_signal(ll_word* flags, uint32_t tag) {
     }
 }
 __device__ __forceinline__ bool ab_wait(ll_word* flags, uint32_t tag, volatile int* abort_flag, int* status) {
-    if (threadIdx.x < 32) {
+    if (threadIdx.x >= AB_SW * 32) {                  // the sampler warp polls; the tensor-core warps go straight to bar.sync
+        const int ln = threadIdx.x & 31;
         const long long t0 = clock64();
         for (;;) {
             bool ok = true;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                const uint32_t seen = ll_tag(ll_load(flags + (32 * k + threadIdx.x) * 16));
+                const uint32_t seen = ll_tag(ll_load(flags + (32 * k + ln) * 16));
                 ok = ok && (static_cast<int32_t>(seen - tag) >= 0);
             }
             if (__all_sync(0xffffffffu, ok)) break;
             if (clock64() - t0 > LL_TIMEOUT_CYCLES) {
                 *abort_flag = 1;
-                if (threadIdx.x == 0) atomicExch(status, VQCPC_ERR_TIMEOUT);
+                if (ln == 0) atomicExch(status, VQCPC_ERR_TIMEOUT);
                 break;
             }
         }
@@ -174,25 +149,25 @@ __device__ __forceinline__ void mma_bf16_a(float (&d)[4], const uint32_t* a, uin
 // one k-tile x weight-row tiles [N0, N1): consecutive MMAs go to different accumulators
 template <int N0, int N1>
 __device__ __forceinline__ void ab_mma_ktile(const uint32_t (&w_hi)[3][2], const uint32_t (&w_lo)[3][2], const uint32_t (&a)[4][8],
-                                             float (&acc)[4][N1 - N0][4]) {
+                                             float (&acc)[4][3][4]) {
 #pragma unroll
     for (int n = N0; n < N1; ++n)
 #pragma unroll
-        for (int m = 0; m < 4; ++m) mma_bf16_a(acc[m][n - N0], &a[m][0], w_hi[n][0], w_hi[n][1]);
+        for (int m = 0; m < 4; ++m) mma_bf16_a(acc[m][n], &a[m][0], w_hi[n][0], w_hi[n][1]);
 #pragma unroll
     for (int n = N0; n < N1; ++n)
 #pragma unroll
-        for (int m = 0; m < 4; ++m) mma_bf16_a(acc[m][n - N0], &a[m][4], w_hi[n][0], w_hi[n][1]);
+        for (int m = 0; m < 4; ++m) mma_bf16_a(acc[m][n], &a[m][4], w_hi[n][0], w_hi[n][1]);
 #pragma unroll
     for (int n = N0; n < N1; ++n)
 #pragma unroll
-        for (int m = 0; m < 4; ++m) mma_bf16_a(acc[m][n - N0], &a[m][0], w_lo[n][0], w_lo[n][1]);
+        for (int m = 0; m < 4; ++m) mma_bf16_a(acc[m][n], &a[m][0], w_lo[n][0], w_lo[n][1]);
 }
 // k-tiles [K0, K1) of this warp's column chunk x all 64 utterances x weight-row tiles [N0, N1): the A fragments of
 // k-tile k+1 are in flight while k-tile k runs on the tensor cores.
 template <int K0, int K1, int N0, int N1>
 __device__ __forceinline__ void ab_mma_pass(const uint32_t (&w_hi)[7][3][2], const uint32_t (&w_lo)[7][3][2], const uint4* hq,
-                                            float (&acc)[4][N1 - N0][4]) {
+                                            float (&acc)[4][3][4]) {
     uint32_t a0[4][8], a1[4][8];
     ab_load_a(hq, K0, a0);
 #pragma unroll
@@ -208,16 +183,16 @@ __device__ __forceinline__ void ab_mma_pass(const uint32_t (&w_hi)[7][3][2], con
 // C fragment of (utterance tile m, weight-row tile n): c0,c1 = (utt m*16 + lane/4, rows n*8 + 2*(lane%4) + {0,1}),
 // c2,c3 = utt + 8
 template <int N0, int N1>
-__device__ __forceinline__ void ab_store_c(float* part_cc, int lane, const float (&acc)[4][N1 - N0][4]) {
+__device__ __forceinline__ void ab_store_c(float* part_cc, int lane, const float (&acc)[4][3][4]) {
 #pragma unroll
     for (int m = 0; m < 4; ++m)
 #pragma unroll
         for (int n = N0; n < N1; ++n) {
             float* d = part_cc + (n * 8 + 2 * (lane & 3)) * AB_PSTR + m * 16 + (lane >> 2);
-            d[0] = acc[m][n - N0][0];
-            d[AB_PSTR] = acc[m][n - N0][1];
-            d[8] = acc[m][n - N0][2];
-            d[AB_PSTR + 8] = acc[m][n - N0][3];
+            d[0] = acc[m][n][0];
+            d[AB_PSTR] = acc[m][n][1];
+            d[8] = acc[m][n][2];
+            d[AB_PSTR + 8] = acc[m][n][3];
         }
 }
 
@@ -285,6 +260,8 @@ __global__ void __launch_bounds__(AB_THREADS, 1) ar_batch_kernel(AbParams p) {
     int frame_left = 0, frame = 0;
     const bool tracing = p.trace != nullptr && cta == p.trace_cta && tid == 0;
 #define AB_TRACE(k) if (tracing && t >= p.trace_t0 && t < p.trace_t0 + p.trace_n) p.trace[(t - p.trace_t0) * 8 + (k)] = clock64();
+    const bool tracing_s = p.trace != nullptr && cta == p.trace_cta && tid == AB_SW * 32;
+#define AB_TRACE_S(k) if (tracing_s && t >= p.trace_t0 && t < p.trace_t0 + p.trace_n) p.trace[(t - p.trace_t0) * 8 + (k)] = clock64();
     for (int t = 0; t < L; ++t) {
         AB_TRACE(0)
         uint32_t* hp = p.hP + static_cast<int64_t>(t & 1) * 2 * AB_PLANE;          // planes of h_t, double buffered by parity
@@ -328,11 +305,15 @@ __global__ void __launch_bounds__(AB_THREADS, 1) ar_batch_kernel(AbParams p) {
         AB_TRACE(2)
 
         // ------------------------------------------------------------------ P2a: row tile 2 = W_hh rows 16..20 + the fc1 rows
+        // (the only part of the contraction the critical path needs: legacy HMMA issues at ~24 cycles per SMSP on this
+        // part, so every MMA moved out of here is ~50 cycles off the step)
         float* part_cc = part + cc * AB_MROWS * AB_PSTR;
-        {
-            float acc[4][1][4];
+        float acc[4][3][4];
+        if (warp < AB_SW) {
 #pragma unroll
-            for (int m = 0; m < 4; ++m) { acc[m][0][0] = acc[m][0][1] = acc[m][0][2] = acc[m][0][3] = 0.f; }
+            for (int m = 0; m < 4; ++m)
+#pragma unroll
+                for (int n = 0; n < 3; ++n) { acc[m][n][0] = acc[m][n][1] = acc[m][n][2] = acc[m][n][3] = 0.f; }
             ab_mma_pass<0, 7, 2, 3>(w_hi, w_lo, hq, acc);
             ab_store_c<2, 3>(part_cc, lane, acc);
         }
@@ -346,19 +327,14 @@ __global__ void __launch_bounds__(AB_THREADS, 1) ar_batch_kernel(AbParams p) {
         }
         AB_TRACE(3)
         ab_signal(p.flags, ++tag);                                                  // barrier 2 (r complete) ...
-        // ------------------------------------------------------------------ P2b: row tiles 0, 1 = W_hh rows 0..15 for the
-        // NEXT step, in three k-tile slices (3 + 2 + 2) that run while barriers 2, 3 and 4 are in flight
-        float acc0[4][2][4];
-#pragma unroll
-        for (int m = 0; m < 4; ++m)
-#pragma unroll
-            for (int n = 0; n < 2; ++n) { acc0[m][n][0] = acc0[m][n][1] = acc0[m][n][2] = acc0[m][n][3] = 0.f; }
-        ab_mma_pass<0, 3, 0, 2>(w_hi, w_lo, hq, acc0);
+        // ------------------------------------------------------------------ P2b: row tiles 0, 1 (W_hh rows 0..15, needed only
+        // by the NEXT step's gates): k-tiles 0..2 while barrier 2 is in flight, the rest after P3 while the sampler works
+        if (warp < AB_SW) ab_mma_pass<0, 3, 0, 2>(w_hi, w_lo, hq, acc);
         if (!ab_wait(p.flags, tag, &abort_flag, p.status)) return;                  // ... barrier 2 wait
         AB_TRACE(4)
 
         // ------------------------------------------------------------------ P3: fc2 rows over relu(fc1 h_t)
-        {
+        if (warp < AB_SW) {
             float a0 = 0.f, a1 = 0.f;
             const float* rcol = p.rT + static_cast<int64_t>(cc3 * 64) * AB_B + slot;
             const float4* w2g = reinterpret_cast<const float4*>(W2s) + static_cast<int64_t>(cc3 * 16) * AB_R;
@@ -381,72 +357,88 @@ __global__ void __launch_bounds__(AB_THREADS, 1) ar_batch_kernel(AbParams p) {
             const int r = tid / AB_B, b = tid % AB_B;
             const float o = (part2[(0 * AB_R + r) * AB_B + b] + part2[(1 * AB_R + r) * AB_B + b]) +
                             (part2[(2 * AB_R + r) * AB_B + b] + part2[(3 * AB_R + r) * AB_B + b]) + b2_s[r];
-            p.oT[(cta * AB_R + r) * AB_B + b] = o;
+            // logits travel as LL words (value + step tag in one 8-byte store): no fence, no barrier
+            if (!teacher && b < nb) ll_store(p.oLL + b * AB_Q + cta * AB_R + r, o, static_cast<uint32_t>(t + 1));
             if (p.out_logits != nullptr && b < nb)
                 p.out_logits[(static_cast<int64_t>(b) * L + t) * AB_Q + cta * AB_R + r] = o;
         }
         AB_TRACE(5)
-        if (!teacher) {
-            ab_signal(p.flags, ++tag);                                              // barrier 3 (logits complete) ...
-            ab_mma_pass<3, 5, 0, 2>(w_hi, w_lo, hq, acc0);
-            if (!ab_wait(p.flags, tag, &abort_flag, p.status)) return;
-            AB_TRACE(6)
-            // -------------------------------------------------------------- P4: CTA b samples utterance b
-            if (warp == 0 && cta < nb) {
-                const int b = cta;
-                float ov[8];
+        if (warp < AB_SW) {
+            ab_mma_pass<3, 7, 0, 2>(w_hi, w_lo, hq, acc);
+            ab_store_c<0, 2>(part_cc, lane, acc);                                   // the eight column-chunk partials meet in SMEM
+        } else if (!teacher && cta < nb) {
+            // -------------------------------------------------------------- P4 (sampler warp): CTA b samples utterance b
+            const int b = cta;
+            const ll_word* src = p.oLL + b * AB_Q + 8 * lane;
+            float ov[8];
+            {
+                const long long t0 = clock64();
+                for (;;) {
+                    bool ok = true;
 #pragma unroll
-                for (int k = 0; k < 8; ++k) ov[k] = ld_strong(p.oT + (8 * lane + k) * AB_B + b);
-                float m = ov[0];
-#pragma unroll
-                for (int k = 1; k < 8; ++k) m = fmaxf(m, ov[k]);
-                m = warp_max(m);
-                float c[8];
-                float run = 0.f;
-#pragma unroll
-                for (int k = 0; k < 8; ++k) { run += __expf(ov[k] - m); c[k] = run; }
-                float incl = run;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const float v = __shfl_up_sync(0xffffffffu, incl, o);
-                    if (lane >= o) incl += v;
-                }
-                const float excl = incl - run;
-                const float S = __shfl_sync(0xffffffffu, incl, 31);
-                const float thr = __ldg(p.uniforms + static_cast<int64_t>(b) * L + t) * S;
-                int loc = 8;
-#pragma unroll
-                for (int k = 7; k >= 0; --k) if (excl + c[k] > thr) loc = k;
-                const unsigned hit = __ballot_sync(0xffffffffu, loc < 8);
-                int x = AB_Q - 1;
-                if (hit != 0u) {
-                    const int src = __ffs(hit) - 1;
-                    x = 8 * src + __shfl_sync(0xffffffffu, loc, src);
-                }
-                if (lane == 0) {
-                    p.xs[b] = x;
-                    if (p.out_wav) p.out_wav[static_cast<int64_t>(b) * L + t] = __ldg(p.lut + x);
-                    if (p.out_codes) p.out_codes[static_cast<int64_t>(b) * L + t] = x;
+                    for (int k = 0; k < 8; k += 2) {
+                        ll_word w0, w1;
+                        ll_load2(src + k, w0, w1);
+                        ok = ok && ll_tag(w0) == static_cast<uint32_t>(t + 1) && ll_tag(w1) == static_cast<uint32_t>(t + 1);
+                        ov[k] = ll_val(w0); ov[k + 1] = ll_val(w1);
+                    }
+                    if (__all_sync(0xffffffffu, ok)) break;
+                    if (clock64() - t0 > LL_TIMEOUT_CYCLES) {
+                        abort_flag = 1;
+                        if (lane == 0) atomicExch(p.status, VQCPC_ERR_TIMEOUT);
+                        break;
+                    }
                 }
             }
-            AB_TRACE(7)
-            ab_signal(p.flags, ++tag);                                              // barrier 4 (codes complete) ...
-            ab_mma_pass<5, 7, 0, 2>(w_hi, w_lo, hq, acc0);
-        } else {
-            ab_mma_pass<3, 7, 0, 2>(w_hi, w_lo, hq, acc0);
-        }
-        // W_hh partials of the eight column chunks meet in shared memory
-        ab_store_c<0, 2>(part_cc, lane, acc0);
-        if (!teacher) {
-            if (!ab_wait(p.flags, tag, &abort_flag, p.status)) return;              // ... barrier 4 wait (ends in __syncthreads)
-            if (tid < AB_B) {
-                int xv = 0;
-                if (tid < nb) asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(xv) : "l"(p.xs + tid) : "memory");
-                xcur[tid] = xv;
+            AB_TRACE_S(6)
+            float m = ov[0];
+#pragma unroll
+            for (int k = 1; k < 8; ++k) m = fmaxf(m, ov[k]);
+            m = warp_max(m);
+            float c[8];
+            float run = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { run += __expf(ov[k] - m); c[k] = run; }
+            float incl = run;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const float v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
             }
-        } else {
-            __syncthreads();
+            const float excl = incl - run;
+            const float S = __shfl_sync(0xffffffffu, incl, 31);
+            const float thr = __ldg(p.uniforms + static_cast<int64_t>(b) * L + t) * S;
+            int loc = 8;
+#pragma unroll
+            for (int k = 7; k >= 0; --k) if (excl + c[k] > thr) loc = k;
+            const unsigned hit = __ballot_sync(0xffffffffu, loc < 8);
+            int x = AB_Q - 1;
+            if (hit != 0u) {
+                const int srcl = __ffs(hit) - 1;
+                x = 8 * srcl + __shfl_sync(0xffffffffu, loc, srcl);
+            }
+            if (lane == 0) {
+                ll_store(p.xLL + b, __int_as_float(x), static_cast<uint32_t>(t + 1));   // the code travels as an LL word too
+                if (p.out_wav) p.out_wav[static_cast<int64_t>(b) * L + t] = __ldg(p.lut + x);
+                if (p.out_codes) p.out_codes[static_cast<int64_t>(b) * L + t] = x;
+            }
+            AB_TRACE_S(7)
         }
+        if (!teacher && tid < AB_B) {
+            // every CTA picks up the 64 sampled codes (threads of warps 0 and 1, after their W_hh slice)
+            int xv = 0;
+            if (tid < nb) {
+                const long long t0 = clock64();
+                for (;;) {
+                    const ll_word w = ll_load(p.xLL + tid);
+                    if (ll_tag(w) == static_cast<uint32_t>(t + 1)) { xv = __float_as_int(ll_val(w)); break; }
+                    if (clock64() - t0 > LL_TIMEOUT_CYCLES) { abort_flag = 1; atomicExch(p.status, VQCPC_ERR_TIMEOUT); break; }
+                }
+            }
+            xcur[tid] = xv;
+        }
+        __syncthreads();
+        if (abort_flag != 0) return;
         for (int i = tid; i < AB_NROW * AB_B; i += AB_THREADS) {
             const int row = i / AB_B, b = i % AB_B;
             float sum = 0.f;
@@ -457,11 +449,12 @@ __global__ void __launch_bounds__(AB_THREADS, 1) ar_batch_kernel(AbParams p) {
         // (the __syncthreads at the top of the next step orders hh / xcur before the gates)
     }
 #undef AB_TRACE
+#undef AB_TRACE_S
 }
 
-// workspace of one launch: [h planes 2 parity x (hi, lo) x 448x64 words][rT 256x64][oT 256x64][xs 64][pad][flags 128x16 words]
+// workspace of one launch: [h 2 parity x 896x64 words][rT 256x64][oLL 64x256 LL words][xLL 64 LL words][flags 128x16 words]
 static size_t ab_ws_bytes() {
-    return sizeof(float) * (2 * AB_H + 2 * AB_FC) * AB_B + 256 + sizeof(ll_word) * AB_CTAS * 16;
+    return sizeof(float) * (2 * AB_H + AB_FC) * AB_B + sizeof(ll_word) * (AB_B * AB_Q + AB_B + AB_CTAS * 16);
 }
 size_t ar_batch_workspace_bytes() { return align_up(ab_ws_bytes(), 256); }
 
@@ -491,9 +484,9 @@ int ar_batch_run(const vqcpc_vocoder_weights* w, const float* G, const float* un
         p.out_logits = out_logits ? out_logits + static_cast<int64_t>(b0) * L * AB_Q : nullptr;
         p.hP = reinterpret_cast<uint32_t*>(base);
         p.rT = reinterpret_cast<float*>(base) + 2 * AB_H * AB_B;
-        p.oT = p.rT + AB_FC * AB_B;
-        p.xs = reinterpret_cast<int*>(p.oT + AB_FC * AB_B);
-        p.flags = reinterpret_cast<ll_word*>(base + sizeof(float) * (2 * AB_H + 2 * AB_FC) * AB_B + 256);
+        p.oLL = reinterpret_cast<ll_word*>(p.rT + AB_FC * AB_B);
+        p.xLL = p.oLL + AB_B * AB_Q;
+        p.flags = p.xLL + AB_B;
         p.status = status;
         p.L = L; p.upsample = w->upsample_t; p.nb = nb;
         p.trace = g_ab_trace; p.trace_cta = g_ab_trace_cta; p.trace_t0 = g_ab_trace_t0; p.trace_n = g_ab_trace_n;
