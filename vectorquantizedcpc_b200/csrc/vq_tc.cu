@@ -334,7 +334,8 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vq_tc_kernel(const __grid_const
             // other's, so both know the row's best two candidates and each takes half of the output work.
             float b1 = fminf(b1a, b1b), b2 = fminf(fmaxf(b1a, b1b), fminf(b2a, b2b));
             part[buf][ch][row] = make_float2(b1, b2);
-            bar_sync(1, VT_EPI_WARPS * 32);
+            bar_sync(1 + quarter, 64);            // only the two warps of this row quarter meet: a warp delayed by an exact
+                                                  // re-decision does not hold up the other six
             {
                 const float2 o = part[buf][ch ^ 1][row];
                 const float n1 = fminf(b1, o.x), n2 = fminf(fmaxf(b1, o.x), fminf(b2, o.y));
@@ -349,15 +350,23 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vq_tc_kernel(const __grid_const
                 const float margin = 6.2e-5f * xn * emax + 1.3e-4f * fmaxf(fabsf(b1), fabsf(b2));
                 if (b2 - b1 <= margin) {
                     // exact fp32 scores of both candidates (arithmetic of the fp32 kernel); ties -> lower index
-                    const float* xr = p.x + fr * VT_D;
-                    const float* ea = p.codebook + i1 * VT_D;
-                    const float* eb = p.codebook + i2 * VT_D;
+                    // (same summation order as the fp32 kernel; 16-byte loads, 12 in flight per round trip)
+                    const float4* xr = reinterpret_cast<const float4*>(p.x + fr * VT_D);
+                    const float4* ea = reinterpret_cast<const float4*>(p.codebook + i1 * VT_D);
+                    const float4* eb = reinterpret_cast<const float4*>(p.codebook + i2 * VT_D);
                     float da = 0.f, db = 0.f;
-#pragma unroll 8
-                    for (int k = 0; k < VT_D; ++k) {
-                        const float xv = __ldg(xr + k);
-                        da = fmaf(xv, __ldg(ea + k), da);
-                        db = fmaf(xv, __ldg(eb + k), db);
+#pragma unroll 1
+                    for (int k4 = 0; k4 < VT_D / 4; k4 += 4) {
+                        float4 xv[4], av[4], bv[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) { xv[u] = __ldg(xr + k4 + u); av[u] = __ldg(ea + k4 + u); bv[u] = __ldg(eb + k4 + u); }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            da = fmaf(xv[u].x, av[u].x, da); db = fmaf(xv[u].x, bv[u].x, db);
+                            da = fmaf(xv[u].y, av[u].y, da); db = fmaf(xv[u].y, bv[u].y, db);
+                            da = fmaf(xv[u].z, av[u].z, da); db = fmaf(xv[u].z, bv[u].z, db);
+                            da = fmaf(xv[u].w, av[u].w, da); db = fmaf(xv[u].w, bv[u].w, db);
+                        }
                     }
                     const float sa = fmaf(-2.0f, da, e2s[i1]), sb = fmaf(-2.0f, db, e2s[i2]);
                     if (sb < sa || (sb == sa && i2 < i1)) i1 = i2;
