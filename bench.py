@@ -448,9 +448,9 @@ def main():
     # ---- the other BASELINE configs, measured in the same run on rank 0's GPU (N = 1 only)
     if not args.no_extra and world == 1:
         extra = {}
-        # sample-loop throughput beyond B = 1: B = 4 (one interleaved launch of the latency kernel) and B = 64 (the
-        # grid-barrier batched kernel, 64 utterance slots per launch), 1 s each
-        for Bb in (4, 64):
+        # sample-loop throughput beyond B = 1: B = 4 (one interleaved launch of the latency kernel), B = 64 (the batched
+        # tensor-core kernel, one group of 64 utterances) and B = 128 (its two-group variant), 1 s each
+        for Bb in (4, 64, 128):
             cb, sb, _ = fixtures.vocoder_inputs(Bb, 50, seed=100 + Bb)
             cbd, sbd = cb.to(dev), sb.to(dev)
             with torch.no_grad():

@@ -387,14 +387,15 @@ def test_vocoder_batched_generate_equals_single_utterance_runs():
 
 
 @pytest.mark.parametrize("B,sel", [
-    (8, [0, 5, 7]),                            # one group of 8 (NT = 4)
-    (21, [0, 10, 11, 20]),                     # two groups 11 + 10 (NT = 4)
-    (64, [0, 31, 32, 63]),                     # two full groups of 32
-    (70, [0, 1, 31, 34, 35, 63, 64, 69]),      # two groups 35 + 35 (NT = 8)
-    (131, [0, 63, 64, 127, 128, 130]),         # launches of 128 (64 + 64) and 3
+    (8, [0, 5, 7]),                            # one group (ar_batch_kernel)
+    (21, [0, 10, 11, 20]),
+    (64, [0, 31, 32, 63]),                     # one full group
+    (70, [0, 1, 31, 34, 35, 63, 64, 69]),      # two interleaved groups 35 + 35 (ar_batch2_kernel)
+    (131, [0, 63, 64, 127, 128, 130]),         # launches of 128 (two groups 64 + 64) and 3
 ])
 def test_vocoder_large_batch_kernel_matches_oracle(B, sel):
-    """B >= 8 runs the grid-barrier batched kernel (two interleaved utterance groups, up to 128 utterances per launch).
+    """B >= 8 runs the batched tensor-core kernels: one group of up to 64 utterances per launch, or two interleaved
+    groups for 65..128.
     Teacher-forced logits against the oracle, and free-running samples consistent with the oracle's CDF."""
     voc, sd = make_vocoder()
     Tc, L = 1, 200
@@ -421,6 +422,31 @@ def test_vocoder_large_batch_kernel_matches_oracle(B, sel):
     # teacher-forced mode through the batched kernel
     tf = voc.forward(x_in.to(dev()), cd, sdv).cpu()
     assert float((tf[sel] - ref).abs().max()) < ATOL_LOGITS
+
+
+def test_vocoder_two_group_kernel_equals_single_group_kernel():
+    """65..128 utterances per launch run as two interleaved groups (ar_batch2_kernel); per utterance the arithmetic is
+    that of the single-group kernel, so samples and teacher-forced logits must agree bit for bit."""
+    from vectorquantizedcpc_b200 import _lib
+    voc, _ = make_vocoder()
+    B, Tc, L = 100, 1, 240
+    codes, spk, u = fixtures.vocoder_inputs(B, Tc, seed=21, n_steps=L)
+    cd, sdv, ud = codes.to(dev()), spk.to(dev()), u.to(dev())
+    wav2, x2, lg2 = voc.generate(cd, sdv, uniforms=ud, n_steps=L, return_mulaw=True, return_logits=True)
+    try:
+        _lib.check(_lib.lib().vqcpc_debug_set_ar_poll_gap(400 | (1 << 29)), "debug")      # two-group variant off
+        wav1, x1, lg1 = voc.generate(cd, sdv, uniforms=ud, n_steps=L, return_mulaw=True, return_logits=True)
+    finally:
+        _lib.check(_lib.lib().vqcpc_debug_set_ar_poll_gap(400), "debug")
+    assert torch.equal(x1, x2) and torch.equal(wav1, wav2) and torch.equal(lg1, lg2)
+    x_in = torch.cat([torch.full((B, 1), 128, dtype=torch.int64, device=dev()), x2[:, :-1].long()], dim=1)
+    tf2 = voc.forward(x_in, cd, sdv)
+    try:
+        _lib.check(_lib.lib().vqcpc_debug_set_ar_poll_gap(400 | (1 << 29)), "debug")
+        tf1 = voc.forward(x_in, cd, sdv)
+    finally:
+        _lib.check(_lib.lib().vqcpc_debug_set_ar_poll_gap(400), "debug")
+    assert torch.equal(tf1, tf2)
 
 
 def test_vocoder_argument_errors():
