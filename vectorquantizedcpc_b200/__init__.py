@@ -3,5 +3,6 @@
 tarepan/VectorQuantizedCPC, behind the reference's own Python method surface.  See DESIGN.md."""
 from .model import ConfEncoder, Encoder, VQEmbeddingEMA  # noqa: F401
 from .network_vocoder import ConfRNNMSVocoder, ConfVocoder, RNNMSVocoder, Vocoder  # noqa: F401
+from . import checkpoint  # noqa: F401  (upstream-format checkpoint ingestion)
 
 __all__ = ["ConfEncoder", "Encoder", "VQEmbeddingEMA", "ConfVocoder", "ConfRNNMSVocoder", "RNNMSVocoder", "Vocoder"]
