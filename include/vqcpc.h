@@ -151,6 +151,13 @@ size_t vqcpc_vocoder_workspace_bytes(int32_t B, int32_t Tc);
 int vqcpc_vocoder_condition(const vqcpc_vocoder_weights* w, const int64_t* codes, const int64_t* speaker,
                             int32_t B, int32_t Tc, void* workspace, size_t workspace_bytes,
                             float* out_G, float* out_p, void* stream);
+/* Ragged batches (the reference sidesteps them with batch 1, vocoder.py:69, datamodule.py:93):
+ * codes (B, Tc) padded to the longest utterance, code_lengths (B,) int32 device array with 1 <= code_lengths[b] <= Tc.
+ * Utterance b's bidirectional prenet runs over its own 2 * code_lengths[b] frames, so its first 320 * code_lengths[b]
+ * samples are exactly those of an unpadded run; the padded tail of out_G / out_p is zero. */
+int vqcpc_vocoder_condition_ragged(const vqcpc_vocoder_weights* w, const int64_t* codes, const int64_t* speaker,
+                                   const int32_t* code_lengths, int32_t B, int32_t Tc, void* workspace,
+                                   size_t workspace_bytes, float* out_G, float* out_p, void* stream);
 /* Vocoder.generate (network_vocoder.py:69-78): one persistent kernel launch per utterance, L <= 320*Tc steps.
  * uniforms (B, L) in [0,1): the injected per-(utterance, step) randomness of the inverse-CDF sampler.
  * out_wav (B, L) fp32; nullable out_codes (B, L) int32 mu-law codes; nullable out_logits (B, L, 256). */

@@ -449,6 +449,51 @@ def test_vocoder_two_group_kernel_equals_single_group_kernel():
     assert torch.equal(tf1, tf2)
 
 
+def test_vocoder_ragged_batch_equals_unpadded_runs():
+    """a padded batch with ``lengths`` must give every utterance exactly its unpadded result -- the
+    bidirectional prenet starts each backward pass at the utterance's own last frame."""
+    voc, _ = make_vocoder()
+    lens = [3, 1, 2]
+    B, Tc = len(lens), max(lens)
+    codes, spk, u = fixtures.vocoder_inputs(B, Tc, seed=31)
+    cd, sdv, ud = codes.to(dev()), spk.to(dev()), u.to(dev())
+    G, p = voc.condition(cd, sdv, return_prenet=True, lengths=lens)
+    wav, x = voc.generate(cd, sdv, uniforms=ud, return_mulaw=True, lengths=torch.tensor(lens))
+    for b, n in enumerate(lens):
+        G1, p1 = voc.condition(cd[b:b + 1, :n], sdv[b:b + 1], return_prenet=True)
+        assert torch.equal(p[b, :2 * n], p1[0]) and torch.equal(G[b, :2 * n], G1[0]), b
+        assert not p[b, 2 * n:].any()
+        w1, x1 = voc.generate(cd[b:b + 1, :n], sdv[b:b + 1], uniforms=ud[b:b + 1, :320 * n], return_mulaw=True)
+        assert torch.equal(wav[b, :320 * n], w1[0]) and torch.equal(x[b, :320 * n], x1[0]), b
+        assert not wav[b, 320 * n:].any()
+    # a padded run WITHOUT lengths differs for the short utterances (backward pass sees the padding)
+    p_pad = voc.condition(cd, sdv, return_prenet=True)[1]
+    assert not torch.equal(p_pad[1, :2], p[1, :2])
+    x_in = torch.cat([torch.full((B, 1), 128, dtype=torch.int64, device=dev()), x[:, :-1]], dim=1)
+    tf = voc.forward(x_in, cd, sdv, lengths=lens)
+    tf1 = voc.forward(x_in[1:2, :320], cd[1:2, :1], sdv[1:2])
+    assert torch.equal(tf[1, :320], tf1[0])
+    with pytest.raises(ValueError):
+        voc.generate(cd, sdv, lengths=[3, 0, 2])
+    with pytest.raises(ValueError):
+        voc.generate(cd, sdv, lengths=[3, 4, 2])
+
+
+def test_encoder_ragged_batch_equals_unpadded_runs():
+    """Encoder.encode_ragged: zero padding is exact for the valid frames (zero-padded conv, per-frame MLP, causal LSTM)."""
+    enc, _ = make_encoder(512, True)
+    g = torch.Generator().manual_seed(5)
+    mels = [torch.rand(80, T, generator=g).to(dev()) for T in (200, 101, 57, 2)]
+    out = enc.encode_ragged(mels)
+    for m, (z, c, idx) in zip(mels, out):
+        z1, c1, i1 = enc.encode(m[None])
+        assert idx.shape[0] == (m.shape[1] - 2) // 2 + 1
+        assert torch.equal(idx, i1[0]) and torch.equal(z, z1[0]) and torch.equal(c, c1[0])
+    assert enc.encode_ragged([]) == []
+    with pytest.raises(ValueError):
+        enc.encode_ragged([torch.rand(79, 10, device=dev())])
+
+
 def test_vocoder_argument_errors():
     voc, _ = make_vocoder()
     z = torch.zeros(1, 2, dtype=torch.int64, device=dev())

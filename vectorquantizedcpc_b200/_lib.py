@@ -65,6 +65,7 @@ SIGNATURES = {
     "vqcpc_vocoder_pack": (C.c_int, [C.POINTER(VocoderWeights), _vp, _vp]),
     "vqcpc_vocoder_workspace_bytes": (_sz, [_i32, _i32]),
     "vqcpc_vocoder_condition": (C.c_int, [C.POINTER(VocoderWeights), _vp, _vp, _i32, _i32, _vp, _sz, _vp, _vp, _vp]),
+    "vqcpc_vocoder_condition_ragged": (C.c_int, [C.POINTER(VocoderWeights), _vp, _vp, _vp, _i32, _i32, _vp, _sz, _vp, _vp, _vp]),
     "vqcpc_vocoder_generate": (C.c_int, [C.POINTER(VocoderWeights), _vp, _vp, _i32, _i32, _i32, _vp, _sz, _vp, _vp, _vp, _vp]),
     "vqcpc_vocoder_logits_tf": (C.c_int, [C.POINTER(VocoderWeights), _vp, _vp, _i32, _i32, _i32, _vp, _sz, _vp, _vp]),
     "vqcpc_check_status": (C.c_int, [_vp, _vp]),

@@ -50,7 +50,7 @@ __global__ void embed_concat_kernel(const float* __restrict__ code_emb, const fl
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(PRE_G, 1)
 bigru_layer_kernel(const float* __restrict__ xproj, const float* __restrict__ w_hh, const float* __restrict__ b_hh,
-                   float* __restrict__ out, int T) {
+                   float* __restrict__ out, int T, const int32_t* __restrict__ code_lengths) {
     __shared__ __align__(16) float h[PRE_H];
     __shared__ float pre[PRE_G];
     __shared__ float an[PRE_H];
@@ -69,8 +69,13 @@ bigru_layer_kernel(const float* __restrict__ xproj, const float* __restrict__ w_
     __syncthreads();
     const float* xp = xproj + static_cast<int64_t>(b) * T * (2 * PRE_G) + dir * PRE_G + tid;
     float* o = out + static_cast<int64_t>(b) * T * (2 * PRE_H) + dir * PRE_H + tid;
-    for (int s = 0; s < T; ++s) {
-        const int t = dir ? (T - 1 - s) : s;
+    // ragged batches: utterance b is Tb = 2 * code_lengths[b] frames long; its backward direction starts at ITS last
+    // frame (a padded tail must not leak into the valid frames); the tail of the output is zero-filled
+    const int Tb = code_lengths ? min(T, 2 * __ldg(code_lengths + b)) : T;
+    if (tid < PRE_H)
+        for (int t = Tb; t < T; ++t) o[static_cast<int64_t>(t) * (2 * PRE_H)] = 0.f;
+    for (int s = 0; s < Tb; ++s) {
+        const int t = dir ? (Tb - 1 - s) : s;
         const float a = __ldg(xp + static_cast<int64_t>(t) * (2 * PRE_G));
         float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
 #pragma unroll
@@ -571,8 +576,8 @@ int vocoder_pack(const vqcpc_vocoder_weights* w, float* eprime_out, cudaStream_t
                       stream);
 }
 
-int vocoder_condition(const vqcpc_vocoder_weights* w, const int64_t* codes, const int64_t* speaker, int B, int Tc,
-                      void* ws, size_t ws_bytes, float* out_G, float* out_p, cudaStream_t stream) {
+int vocoder_condition(const vqcpc_vocoder_weights* w, const int64_t* codes, const int64_t* speaker, const int32_t* code_lengths,
+                      int B, int Tc, void* ws, size_t ws_bytes, float* out_G, float* out_p, cudaStream_t stream) {
     int rc = check_vocoder_dims(w);
     if (rc) return rc;
     VQ_ARG(codes && speaker && ws && out_G, "vocoder_condition: null pointer");
@@ -598,12 +603,12 @@ int vocoder_condition(const vqcpc_vocoder_weights* w, const int64_t* codes, cons
     }
     // layer 0
     if ((rc = gemm_dense(u, 128, w->pre_w_ih[0], 128, w->pre_b_ih[0], xproj, 768, rows, 768, 128, stream))) return rc;
-    bigru_layer_kernel<<<dim3(2, B), PRE_G, 0, stream>>>(xproj, w->pre_w_hh[0], w->pre_b_hh[0], p0, T2);
+    bigru_layer_kernel<<<dim3(2, B), PRE_G, 0, stream>>>(xproj, w->pre_w_hh[0], w->pre_b_hh[0], p0, T2, code_lengths);
     VQ_CUDA(cudaGetLastError());
     count_launch(1);
     // layer 1 (input = [fwd;bwd] of layer 0)
     if ((rc = gemm_dense(p0, 256, w->pre_w_ih[1], 256, w->pre_b_ih[1], xproj, 768, rows, 768, 256, stream))) return rc;
-    bigru_layer_kernel<<<dim3(2, B), PRE_G, 0, stream>>>(xproj, w->pre_w_hh[1], w->pre_b_hh[1], p1, T2);
+    bigru_layer_kernel<<<dim3(2, B), PRE_G, 0, stream>>>(xproj, w->pre_w_hh[1], w->pre_b_hh[1], p1, T2, code_lengths);
     VQ_CUDA(cudaGetLastError());
     count_launch(1);
     // hoisted conditioning half of the AR input projection: G = p . W_ih[:, 256:]^T + b_ih
@@ -736,7 +741,14 @@ extern "C" size_t vqcpc_vocoder_workspace_bytes(int32_t B, int32_t Tc) { return 
 extern "C" int vqcpc_vocoder_condition(const vqcpc_vocoder_weights* w, const int64_t* codes, const int64_t* speaker,
                                        int32_t B, int32_t Tc, void* workspace, size_t workspace_bytes, float* out_G,
                                        float* out_p, void* stream) {
-    return vqcpc::vocoder_condition(w, codes, speaker, B, Tc, workspace, workspace_bytes, out_G, out_p,
+    return vqcpc::vocoder_condition(w, codes, speaker, nullptr, B, Tc, workspace, workspace_bytes, out_G, out_p,
+                                    static_cast<cudaStream_t>(stream));
+}
+extern "C" int vqcpc_vocoder_condition_ragged(const vqcpc_vocoder_weights* w, const int64_t* codes, const int64_t* speaker,
+                                              const int32_t* code_lengths, int32_t B, int32_t Tc, void* workspace,
+                                              size_t workspace_bytes, float* out_G, float* out_p, void* stream) {
+    if (code_lengths == nullptr) { vqcpc::set_error("vocoder_condition_ragged: code_lengths is required"); return VQCPC_ERR_ARG; }
+    return vqcpc::vocoder_condition(w, codes, speaker, code_lengths, B, Tc, workspace, workspace_bytes, out_G, out_p,
                                     static_cast<cudaStream_t>(stream));
 }
 extern "C" int vqcpc_vocoder_generate(const vqcpc_vocoder_weights* w, const float* G, const float* uniforms, int32_t B,

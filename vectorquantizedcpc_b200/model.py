@@ -178,6 +178,30 @@ class Encoder(nn.Module):
         z, c, idx, _, _ = self._encode(mel, want_aux=bool(self.encoder[-1]._forward_hooks))
         return z, c, idx
 
+    def encode_ragged(self, mels):
+        """Ragged batch: ``mels`` = sequence of (80, T_b) tensors -> list of per-utterance
+        ``(z (T'_b, 64), c (T'_b, 256), indices (T'_b,))``, T'_b = (T_b - 2)//2 + 1, from ONE batched call.
+
+        Exact, not approximate: the strided convolution pads with zeros (model.py:43), LayerNorm / Linear / VQ act
+        per frame and the LSTM is causal (model.py:57), so the valid frames of a zero-padded utterance equal its
+        unpadded run."""
+        mels = list(mels)
+        if not mels:
+            return []
+        for m in mels:
+            if m.dim() != 2 or m.shape[0] != self.conf.in_channels or m.shape[1] < 2:
+                raise ValueError(f"every mel must be ({self.conf.in_channels}, T >= 2), got {tuple(m.shape)}")
+        T = max(m.shape[1] for m in mels)
+        batch = mels[0].new_zeros(len(mels), self.conf.in_channels, T)
+        for b, m in enumerate(mels):
+            batch[b, :, :m.shape[1]] = m
+        z, c, idx = self.encode(batch)
+        out = []
+        for b, m in enumerate(mels):
+            n = (m.shape[1] - 2) // 2 + 1
+            out.append((z[b, :n], c[b, :n], idx[b, :n]))
+        return out
+
     def encode_with_aux(self, mel: Tensor):
         """``encode`` plus the pre-VQ projection (B,T',64) -- what encode.py:34-40 captures with a forward hook."""
         z, c, idx, prevq, _ = self._encode(mel, want_aux=True)

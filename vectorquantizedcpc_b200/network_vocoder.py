@@ -218,10 +218,22 @@ class Vocoder(nn.Module):
             if bool(bad):
                 raise IndexError("code index or speaker id out of range (nn.Embedding would raise)")
 
-    def condition(self, z: Tensor, speaker: Tensor, return_prenet: bool = False):
+    def _check_lengths(self, lengths, z: Tensor) -> Tensor:
+        """``lengths`` (B,) = valid code frames per utterance of a padded batch -> int32 device tensor."""
+        lengths = torch.as_tensor(lengths)
+        if lengths.dim() != 1 or lengths.shape[0] != z.shape[0] or lengths.dtype.is_floating_point:
+            raise ValueError("lengths must be an integer vector with one entry per utterance")
+        if lengths.numel() and (int(lengths.min()) < 1 or int(lengths.max()) > z.shape[1]):
+            raise ValueError(f"lengths must lie in [1, {z.shape[1]}]")
+        return lengths.to(device=z.device, dtype=torch.int32).contiguous()
+
+    def condition(self, z: Tensor, speaker: Tensor, return_prenet: bool = False, lengths=None):
         """Embeddings + x2 nearest + concat (network_vocoder.py:73-77), prenet biGRU, hoisted input projection
-        G (B, 2Tc, 2688).  With ``return_prenet`` also the prenet output p (B, 2Tc, 256)."""
+        G (B, 2Tc, 2688).  With ``return_prenet`` also the prenet output p (B, 2Tc, 256).  ``lengths`` (B,): ragged
+        batch -- utterance b's bidirectional prenet runs over its own 2*lengths[b] frames, the padded tail is zero."""
         self._check_inputs(z, speaker)
+        if lengths is not None:
+            lengths = self._check_lengths(lengths, z)
         w, _keep = self.pack_weights()
         B, Tc = z.shape
         dev = z.device
@@ -232,22 +244,31 @@ class Vocoder(nn.Module):
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         zc, sc = z.contiguous(), speaker.contiguous()
         with torch.cuda.device(dev):
-            _lib.check(lib.vqcpc_vocoder_condition(C.byref(w), _lib.ptr(zc), _lib.ptr(sc), B, Tc, _lib.ptr(ws), ws_bytes,
-                                                   _lib.ptr(G), _lib.ptr(p), _lib.current_stream_ptr()),
-                       "Vocoder.condition")
+            if lengths is None:
+                st = lib.vqcpc_vocoder_condition(C.byref(w), _lib.ptr(zc), _lib.ptr(sc), B, Tc, _lib.ptr(ws), ws_bytes,
+                                                 _lib.ptr(G), _lib.ptr(p), _lib.current_stream_ptr())
+            else:
+                st = lib.vqcpc_vocoder_condition_ragged(C.byref(w), _lib.ptr(zc), _lib.ptr(sc), _lib.ptr(lengths), B, Tc,
+                                                        _lib.ptr(ws), ws_bytes, _lib.ptr(G), _lib.ptr(p),
+                                                        _lib.current_stream_ptr())
+            _lib.check(st, "Vocoder.condition")
         return (G, p) if return_prenet else G
 
     def generate(self, z: Tensor, speaker: Tensor, uniforms: Optional[Tensor] = None, return_mulaw: bool = False,
                  n_steps: Optional[int] = None, generator: Optional[torch.Generator] = None,
-                 return_logits: bool = False):
+                 return_logits: bool = False, lengths=None):
         """Generate utterances from a batch of (latent_code, speaker_index) -- network_vocoder.py:69-78.
 
         z (B, Tc) int64, speaker (B,) int64 -> wav (B, L) fp32 on the input device, L = 320*Tc (or ``n_steps``).
         ``uniforms`` (B, L) in [0,1) injects the sampler's randomness (one per utterance and step); when None
         they are drawn with ``torch.rand(generator=generator)`` on the device.  One persistent kernel launch per
-        utterance; no per-sample host work."""
+        group of utterances; no per-sample host work.
+
+        ``lengths`` (B,) int: ragged batch -- z is padded to the longest utterance and utterance b
+        has lengths[b] valid code frames.  Its first 320*lengths[b] samples are exactly what an unpadded call with
+        the same uniforms returns; the rest of its row is set to 0 (use ``wav[b, :320*lengths[b]]``)."""
         _check_no_grad()
-        G = self.condition(z, speaker)
+        G = self.condition(z, speaker, lengths=lengths)
         w, _keep = self.pack_weights()
         B, Tc = z.shape
         dev = z.device
@@ -274,6 +295,10 @@ class Vocoder(nn.Module):
             _lib.check(st, "Vocoder.generate")
             if B > 0 and L > 0:
                 _lib.check(lib.vqcpc_check_status(_lib.ptr(ws), _lib.current_stream_ptr()), "Vocoder.generate")
+        if lengths is not None and B > 0 and L > 0:
+            valid = (torch.arange(L, device=dev)[None, :] <
+                     (torch.as_tensor(lengths, device=dev).to(torch.int64) * (2 * self.conf.rnnms.upsampling_t))[:, None])
+            wav = wav * valid
         out = (wav,)
         if return_mulaw:
             out += (codes.to(torch.int64),)
@@ -281,16 +306,17 @@ class Vocoder(nn.Module):
             out += (logits,)
         return out[0] if len(out) == 1 else out
 
-    def forward(self, x: Tensor, z: Tensor, speaker: Tensor) -> Tensor:
+    def forward(self, x: Tensor, z: Tensor, speaker: Tensor, lengths=None) -> Tensor:
         """Teacher-forced energies (B, L, 256) -- network_vocoder.py:41-67; x (B, L) int64 mu-law series is the
-        AR input (vocoder.py:62: ``audio_series[:, :-1]``).  Inference-only (no autograd graph)."""
+        AR input (vocoder.py:62: ``audio_series[:, :-1]``).  Inference-only (no autograd graph).  ``lengths``: as in
+        ``generate`` (energies beyond 320*lengths[b] belong to the padding and carry no meaning)."""
         _check_no_grad()
         _lib.require_cuda(x, "x")
         if x.dim() != 2 or x.shape[0] != z.shape[0] or x.dtype != torch.int64:
             raise ValueError("x must be (B, L) int64")
         if x.numel() and bool(((x < 0) | (x > 255)).any()):
             raise IndexError("mu-law code out of range [0, 255]")
-        G = self.condition(z, speaker)
+        G = self.condition(z, speaker, lengths=lengths)
         w, _keep = self.pack_weights()
         B, Tc = z.shape
         L = x.shape[1]
