@@ -516,6 +516,12 @@ int gemm_tc_plan(TcPlan* plan, const void* a_planes, const void* w_planes, const
     static_assert(sizeof(CUtensorMap) == sizeof(plan->map_a), "TcPlan map storage");
     const int planes = nseg == 3 ? 2 : 1;
     plan->bn = (N % 256 == 0) ? 256 : (N % 128 == 0 ? 128 : 64);
+    {
+        // small problems (the LSTM's per-step product at a few hundred utterances): narrower column tiles until at
+        // least half of the 148 SMs have a tile
+        long long tiles = static_cast<long long>((M + TC_BM - 1) / TC_BM) * (N / plan->bn);
+        while (plan->bn > 64 && tiles * 2 <= 148) { plan->bn /= 2; tiles *= 2; }
+    }
     int rc = make_map(reinterpret_cast<CUtensorMap*>(plan->map_a), a_planes, M, static_cast<long long>(planes) * K,
                       static_cast<long long>(planes) * K, TC_BM);
     if (rc) return rc;
