@@ -168,16 +168,15 @@ __device__ __forceinline__ void ab_mma_ktile(const uint32_t (&w_hi)[3][2], const
 template <int K0, int K1, int N0, int N1>
 __device__ __forceinline__ void ab_mma_pass(const uint32_t (&w_hi)[7][3][2], const uint32_t (&w_lo)[7][3][2], const uint4* hq,
                                             float (&acc)[4][3][4]) {
-    uint32_t a0[4][8], a1[4][8];
-    ab_load_a(hq, K0, a0);
+    // three rotating fragment buffers: the loads of k-tiles k+1 and k+2 are in flight while k-tile k runs on the
+    // tensor cores (an L2 round trip under load is longer than the MMAs of one k-tile)
+    uint32_t a[3][4][8];
+    ab_load_a(hq, K0, a[0]);
+    if (K0 + 1 < K1) ab_load_a(hq, K0 + 1, a[1]);
 #pragma unroll
-    for (int k = K0; k < K1; k += 2) {
-        if (k + 1 < K1) ab_load_a(hq, k + 1, a1);
-        ab_mma_ktile<N0, N1>(w_hi[k], w_lo[k], a0, acc);
-        if (k + 1 < K1) {
-            if (k + 2 < K1) ab_load_a(hq, k + 2, a0);
-            ab_mma_ktile<N0, N1>(w_hi[k + 1], w_lo[k + 1], a1, acc);
-        }
+    for (int k = K0; k < K1; ++k) {
+        if (k + 2 < K1) ab_load_a(hq, k + 2, a[(k - K0 + 2) % 3]);
+        ab_mma_ktile<N0, N1>(w_hi[k], w_lo[k], a[(k - K0) % 3], acc);
     }
 }
 // C fragment of (utterance tile m, weight-row tile n): c0,c1 = (utt m*16 + lane/4, rows n*8 + 2*(lane%4) + {0,1}),
