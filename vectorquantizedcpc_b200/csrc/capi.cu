@@ -2,6 +2,10 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <mutex>
+#include <utility>
+#include <vector>
+
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -19,21 +23,36 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
-static int cached_attr(cudaDeviceAttr attr) {
+// attribute of the CURRENT device, cached per device (a process may drive several GPUs)
+static int cached_attr(cudaDeviceAttr attr, int (&cache)[64]) {
     int dev = 0, v = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (dev >= 0 && dev < 64 && cache[dev] != 0) return cache[dev];
     if (cudaDeviceGetAttribute(&v, attr, dev) != cudaSuccess) return 0;
+    if (dev >= 0 && dev < 64) cache[dev] = v;
     return v;
 }
 int device_sm_count() {
-    static thread_local int v = 0;
-    if (v == 0) v = cached_attr(cudaDevAttrMultiProcessorCount);
-    return v;
+    static int cache[64] = {0};
+    return cached_attr(cudaDevAttrMultiProcessorCount, cache);
+}
+// One-time opt-in to > 48 KB of dynamic shared memory, remembered per (kernel, device): a function attribute is a
+// per-device property, so a process that drives several GPUs must set it on each of them.
+int ensure_dyn_smem(const void* func, int bytes) {
+    static std::mutex mu;
+    static std::vector<std::pair<const void*, int>> done;
+    int dev = 0;
+    VQ_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(mu);
+    for (const auto& e : done)
+        if (e.first == func && e.second == dev) return VQCPC_OK;
+    VQ_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    done.emplace_back(func, dev);
+    return VQCPC_OK;
 }
 int device_cc_major() {
-    static thread_local int v = 0;
-    if (v == 0) v = cached_attr(cudaDevAttrComputeCapabilityMajor);
-    return v;
+    static int cache[64] = {0};
+    return cached_attr(cudaDevAttrComputeCapabilityMajor, cache);
 }
 
 }  // namespace vqcpc

@@ -292,11 +292,7 @@ int vq_lookup(const float* x, const float* codebook, int64_t n, int n_codes, int
     VQ_ARG(n_codes == VQ_M && dim == VQ_D, "vq_lookup: only a 512x64 codebook is supported (got %dx%d)", n_codes, dim);
     VQ_ARG(n >= 0, "vq_lookup: negative frame count");
     if (n == 0) return VQCPC_OK;
-    static bool attr_set = false;
-    if (!attr_set) {
-        VQ_CUDA(cudaFuncSetAttribute(vq_lookup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VQ_SMEM));
-        attr_set = true;
-    }
+    if (int rc_attr = ensure_dyn_smem(reinterpret_cast<const void*>(vq_lookup_kernel), static_cast<int>(VQ_SMEM))) return rc_attr;
     const int64_t n_tiles = (n + VQ_TF - 1) / VQ_TF;
     const int sms = device_sm_count();
     const unsigned grid = static_cast<unsigned>(n_tiles < sms ? n_tiles : sms);

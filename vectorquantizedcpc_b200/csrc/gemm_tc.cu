@@ -490,11 +490,7 @@ static int make_map(CUtensorMap* map, const void* base, long long rows, long lon
 template <int BN>
 static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mw, const TcParams& p, cudaStream_t stream) {
     constexpr size_t smem = TC_STAGES * (TC_BM * TC_BK * 2 + BN * TC_BK * 2) + 1024;
-    static bool attr_set = false;
-    if (!attr_set) {
-        VQ_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        attr_set = true;
-    }
+    if (int rc_attr = ensure_dyn_smem(reinterpret_cast<const void*>(gemm_tc_kernel<BN>), static_cast<int>(smem))) return rc_attr;
     const int tiles = ((p.M + TC_BM - 1) / TC_BM) * (p.N / BN);
     const int sms = device_sm_count();
     gemm_tc_kernel<BN><<<tiles < sms ? tiles : sms, TC_THREADS, smem, stream>>>(ma, mw, p);
@@ -559,11 +555,7 @@ bool gemm_tc_ln_supported(int N) { return N == 512 || N == 768; }
 template <int NT>
 static int launch_tc_ln(const CUtensorMap& ma, const CUtensorMap& mw, const TcLnParams& p, cudaStream_t stream) {
     constexpr size_t smem = TC_STAGES * (TC_BM * TC_BK * 2 + 256 * TC_BK * 2) + 1024;
-    static bool attr_set = false;
-    if (!attr_set) {
-        VQ_CUDA(cudaFuncSetAttribute(gemm_tc_ln_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        attr_set = true;
-    }
+    if (int rc_attr = ensure_dyn_smem(reinterpret_cast<const void*>(gemm_tc_ln_kernel<NT>), static_cast<int>(smem))) return rc_attr;
     const int blocks = (p.M + TC_BM - 1) / TC_BM;
     int sms = device_sm_count();
     if (sms > 148) sms = 148;

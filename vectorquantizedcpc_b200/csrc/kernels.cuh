@@ -41,6 +41,7 @@ int vq_lookup_auto(const float* x, const float* codebook, int64_t n, float* q, i
 
 // vocoder_batch.cu: batched sample loop (up to 64 utterances per launch, grid-barrier phases)
 size_t ar_batch_workspace_bytes();
+int ensure_dyn_smem(const void* func, int bytes);   // per-(kernel, device) opt-in to large dynamic shared memory
 
 // persistent-kernel workspace header (first bytes of every workspace handed to a persistent kernel)
 struct WorkspaceHeader {

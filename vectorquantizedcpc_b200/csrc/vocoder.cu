@@ -626,11 +626,7 @@ template <int NB>
 static int ar_launch(ArParams& p, cudaStream_t stream) {
     void* args[] = {&p};
     constexpr size_t dyn = sizeof(float) * NB * 2 * AR_HPAD;
-    static bool attr_set = false;
-    if (!attr_set) {
-        VQ_CUDA(cudaFuncSetAttribute(ar_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-        attr_set = true;
-    }
+    if (int rc_attr = ensure_dyn_smem(reinterpret_cast<const void*>(ar_kernel<NB>), static_cast<int>(dyn))) return rc_attr;
     VQ_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(ar_kernel<NB>), dim3(AR_CTAS), dim3(AR_THREADS), args, dyn,
                                         stream));
     count_launch(1);

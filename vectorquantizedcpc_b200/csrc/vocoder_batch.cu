@@ -806,12 +806,8 @@ int g_ab_two_group = 1;      // debug switch (vqcpc_debug_set_ar_poll_gap bit 29
 
 int ar_batch_run(const vqcpc_vocoder_weights* w, const float* G, const float* uniforms, const int64_t* x_in, int B, int T2,
                  int L, void* ws, int* status, float* out_wav, int32_t* out_codes, float* out_logits, cudaStream_t stream) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        VQ_CUDA(cudaFuncSetAttribute(ar_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(AB_SMEM)));
-        VQ_CUDA(cudaFuncSetAttribute(ar_batch2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(AB2_SMEM)));
-        attr_set = true;
-    }
+    if (int rc_attr = ensure_dyn_smem(reinterpret_cast<const void*>(ar_batch_kernel), static_cast<int>(AB_SMEM))) return rc_attr;
+    if (int rc_attr = ensure_dyn_smem(reinterpret_cast<const void*>(ar_batch2_kernel), static_cast<int>(AB2_SMEM))) return rc_attr;
     unsigned char* base = static_cast<unsigned char*>(ws);
     const size_t gbytes = align_up(ab_ws_bytes(), 256);
     auto carve = [&](unsigned char* gb, uint32_t*& hP, float*& rT, ll_word*& oLL, ll_word*& xLL, ll_word*& flags) {

@@ -440,11 +440,7 @@ int vq_lookup_tc(const float* x, const float* codebook, int64_t n, float* q, int
     CUresult r = fn(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, planes_ws, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("vq_lookup_tc: cuTensorMapEncodeTiled failed (%d)", static_cast<int>(r)); return VQCPC_ERR_CUDA; }
-    static bool attr_set = false;
-    if (!attr_set) {
-        VQ_CUDA(cudaFuncSetAttribute(vq_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(VT_SMEM)));
-        attr_set = true;
-    }
+    if (int rc_attr = ensure_dyn_smem(reinterpret_cast<const void*>(vq_tc_kernel), static_cast<int>(VT_SMEM))) return rc_attr;
     const long long n_tiles = (n + VT_TF - 1) / VT_TF;
     const int sms = device_sm_count();
     static int dbg = -1;
