@@ -498,6 +498,9 @@ __global__ void lstm_gate_kernel(const float* __restrict__ gates, const float* _
                                  const int64_t* __restrict__ idx, int t, int Tp, float* __restrict__ cstate,
                                  float* __restrict__ out, __nv_bfloat16* __restrict__ hplanes, int B) {
     const int64_t total = static_cast<int64_t>(B) * (LSTM_H / 4);
+    // programmatic dependent launch (no-ops otherwise): wait for the step's GEMM, then let the next GEMM start its prologue
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
         const int b = static_cast<int>(i / (LSTM_H / 4)), q = static_cast<int>(i % (LSTM_H / 4));
@@ -565,14 +568,28 @@ int lstm_forward(const vqcpc_encoder_weights* w, const int64_t* idx, int B, int 
         const unsigned grid = static_cast<unsigned>((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
         for (int t = 0; t < Tp; ++t) {
             if (t > 0) {
-                if (tc) rc = gemm_tc_run(&plan, stream);
+                if (tc) rc = gemm_tc_run(&plan, stream, true);
                 else rc = gemm_dense(out_c + static_cast<int64_t>(t - 1) * LSTM_H, static_cast<int64_t>(Tp) * LSTM_H, w->lstm_w_hh,
                                      LSTM_H, nullptr, gates, LSTM_G, B, LSTM_G, LSTM_H, stream);
                 if (rc) return rc;
             }
-            lstm_gate_kernel<<<grid, 256, 0, stream>>>(t > 0 ? gates : nullptr, table, idx, t, Tp, cstate, out_c,
-                                                       tc ? hplanes : nullptr, B);
-            VQ_CUDA(cudaGetLastError());
+            {
+                // both kernels of a step are launched as programmatic dependents: the prologue of each overlaps the tail
+                // of its predecessor (150 steps x 2 kernel boundaries per utterance batch)
+                cudaLaunchConfig_t cfg{};
+                cfg.gridDim = dim3(grid);
+                cfg.blockDim = dim3(256);
+                cfg.stream = stream;
+                cudaLaunchAttribute attr[1];
+                attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+                attr[0].val.programmaticStreamSerializationAllowed = 1;
+                cfg.attrs = attr;
+                cfg.numAttrs = (tc && t > 0) ? 1 : 0;
+                const float* gates_in = t > 0 ? gates : nullptr;
+                __nv_bfloat16* planes_out = tc ? hplanes : nullptr;
+                VQ_CUDA(cudaLaunchKernelEx(&cfg, lstm_gate_kernel, gates_in, static_cast<const float*>(table), idx, t, Tp, cstate,
+                                           out_c, planes_out, B));
+            }
             count_launch(1);
         }
         return VQCPC_OK;

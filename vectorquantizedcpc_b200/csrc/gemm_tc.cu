@@ -130,6 +130,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_slot;
+    // Programmatic dependent launch: everything above (barrier init, TMEM allocation) may overlap the tail of the
+    // previous kernel in the stream; from here on its results are read and its inputs overwritten.  (No-ops when the
+    // kernel was launched without the attribute.)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     const int tiles_m = (p.M + TC_BM - 1) / TC_BM, tiles_n = p.N / BN;
     const int n_tiles = tiles_m * tiles_n;
@@ -488,13 +493,22 @@ static int make_map(CUtensorMap* map, const void* base, long long rows, long lon
 }
 
 template <int BN>
-static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mw, const TcParams& p, cudaStream_t stream) {
+static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mw, const TcParams& p, cudaStream_t stream, bool pdl) {
     constexpr size_t smem = TC_STAGES * (TC_BM * TC_BK * 2 + BN * TC_BK * 2) + 1024;
     if (int rc_attr = ensure_dyn_smem(reinterpret_cast<const void*>(gemm_tc_kernel<BN>), static_cast<int>(smem))) return rc_attr;
     const int tiles = ((p.M + TC_BM - 1) / TC_BM) * (p.N / BN);
     const int sms = device_sm_count();
-    gemm_tc_kernel<BN><<<tiles < sms ? tiles : sms, TC_THREADS, smem, stream>>>(ma, mw, p);
-    VQ_CUDA(cudaGetLastError());
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(tiles < sms ? tiles : sms);
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    VQ_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN>, ma, mw, p));
     count_launch(1);
     return VQCPC_OK;
 }
@@ -528,13 +542,13 @@ int gemm_tc_plan(TcPlan* plan, const void* a_planes, const void* w_planes, const
     return VQCPC_OK;
 }
 
-int gemm_tc_run(const TcPlan* plan, cudaStream_t stream) {
+int gemm_tc_run(const TcPlan* plan, cudaStream_t stream, bool pdl) {
     const CUtensorMap& ma = *reinterpret_cast<const CUtensorMap*>(plan->map_a);
     const CUtensorMap& mw = *reinterpret_cast<const CUtensorMap*>(plan->map_w);
     TcParams p{plan->C, plan->bias, plan->err, plan->ldc, plan->M, plan->N, plan->K, plan->nseg};
-    if (plan->bn == 256) return launch_tc<256>(ma, mw, p, stream);
-    if (plan->bn == 128) return launch_tc<128>(ma, mw, p, stream);
-    return launch_tc<64>(ma, mw, p, stream);
+    if (plan->bn == 256) return launch_tc<256>(ma, mw, p, stream, pdl);
+    if (plan->bn == 128) return launch_tc<128>(ma, mw, p, stream, pdl);
+    return launch_tc<64>(ma, mw, p, stream, pdl);
 }
 
 int gemm_tc(const void* a_planes, const void* w_planes, const float* bias, float* C, long long ldc, int M, int N, int K,
@@ -543,7 +557,7 @@ int gemm_tc(const void* a_planes, const void* w_planes, const float* bias, float
     TcPlan plan;
     int rc = gemm_tc_plan(&plan, a_planes, w_planes, bias, C, ldc, M, N, K, nseg, err_flag);
     if (rc) return rc;
-    return gemm_tc_run(&plan, stream);
+    return gemm_tc_run(&plan, stream, false);
 }
 
 
