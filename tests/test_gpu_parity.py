@@ -255,6 +255,42 @@ def test_encoder_tensor_core_mode_matches_oracle(C_, B, T):
     assert torch.equal(idx32, io)
 
 
+def test_encoder_full_size_properties():
+    """BASELINE configs[3] at full size (4096 utterances x 3 s = 614 400 frames, C = 768, tensor-core mode): size-
+    independent properties plus an oracle check on a sample of utterances.
+      * every index is a valid code and z is exactly the gathered codebook row (gather consistency);
+      * |c| < 1 (an LSTM output), no NaN;
+      * batch independence: utterances re-encoded alone (fp32 parity path) give the same indices except near-ties of
+        the size the bf16x3 error allows, and c within tolerance where the indices agree;
+      * the sampled utterances match the CPU oracle the same way."""
+    enc, sd = make_encoder(768, True)
+    B, T = 4096, 300
+    mel = fixtures.synthetic_mel(B, T, seed=0)
+    md = mel.to(dev())
+    z, c, idx, prevq = enc.encode_with_aux(md)
+    Tp = (T - 2) // 2 + 1
+    assert z.shape == (B, Tp, 64) and c.shape == (B, Tp, 256) and idx.shape == (B, Tp) and idx.dtype == torch.int64
+    assert int(idx.min()) >= 0 and int(idx.max()) < 512
+    cb = enc.codebook.embedding
+    assert torch.equal(z, cb[idx])
+    assert bool(torch.isfinite(c).all()) and float(c.abs().max()) < 1.0
+    sel = [0, 1, 2047, 4095]
+    enc.gemm_mode = "fp32"
+    z1, c1, i1, p1 = enc.encode_with_aux(md[sel])
+    enc.gemm_mode = "auto"
+    zo, co, io, zp = oenc.encode(sd, mel[sel], return_aux=True)
+    assert torch.equal(i1.cpu(), io)                                   # fp32 path == oracle, bit-exact indices
+    scale = float(zp.abs().max())
+    err = float((prevq[sel].cpu() - zp).abs().max())
+    print(f"[encode 4096x3s] max|dz_pre| (bf16x3 vs oracle, 4 utterances) = {err:.2e}, scale {scale:.2f}")
+    assert err <= 1e-4 * scale + 1e-5
+    rep = oenc.classify_index_mismatches(zp, sd["codebook.embedding"], idx[sel].cpu(), io, slack=4 * err * 2.0)
+    assert rep["hard"] == 0, rep
+    ok = (idx[sel].cpu() == io).all(dim=1)
+    assert ok.any()
+    assert torch.allclose(c[sel].cpu()[ok], co[ok], rtol=RTOL, atol=ATOL_C)
+
+
 def test_encoder_matches_oracle_other_shapes_and_hook():
     enc, sd = make_encoder(512, True)
     aux = []
