@@ -473,6 +473,14 @@ def main():
                                                          "traffic": 470.2e6,   # ncu, profiles/r01_ncu_vq_tc_summary.txt
                                                          "note": "timed through VQEmbeddingEMA.encode (includes the status sync)"}}
             del xd
+        # wave -> log-mel front-end (preprocess.py:53-75), 64 utterances x 3 s
+        from vectorquantizedcpc_b200 import LogMel
+        fe = LogMel().to(dev)
+        wv = (torch.rand(64, 48000, generator=torch.Generator().manual_seed(3)) * 2 - 1).to(dev)
+        with torch.no_grad():
+            ms = timed(lambda: fe(wv), 5, 3) / 5
+        extra["logmel_64x3s"] = {"ms": ms, "audio_seconds_per_s": 64 * 3.0 / (ms * 1e-3), "frames_per_s": 64 * 301 / (ms * 1e-3)}
+        del wv
         # configs[0]: Encoder.encode on one 2 s utterance (latency), C = 768 and 512
         for Cc in (768, 512):
             sd = fixtures.encoder_init_state(Cc, seed=13)

@@ -179,6 +179,24 @@ int vqcpc_debug_set_ar_poll_gap(int32_t packed);
 /* Measures the bare 128-way LL exchange of the sample loop (no compute): mean SM cycles per exchange over `iters`
  * exchanges.  workspace >= 64 KiB.  Three exchanges per step are the latency floor bench.py reports. */
 int vqcpc_debug_exchange_floor(void* workspace, size_t workspace_bytes, int32_t iters, double* mean_cycles, void* stream);
+/* ---- log-mel front-end: the step before Encoder.encode.
+ * Replaces wave_to_mel, /root/reference/preprocess.py:53-75 (the same arithmetic is inline in convert.py:54-70):
+ * peak scaling to 0.999, pre-emphasis lfilter([1, -preemph], [1]), |STFT| (hann(win_length) centred in n_fft, hop_length,
+ * center=True with reflect padding), mel projection, 20 log10 with amin 1e-5, per-utterance top_db clamp, / top_db + 1.
+ * wave (B, N) fp32, nullable lengths (B,) int32 = samples per utterance of a padded batch (each > n_fft / 2);
+ * window (win_length,), dft (2 * n_freq_padded, win_length) = [cos rows | sin rows] of 2 pi k j / n_fft (padding rows
+ * zero), melw (n_mels, n_freq_padded) = the mel filterbank (padding columns zero) -- all fp32 device arrays built once
+ * by the host (vectorquantizedcpc_b200/frontend.py).  out (B, n_mels, T) fp32, T = 1 + N / hop_length: the layout
+ * Encoder.encode takes; frames beyond 1 + lengths[b] / hop_length are 0. */
+typedef struct {
+    int32_t n_fft, win_length, hop_length, n_mels;
+    int32_t n_freq_padded;   /* n_fft / 2 + 1 rounded up to a multiple of 16 */
+    float preemph, top_db;
+} vqcpc_logmel_config;
+size_t vqcpc_logmel_workspace_bytes(const vqcpc_logmel_config* cfg, int32_t B, int32_t N);
+int vqcpc_logmel_forward(const vqcpc_logmel_config* cfg, const float* wave, const int32_t* lengths, int32_t B, int32_t N,
+                         const float* window, const float* dft, const float* melw, void* workspace, size_t workspace_bytes,
+                         float* out, void* stream);
 /* Reads (and clears) the device-side status word of the persistent kernels in `workspace` after the stream
  * has been synchronised by the caller: 0 ok, VQCPC_ERR_TIMEOUT if an exchange timed out. */
 int vqcpc_check_status(void* workspace, void* stream);

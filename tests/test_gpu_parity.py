@@ -530,6 +530,50 @@ def test_encoder_ragged_batch_equals_unpadded_runs():
         enc.encode_ragged([torch.rand(79, 10, device=dev())])
 
 
+def _fe_signal(n, seed):
+    g = np.random.default_rng(seed)
+    t = np.arange(n) / 16000.0
+    x = 0.3 * np.sin(2 * np.pi * 180 * t) + 0.2 * np.sin(2 * np.pi * 2900 * t * (1 + 0.3 * t)) + 0.03 * g.standard_normal(n)
+    x[: n // 7] *= 1e-3                                   # a quiet stretch: exercises the top_db clamp
+    return x.astype(np.float32)
+
+
+def test_logmel_frontend_matches_oracle():
+    """wave -> log-mel (preprocess.py:53-75) on the GPU against the float64 oracle; tolerance 2e-4 in the
+    normalised units (1.0 = top_db = 80 dB), i.e. 0.016 dB.  Includes a ragged batch: every utterance is scaled, framed,
+    reflected and clamped on its own."""
+    from oracle import frontend as ofe
+    from vectorquantizedcpc_b200.frontend import LogMel, wave_to_mel
+    fe = LogMel().to(dev())
+    lens = [48000, 16000, 5000, 1025]
+    waves = [_fe_signal(n, 10 + i) for i, n in enumerate(lens)]
+    for w in waves[:2]:
+        ref = ofe.wave_to_mel(w)
+        got = fe(torch.from_numpy(w).to(dev()))[0].cpu().double().numpy()
+        assert got.shape == ref.shape == (80, 1 + len(w) // 160)
+        err = np.abs(got - ref).max()
+        print(f"[logmel N={len(w)}] max abs err {err:.2e} (range {ref.min():.3f}..{ref.max():.3f})")
+        assert err < 2e-4
+    batch = torch.zeros(len(lens), max(lens))
+    for b, w in enumerate(waves):
+        batch[b, :len(w)] = torch.from_numpy(w)
+    out = fe(batch.to(dev()), lengths=lens).cpu().double().numpy()
+    assert out.shape == (4, 80, 301)
+    for b, w in enumerate(waves):
+        Tb = 1 + len(w) // 160
+        assert np.abs(out[b, :, :Tb] - ofe.wave_to_mel(w)).max() < 2e-4, b
+        assert not out[b, :, Tb:].any()
+    assert torch.equal(wave_to_mel(torch.from_numpy(waves[1]).to(dev())), fe(torch.from_numpy(waves[1]).to(dev()))[0])
+    # the output feeds Encoder.encode directly
+    enc, _ = make_encoder(512, True)
+    z, c, idx = enc.encode(fe(torch.from_numpy(waves[1]).to(dev())))
+    assert idx.shape == (1, (101 - 2) // 2 + 1)
+    with pytest.raises(ValueError):
+        fe(torch.zeros(1, 1024, device=dev()))
+    with pytest.raises(ValueError):
+        fe(batch.to(dev()), lengths=[48000, 16000, 5000, 1000])
+
+
 def test_vocoder_argument_errors():
     voc, _ = make_vocoder()
     z = torch.zeros(1, 2, dtype=torch.int64, device=dev())

@@ -44,6 +44,12 @@ class VocoderWeights(C.Structure):
 
 
 # name -> (restype, argtypes); must list EVERY symbol include/vqcpc.h declares (tests/test_abi_cpu.py checks)
+class LogMelConfig(C.Structure):
+    """``vqcpc_logmel_config`` (include/vqcpc.h)."""
+    _fields_ = [("n_fft", C.c_int32), ("win_length", C.c_int32), ("hop_length", C.c_int32), ("n_mels", C.c_int32),
+                ("n_freq_padded", C.c_int32), ("preemph", C.c_float), ("top_db", C.c_float)]
+
+
 _vp, _i32, _i64, _sz = C.c_void_p, C.c_int32, C.c_int64, C.c_size_t
 SIGNATURES = {
     "vqcpc_last_error": (C.c_char_p, []),
@@ -65,6 +71,8 @@ SIGNATURES = {
     "vqcpc_vocoder_pack": (C.c_int, [C.POINTER(VocoderWeights), _vp, _vp]),
     "vqcpc_vocoder_workspace_bytes": (_sz, [_i32, _i32]),
     "vqcpc_vocoder_condition": (C.c_int, [C.POINTER(VocoderWeights), _vp, _vp, _i32, _i32, _vp, _sz, _vp, _vp, _vp]),
+    "vqcpc_logmel_workspace_bytes": (_sz, [C.POINTER(LogMelConfig), _i32, _i32]),
+    "vqcpc_logmel_forward": (C.c_int, [C.POINTER(LogMelConfig), _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _sz, _vp, _vp]),
     "vqcpc_vocoder_condition_ragged": (C.c_int, [C.POINTER(VocoderWeights), _vp, _vp, _vp, _i32, _i32, _vp, _sz, _vp, _vp, _vp]),
     "vqcpc_vocoder_generate": (C.c_int, [C.POINTER(VocoderWeights), _vp, _vp, _i32, _i32, _i32, _vp, _sz, _vp, _vp, _vp, _vp]),
     "vqcpc_vocoder_logits_tf": (C.c_int, [C.POINTER(VocoderWeights), _vp, _vp, _i32, _i32, _i32, _vp, _sz, _vp, _vp]),
