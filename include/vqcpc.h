@@ -197,6 +197,16 @@ size_t vqcpc_logmel_workspace_bytes(const vqcpc_logmel_config* cfg, int32_t B, i
 int vqcpc_logmel_forward(const vqcpc_logmel_config* cfg, const float* wave, const int32_t* lengths, int32_t B, int32_t N,
                          const float* window, const float* dft, const float* melw, void* workspace, size_t workspace_bytes,
                          float* out, void* stream);
+/* ---- output stage of convert.py: pyloudnorm's integrated loudness and gain.
+ * Replaces pyloudnorm.Meter(sr).integrated_loudness (convert.py:50,57,79) and pyloudnorm.normalize.loudness
+ * (convert.py:80): K-weighting biquads for `rate`, 400 ms blocks / 75 % overlap, -70 LUFS absolute and -10 LU relative
+ * gates.  wave (B, N) fp32 mono, nullable lengths (B,) int32; out_lufs (B,) fp32 (-inf for silence, as pyloudnorm).
+ * vqcpc_loudness_normalize writes out_wave = wave * 10^((target_lufs[b] - measured[b]) / 20) (0 beyond lengths[b]). */
+size_t vqcpc_loudness_workspace_bytes(int32_t B, int32_t N, int32_t rate);
+int vqcpc_integrated_loudness(const float* wave, const int32_t* lengths, int32_t B, int32_t N, int32_t rate, void* workspace,
+                              size_t workspace_bytes, float* out_lufs, void* stream);
+int vqcpc_loudness_normalize(const float* wave, const int32_t* lengths, const float* target_lufs, int32_t B, int32_t N, int32_t rate,
+                             void* workspace, size_t workspace_bytes, float* out_wave, float* out_measured_lufs, void* stream);
 /* Reads (and clears) the device-side status word of the persistent kernels in `workspace` after the stream
  * has been synchronised by the caller: 0 ok, VQCPC_ERR_TIMEOUT if an exchange timed out. */
 int vqcpc_check_status(void* workspace, void* stream);

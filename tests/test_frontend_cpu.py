@@ -74,3 +74,19 @@ def test_product_constant_matrices():
     spec = np.abs(np.fft.rfft(frame))
     re, im = lm.dft[:1025].double().numpy() @ a, lm.dft[1040:1040 + 1025].double().numpy() @ a
     assert np.allclose(np.hypot(re, im), spec, rtol=1e-4, atol=1e-4)
+
+
+def test_loudness_oracle_matches_torchaudio_bs1770():
+    """oracle/loudness.py restates pyloudnorm (absent here); torchaudio.functional.loudness is an independent BS.1770-4
+    implementation -- agreement within 0.05 LU on signals long enough that one trailing block does not matter."""
+    from oracle import loudness as olo
+    for seed, scale in ((5, 1.0), (6, 0.1), (7, 0.01)):
+        x = _signal(48000, seed) * scale
+        ref = float(torchaudio.functional.loudness(torch.from_numpy(x)[None], 16000))
+        got = olo.integrated_loudness(x, 16000)
+        assert abs(got - ref) < 0.05, (got, ref)
+    a = olo.integrated_loudness(_signal(48000, 5), 16000)
+    assert abs(olo.integrated_loudness(_signal(48000, 5) * 0.5, 16000) - (a + 20 * np.log10(0.5))) < 1e-9     # linearity
+    y = olo.normalize_loudness(_signal(48000, 5), a, -23.0)
+    assert abs(olo.integrated_loudness(y, 16000) + 23.0) < 1e-9
+    assert olo.integrated_loudness(np.zeros(16000), 16000) == -np.inf

@@ -574,6 +574,58 @@ def test_logmel_frontend_matches_oracle():
         fe(batch.to(dev()), lengths=[48000, 16000, 5000, 1000])
 
 
+def test_loudness_output_stage_matches_oracle():
+    """convert.py:57,79-80 (pyloudnorm integrated loudness + gain) on the GPU against the oracle."""
+    from oracle import loudness as olo
+    from vectorquantizedcpc_b200.loudness import integrated_loudness, loudness_normalize
+    lens = [48000, 30000, 16000, 6401]
+    waves = [_fe_signal(n, 40 + i) * s for i, (n, s) in enumerate(zip(lens, (1.0, 0.2, 0.01, 0.5)))]
+    batch = torch.zeros(len(lens), max(lens))
+    for b, w in enumerate(waves):
+        batch[b, :len(w)] = torch.from_numpy(w)
+    bd = batch.to(dev())
+    lufs = integrated_loudness(bd, 16000, lengths=lens).cpu()
+    ref = torch.tensor([olo.integrated_loudness(w, 16000) for w in waves])
+    print("[loudness] GPU", [round(float(v), 4) for v in lufs], "oracle", [round(float(v), 4) for v in ref])
+    assert float((lufs - ref).abs().max()) < 2e-3                                   # LU
+    one = integrated_loudness(torch.from_numpy(waves[1]).to(dev()))                  # unpadded single utterance
+    assert abs(float(one[0]) - float(ref[1])) < 2e-3
+    target = torch.tensor([-23.0, -20.0, -30.0, -18.0])
+    out, measured = loudness_normalize(bd, target, 16000, lengths=lens)
+    assert torch.allclose(measured.cpu(), lufs, atol=1e-6)
+    for b, w in enumerate(waves):
+        exp = olo.normalize_loudness(w, float(ref[b]), float(target[b]))
+        got = out[b, :len(w)].cpu().double().numpy()
+        assert np.abs(got - exp).max() <= 5e-4 * np.abs(exp).max()
+        assert not out[b, len(w):].any()
+    assert float(integrated_loudness(torch.zeros(1, 16000, device=dev()))[0]) == float("-inf")   # silence, as pyloudnorm
+    with pytest.raises(ValueError):
+        integrated_loudness(torch.zeros(1, 6400, device=dev()))
+
+
+def test_convert_batch_equals_per_utterance_pipeline():
+    """convert.py:52-83 for a ragged batch on the GPU: every utterance must come out exactly as when it is converted
+    alone (front-end, encoder, ragged prenet, sample loop and loudness stage all act per utterance)."""
+    from vectorquantizedcpc_b200 import convert_batch
+    enc, _ = make_encoder(512, True)
+    voc, _ = make_vocoder()
+    lens = [9000, 7000, 8200]
+    waves = [torch.from_numpy(_fe_signal(n, 60 + i)).to(dev()) for i, n in enumerate(lens)]
+    spk = torch.tensor([3, 50, 101])
+    code_lens = [((1 + n // 160) - 2) // 2 + 1 for n in lens]
+    u = torch.rand(3, 320 * max(code_lens), generator=torch.Generator().manual_seed(9)).to(dev())
+    outs = convert_batch(enc, voc, waves, spk, uniforms=u)
+    for b, w in enumerate(waves):
+        assert outs[b].shape == (320 * code_lens[b],)
+        alone = convert_batch(enc, voc, [w], spk[b:b + 1], uniforms=u[b:b + 1, :320 * code_lens[b]])[0]
+        assert torch.equal(outs[b], alone), b
+    raw = convert_batch(enc, voc, waves, spk, uniforms=u, match_loudness=False)
+    from vectorquantizedcpc_b200 import integrated_loudness
+    src = integrated_loudness(waves[0])
+    assert abs(float(integrated_loudness(outs[0])[0]) - float(src[0])) < 1e-2       # output loudness = source loudness
+    assert not torch.equal(raw[0], outs[0])
+
+
 def test_vocoder_argument_errors():
     voc, _ = make_vocoder()
     z = torch.zeros(1, 2, dtype=torch.int64, device=dev())

@@ -5,6 +5,8 @@ from .model import ConfEncoder, Encoder, VQEmbeddingEMA  # noqa: F401
 from .network_vocoder import ConfRNNMSVocoder, ConfVocoder, RNNMSVocoder, Vocoder  # noqa: F401
 from . import checkpoint  # noqa: F401  (upstream-format checkpoint ingestion)
 from .frontend import ConfPreprocessing, LogMel, wave_to_mel  # noqa: F401  (log-mel front-end, preprocess.py:53-75)
+from .loudness import integrated_loudness, loudness_normalize  # noqa: F401  (convert.py:57,79-80)
+from .pipeline import convert_batch  # noqa: F401  (convert.py:52-83 for a ragged batch)
 
 __all__ = ["ConfEncoder", "Encoder", "VQEmbeddingEMA", "ConfVocoder", "ConfRNNMSVocoder", "RNNMSVocoder", "Vocoder",
-           "ConfPreprocessing", "LogMel", "wave_to_mel", "checkpoint"]
+           "ConfPreprocessing", "LogMel", "wave_to_mel", "integrated_loudness", "loudness_normalize", "convert_batch", "checkpoint"]

@@ -71,6 +71,9 @@ SIGNATURES = {
     "vqcpc_vocoder_pack": (C.c_int, [C.POINTER(VocoderWeights), _vp, _vp]),
     "vqcpc_vocoder_workspace_bytes": (_sz, [_i32, _i32]),
     "vqcpc_vocoder_condition": (C.c_int, [C.POINTER(VocoderWeights), _vp, _vp, _i32, _i32, _vp, _sz, _vp, _vp, _vp]),
+    "vqcpc_loudness_workspace_bytes": (_sz, [_i32, _i32, _i32]),
+    "vqcpc_integrated_loudness": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp, _sz, _vp, _vp]),
+    "vqcpc_loudness_normalize": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _sz, _vp, _vp, _vp]),
     "vqcpc_logmel_workspace_bytes": (_sz, [C.POINTER(LogMelConfig), _i32, _i32]),
     "vqcpc_logmel_forward": (C.c_int, [C.POINTER(LogMelConfig), _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _sz, _vp, _vp]),
     "vqcpc_vocoder_condition_ragged": (C.c_int, [C.POINTER(VocoderWeights), _vp, _vp, _vp, _i32, _i32, _vp, _sz, _vp, _vp, _vp]),
