@@ -28,4 +28,12 @@ Pinning status
   published RNN_MS / WaveRNN algorithm with the dimensions the reference pins
   in ``config.py:62-77,199`` and the glue it pins in
   ``network_vocoder.py:41-78``.
+* ``oracle.frontend`` (``wave_to_mel``, ``preprocess.py:53-75``) and
+  ``oracle.loudness`` (``convert.py:57,79-80``) -- the "next" rows of
+  SURVEY.md 8f: **PARITY UNPINNED against the third-party packages the
+  reference delegates to** (``librosa ^0.8.0``, ``pyloudnorm``; both absent
+  from this image).  Their published algorithms are restated and pinned to
+  independent implementations that ARE here: torchaudio's librosa-compatible
+  ``MelSpectrogram`` / Slaney filterbank, scipy's STFT and ``lfilter``, and
+  ``torchaudio.functional.loudness`` (``tests/test_frontend_cpu.py``).
 """
