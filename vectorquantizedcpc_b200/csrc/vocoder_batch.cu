@@ -69,7 +69,7 @@ constexpr int AB_HH = AB_NROW * AB_B;
 constexpr int AB_HOWN = AB_U * AB_B;
 constexpr int AB_GC = AB_NROW * AB_B;
 constexpr size_t AB_SMEM = sizeof(float) * (AB_W2S + AB_ES + AB_PART + AB_PART2 + AB_HH + AB_HOWN + AB_GC) + sizeof(int) * AB_B;
-constexpr int AB_PLANE = (AB_H / 2) * AB_B;         // uint32 words of one bf16x2 plane: [448 column pairs][64]
+constexpr int AB_PLANE = (AB_H / 2) * AB_B;         // 2 * AB_PLANE uint32 words = one parity buffer of h (hi and lo halves of every element)
 
 __device__ __forceinline__ float ld_strong(const float* p) {
     float v;
@@ -110,16 +110,6 @@ __device__ __forceinline__ bool ab_wait(ll_word* flags, uint32_t tag, volatile i
     return *abort_flag == 0;
 }
 
-__device__ __forceinline__ uint32_t ld_strong_u32(const uint32_t* p) {
-    uint32_t v;
-    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
 __device__ __forceinline__ void split_pair(float x, float y, uint32_t& hi, uint32_t& lo) {
     const __nv_bfloat162 h = __floats2bfloat162_rn(x, y);
     hi = *reinterpret_cast<const uint32_t*>(&h);
@@ -293,7 +283,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1) ar_batch_kernel(AbParams p) {
 #define AB_TRACE_S(k) if (tracing_s && t >= p.trace_t0 && t < p.trace_t0 + p.trace_n) p.trace[(t - p.trace_t0) * 8 + (k)] = clock64();
     for (int t = 0; t < L; ++t) {
         AB_TRACE(0)
-        uint32_t* hp = p.hP + static_cast<int64_t>(t & 1) * 2 * AB_PLANE;          // planes of h_t, double buffered by parity
+        uint32_t* hp = p.hP + static_cast<int64_t>(t & 1) * 2 * AB_PLANE;          // h_t fragments, double buffered by parity
         const uint4* hq = reinterpret_cast<const uint4*>(hp) + ((cc * 7 * 4) * 32 + lane) * 2;   // this warp's first (k-tile, utterance tile)
         // ------------------------------------------------------------------ G: conditioning reload, gates, h_t planes
         if (frame_left == 0) {

@@ -19,6 +19,11 @@
 #include <cuda_bf16.h>
 #include <stdlib.h>
 
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -109,6 +114,8 @@ struct VqTcParams {
     int* err;
     long long n;
     int debug;               // bit 0: skip the argmin math, bit 1: skip the gather/output, bit 2: converters skip the x loads
+    long long* trace;        // optional (VQCPC_VQ_TRACE): clock64 stamps of CTA 0, [tile iteration][16]
+    int trace_iters;
 };
 
 __global__ void __launch_bounds__(VT_THREADS, 1) vq_tc_kernel(const __grid_constant__ CUtensorMap map_cb, VqTcParams p) {
@@ -166,6 +173,8 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vq_tc_kernel(const __grid_const
     __syncthreads();
     const uint32_t tmem_base = tmem_base_slot;
     const long long n_tiles = (p.n + VT_TF - 1) / VT_TF;
+    // phase stamps of CTA 0: slots 0-3 MMA issuer, 4-6 converter warp 1, 7-13 epilogue warp (quarter 0, ch 0)
+#define VT_TRACE(slot) if (p.trace != nullptr && blockIdx.x == 0 && lane == 0 && it < p.trace_iters) p.trace[it * 16 + (slot)] = clock64();
 
     if (warp == VT_MMA_WARP) {
         // ------------------------------------------------------------------ MMA issuer
@@ -175,8 +184,10 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vq_tc_kernel(const __grid_const
             int it = 0;
             for (long long tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x, ++it) {
                 const int buf = it & 1;
+                VT_TRACE(0)
                 ok = mbar_wait(&xfull_bar[buf], xphase[buf], p.err);       // planes of this tile are in shared memory
                 if (!ok) break;
+                VT_TRACE(1)
                 xphase[buf] ^= 1;
                 tc_fence_after();
                 const uint32_t xa = smem_u32(x_s + buf * VT_XBUF);
@@ -201,6 +212,7 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vq_tc_kernel(const __grid_const
                     }
                     tc_commit(&tfull_bar[half]);
                     tphase[half] ^= 1;
+                    if (half == 0) { VT_TRACE(2) } else { VT_TRACE(3) }
                 }
                 tc_commit(&xempty_bar[buf]);                               // planes buffer reusable
             }
@@ -229,10 +241,12 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vq_tc_kernel(const __grid_const
         if (blockIdx.x < n_tiles) load_tile(blockIdx.x, cur);
         for (long long tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x, ++it) {
             const int buf = it & 1;
+            if (warp == VT_CONV_WARP0) { VT_TRACE(4) }
             ok = mbar_wait(&xempty_bar[buf], ephase[buf] ^ 1, p.err);      // MMAs of the tile two iterations ago are done
             ok = __all_sync(0xffffffffu, ok);
             if (!ok) break;
             ephase[buf] ^= 1;
+            if (warp == VT_CONV_WARP0) { VT_TRACE(5) }
             unsigned char* hi = x_s + buf * VT_XBUF;
             unsigned char* lo = hi + VT_PLANE;
             float ssq[8];
@@ -272,6 +286,7 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vq_tc_kernel(const __grid_const
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic-proxy stores -> visible to tcgen05.mma
             __syncwarp();
             if (lane == 0) mbar_arrive(&xfull_bar[buf]);
+            if (warp == VT_CONV_WARP0) { VT_TRACE(6) }
             if (tile + gridDim.x < n_tiles) load_tile(tile + gridDim.x, cur);   // prefetch the next tile's rows
         }
     } else {
@@ -286,18 +301,28 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vq_tc_kernel(const __grid_const
         bool ok = true;
         int it = 0;
         const float emax = emax_s;
+        uint32_t keymask;
+        asm("mov.u32 %0, 0xfffffe00;" : "=r"(keymask));     // opaque to constant propagation on purpose (see the LOP3 below)
         for (long long tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x, ++it) {
             const int buf = it & 1;
-            float b1a = INFINITY, b2a = INFINITY, b1b = INFINITY, b2b = INFINITY, xn = 0.f;
+            float b1 = INFINITY, b2 = INFINITY, xn = 0.f;
+            if (e == 0) { VT_TRACE(7) }
             for (int half = 0; half < 2 && ok; ++half) {
                 ok = mbar_wait(&tfull_bar[half], tphase[half], p.err);
                 ok = __all_sync(0xffffffffu, ok);
                 if (!ok) break;
                 tphase[half] ^= 1;
                 tc_fence_after();
+                if (e == 0) { if (half == 0) { VT_TRACE(8) } else { VT_TRACE(10) } }
                 if (half == 0) xn = xnorm[buf][row];      // read now: the converters may refill this slot two tiles later
                 // software-pipelined TMEM reads: the load of chunk c+1 is in flight while chunk c is reduced
-                const uint32_t tbase = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + half * 256 + ch * 128;
+                const int col0 = half * 256 + ch * 128;
+                const uint32_t tbase = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + col0;
+                const float* e2p = &e2s[col0];
+                // the index packed into the score is LOCAL to these 128 columns -- an immediate of the LOP3; a global index
+                // costs one integer add per element on the same (half-rate) pipe as the min/max.  It is widened when the
+                // half is folded into (b1, b2).
+                float b1a = INFINITY, b2a = INFINITY, b1b = INFINITY, b2b = INFINITY;
                 uint32_t va[32], vb[32];
                 tc_ld32(tbase, va);
 #pragma unroll
@@ -307,16 +332,19 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vq_tc_kernel(const __grid_const
                     uint32_t (&vn)[32] = (cc & 1) ? va : vb;
                     tc_wait_ld();
                     if (cc + 1 < 4) tc_ld32(tbase + 32 * (cc + 1), vn);
-                    const int col = half * 256 + ch * 128 + 32 * cc;
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
-                        const float4 e4 = *reinterpret_cast<const float4*>(&e2s[col + j]);    // broadcast LDS.128
+                        const float4 e4 = *reinterpret_cast<const float4*>(e2p + 32 * cc + j);    // broadcast LDS.128
                         const float ev[4] = {e4.x, e4.y, e4.z, e4.w};
                         float k[4];
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
                             const float sc = ev[q] + __uint_as_float(v[j + q]);               // |e|^2 + (-2 x.e)
-                            k[q] = __uint_as_float((__float_as_uint(sc) & 0xfffffe00u) | static_cast<uint32_t>(col + j + q));
+                            // one LOP3: (bits & mask) | local index -- the mask sits in a register so that the index can be
+                            // the instruction's single immediate operand
+                            uint32_t kb;
+                            asm("lop3.b32 %0, %1, %2, %3, 0xea;" : "=r"(kb) : "r"(__float_as_uint(sc)), "r"(keymask), "r"(32 * cc + j + q));
+                            k[q] = __uint_as_float(kb);
                         }
                         // merge the pair (lo <= hi) into the running (b1 <= b2): 5 ops per 2 elements
                         const float lo0 = fminf(k[0], k[1]), hi0 = fmaxf(k[0], k[1]);
@@ -328,14 +356,20 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vq_tc_kernel(const __grid_const
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty_bar[half]);
+                // fold this half's two chains into the tile's best two, with code indices (local index < 128, col0 a multiple of 128)
+                const float h1 = __uint_as_float(__float_as_uint(fminf(b1a, b1b)) + static_cast<uint32_t>(col0));
+                const float h2 = __uint_as_float(__float_as_uint(fminf(fmaxf(b1a, b1b), fminf(b2a, b2b))) + static_cast<uint32_t>(col0));
+                b2 = fminf(fmaxf(b1, h1), fminf(b2, h2));
+                b1 = fminf(b1, h1);
+                if (e == 0) { if (half == 0) { VT_TRACE(9) } else { VT_TRACE(11) } }
             }
             if (!ok) break;
-            // merge the two chains, then the two column halves: both warps of a row publish their pair, both read the
-            // other's, so both know the row's best two candidates and each takes half of the output work.
-            float b1 = fminf(b1a, b1b), b2 = fminf(fmaxf(b1a, b1b), fminf(b2a, b2b));
+            // merge the two column halves: both warps of a row publish their pair, both read the other's, so both know
+            // the row's best two candidates and each takes half of the output work.
             part[buf][ch][row] = make_float2(b1, b2);
             bar_sync(1 + quarter, 64);            // only the two warps of this row quarter meet: a warp delayed by an exact
                                                   // re-decision does not hold up the other six
+            if (e == 0) { VT_TRACE(12) }
             {
                 const float2 o = part[buf][ch ^ 1][row];
                 const float n1 = fminf(b1, o.x), n2 = fminf(fmaxf(b1, o.x), fminf(b2, o.y));
@@ -387,8 +421,10 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vq_tc_kernel(const __grid_const
                     }
                 }
             }
+            if (e == 0) { VT_TRACE(13) }
         }
     }
+#undef VT_TRACE
     tc_fence_before();
     __syncthreads();
     if (warp == VT_MMA_WARP) {
@@ -445,10 +481,44 @@ int vq_lookup_tc(const float* x, const float* codebook, int64_t n, float* q, int
     const int sms = device_sm_count();
     static int dbg = -1;
     if (dbg < 0) { const char* e = getenv("VQCPC_VQ_DEBUG"); dbg = e ? atoi(e) : 0; }
-    VqTcParams p{x, codebook, q, idx, err, static_cast<long long>(n), dbg};
+    // VQCPC_VQ_TRACE=<iterations>: phase stamps of CTA 0 (MMA issuer, one converter warp, one epilogue warp), printed to
+    // stderr as median cycles per tile -- the diagnostic behind the pipeline numbers in DESIGN.md 4.3
+    static int trace_iters = -1;
+    if (trace_iters < 0) { const char* e = getenv("VQCPC_VQ_TRACE"); trace_iters = e ? atoi(e) : 0; }
+    long long* d_trace = nullptr;
+    if (trace_iters > 0) {
+        VQ_CUDA(cudaMalloc(&d_trace, sizeof(long long) * 16 * trace_iters));
+        VQ_CUDA(cudaMemsetAsync(d_trace, 0, sizeof(long long) * 16 * trace_iters, stream));
+    }
+    VqTcParams p{x, codebook, q, idx, err, static_cast<long long>(n), dbg, d_trace, trace_iters};
     vq_tc_kernel<<<static_cast<unsigned>(n_tiles < sms ? n_tiles : sms), VT_THREADS, VT_SMEM, stream>>>(map, p);
     VQ_CUDA(cudaGetLastError());
     count_launch(1);
+    if (d_trace != nullptr) {
+        std::vector<long long> h(16 * static_cast<size_t>(trace_iters));
+        VQ_CUDA(cudaMemcpyAsync(h.data(), d_trace, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost, stream));
+        VQ_CUDA(cudaStreamSynchronize(stream));
+        VQ_CUDA(cudaFree(d_trace));
+        const long long per_cta = (n_tiles + (n_tiles < sms ? n_tiles : sms) - 1) / (n_tiles < sms ? n_tiles : sms);
+        const int iters = static_cast<int>(per_cta - 1 < trace_iters ? per_cta - 1 : trace_iters);
+        if (iters > 4) {
+            // differences between stamps, median over iterations 2 .. iters-1 (steady state)
+            auto med = [&](int a_slot, int a_it_off, int b_slot) {
+                std::vector<long long> d;
+                for (int it = 2; it + a_it_off < iters; ++it) d.push_back(h[(it + a_it_off) * 16 + a_slot] - h[it * 16 + b_slot]);
+                std::sort(d.begin(), d.end());
+                return d.empty() ? 0LL : d[d.size() / 2];
+            };
+            fprintf(stderr,
+                    "[vq_tc trace, CTA 0, cycles, median of %d tiles]\n"
+                    "  tile period (epilogue warp)      %lld\n"
+                    "  MMA issuer : wait x planes %lld | issue+commit half0 %lld | half1 (incl. wait for a free accumulator) %lld\n"
+                    "  converter  : wait free plane buffer %lld | convert + publish %lld | rest of its loop (prefetch issue) %lld\n"
+                    "  epilogue   : wait acc0 %lld | top-2 half0 %lld | wait acc1 %lld | top-2 half1 %lld | merge+barrier %lld | re-decide + output %lld\n",
+                    iters - 2, med(7, 1, 7), med(1, 0, 0), med(2, 0, 1), med(3, 0, 2), med(5, 0, 4), med(6, 0, 5), med(4, 1, 6),
+                    med(8, 0, 7), med(9, 0, 8), med(10, 0, 9), med(11, 0, 10), med(12, 0, 11), med(13, 0, 12));
+        }
+    }
     return VQCPC_OK;
 }
 
