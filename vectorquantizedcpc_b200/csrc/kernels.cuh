@@ -33,7 +33,7 @@ int vq_lookup(const float* x, const float* codebook, int64_t n, int n_codes, int
               cudaStream_t stream);
 // tensor-core search (vq_tc.cu); vq_lookup_auto picks it for n >= VQ_TC_MIN_FRAMES when scratch is provided
 constexpr int64_t VQ_TC_MIN_FRAMES = 8192;
-constexpr size_t VQ_TC_PLANES_BYTES = 512 * 128 * 2;
+constexpr size_t VQ_TC_PLANES_BYTES = 512 * 128 * 2 + 512 * 4 + 512 * 32;   // bf16 hi/lo planes of -2e | |e|^2 fp32 | |e|^2 MMA block
 int vq_lookup_tc(const float* x, const float* codebook, int64_t n, float* q, int64_t* idx, void* planes_ws, int* err,
                  cudaStream_t stream);
 int vq_lookup_auto(const float* x, const float* codebook, int64_t n, float* q, int64_t* idx, void* planes_ws, int* err,

@@ -88,6 +88,16 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
     d |= static_cast<uint64_t>(2) << 61;
     return d;
 }
+// K-major SWIZZLE_32B tile (rows of 32 bytes, 8-row groups 256 bytes apart): one K = 16 step of bf16
+__device__ __forceinline__ uint64_t umma_desc_sw32(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3fff);
+    d |= static_cast<uint64_t>(1) << 16;
+    d |= static_cast<uint64_t>(256 >> 4) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(6) << 61;
+    return d;
+}
 __device__ __forceinline__ float fmin3(float a, float b, float c) {
     float d;
     asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));     // FMNMX3
@@ -102,13 +112,17 @@ constexpr uint32_t VT_CB_HALF = 256 * 128;                 // bytes of one (plan
 constexpr uint32_t VT_CB_BYTES = 4 * VT_CB_HALF;           // hi/lo x two halves = 128 KB
 constexpr uint32_t VT_PLANE = VT_TF * 128;                 // 16 KB: one bf16 plane of an x tile
 constexpr uint32_t VT_XBUF = 2 * VT_PLANE;                 // hi + lo
-constexpr size_t VT_SMEM = VT_CB_BYTES + 2 * VT_XBUF + 1024;
+constexpr uint32_t VT_AUG_A = VT_TF * 32;                  // 4 KB: constant ones block, 128 rows x 32 B (one K = 16 step)
+constexpr uint32_t VT_AUG_B = VT_M * 32;                   // 16 KB: |e|^2 block, 512 rows x 32 B
+constexpr size_t VT_SMEM = VT_CB_BYTES + 2 * VT_XBUF + VT_AUG_A + VT_AUG_B + 1024;
 constexpr uint32_t VT_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(256 >> 3) << 17) |
                               (static_cast<uint32_t>(128 >> 4) << 24);
 
 struct VqTcParams {
     const float* x;          // (n, 64)
     const float* codebook;   // (512, 64) fp32
+    const float* e2;         // (512,) |e_m|^2, fp32 kernel's arithmetic (vq_prepare_kernel)
+    const uint4* aug_b;      // (512, 2) the |e|^2 MMA block, 32 bytes per code
     float* out_q;            // (n, 64)
     int64_t* out_idx;        // (n,)
     int* err;
@@ -130,7 +144,10 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vq_tc_kernel(const __grid_const
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(vt_smem) + 1023) & ~uintptr_t(1023));
     unsigned char* cb_s = smem;                       // [plane][half][256 rows][128 B]
     unsigned char* x_s = smem + VT_CB_BYTES;          // [buf][plane][128 rows][128 B]
+    unsigned char* aug_a = x_s + 2 * VT_XBUF;         // [128 rows][16 bf16]   (SWIZZLE_32B tile)
+    unsigned char* aug_b = aug_a + VT_AUG_A;          // [512 rows][16 bf16]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (p.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) p.trace[14] = clock64();      // kernel entry
 
     if (threadIdx.x == 0) {
         mbar_init(&cb_bar, 1);
@@ -147,14 +164,18 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vq_tc_kernel(const __grid_const
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    // |e_m|^2 with the fp32 kernel's arithmetic (sequential FMA over k) and max |e_m|
-    for (int m = threadIdx.x; m < VT_M; m += VT_THREADS) {
-        const float* e = p.codebook + m * VT_D;
-        float s = 0.f;
-#pragma unroll 8
-        for (int k = 0; k < VT_D; ++k) s = fmaf(__ldg(e + k), __ldg(e + k), s);
-        e2s[m] = s;
+    // |e_m|^2 and its MMA block were prepared once by vq_prepare_kernel: |e_m|^2 rides into the accumulator through one
+    // extra K = 16 MMA step (A row = ones, B row m = 0.5 |e_m|^2 split into three bf16 pieces, exact to fp32 precision;
+    // both 16-byte halves of a row carry the same three entries, so the product is |e_m|^2 whatever the swizzle does
+    // with the two halves of either operand's rows).
+    for (int m = threadIdx.x; m < VT_M; m += VT_THREADS) e2s[m] = __ldg(p.e2 + m);
+    for (int i = threadIdx.x; i < VT_M * 2; i += VT_THREADS) reinterpret_cast<uint4*>(aug_b)[i] = __ldg(p.aug_b + i);
+    for (int r = threadIdx.x; r < VT_TF; r += VT_THREADS) {
+        __nv_bfloat16* arow = reinterpret_cast<__nv_bfloat16*>(aug_a + r * 32);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) arow[k] = __float2bfloat16_rn((k & 7) < 3 ? 1.0f : 0.0f);
     }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");        // generic-proxy stores -> visible to tcgen05.mma
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -209,6 +230,7 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vq_tc_kernel(const __grid_const
 #pragma unroll
                     for (int k = 0; k < 4; ++k) tc_mma_f16(d, a_lo + 2 * k, b_hi + 2 * k, VT_IDESC, 1u);
                     }
+                    tc_mma_f16(d, umma_desc_sw32(smem_u32(aug_a)), umma_desc_sw32(smem_u32(aug_b) + half * 256 * 32), VT_IDESC, 1u);   // + |e|^2
                     }
                     tc_commit(&tfull_bar[half]);
                     tphase[half] ^= 1;
@@ -318,7 +340,6 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vq_tc_kernel(const __grid_const
                 // software-pipelined TMEM reads: the load of chunk c+1 is in flight while chunk c is reduced
                 const int col0 = half * 256 + ch * 128;
                 const uint32_t tbase = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + col0;
-                const float* e2p = &e2s[col0];
                 // the index packed into the score is LOCAL to these 128 columns -- an immediate of the LOP3; a global index
                 // costs one integer add per element on the same (half-rate) pipe as the min/max.  It is widened when the
                 // half is folded into (b1, b2).
@@ -334,12 +355,10 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vq_tc_kernel(const __grid_const
                     if (cc + 1 < 4) tc_ld32(tbase + 32 * (cc + 1), vn);
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
-                        const float4 e4 = *reinterpret_cast<const float4*>(e2p + 32 * cc + j);    // broadcast LDS.128
-                        const float ev[4] = {e4.x, e4.y, e4.z, e4.w};
                         float k[4];
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
-                            const float sc = ev[q] + __uint_as_float(v[j + q]);               // |e|^2 + (-2 x.e)
+                            const float sc = __uint_as_float(v[j + q]);                       // |e|^2 - 2 x.e, all from the tensor cores
                             // one LOP3: (bits & mask) | local index -- the mask sits in a register so that the index can be
                             // the instruction's single immediate operand
                             uint32_t kb;
@@ -427,22 +446,38 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vq_tc_kernel(const __grid_const
 #undef VT_TRACE
     tc_fence_before();
     __syncthreads();
+    if (p.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) p.trace[15] = clock64();      // all roles done
     if (warp == VT_MMA_WARP) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
     }
 }
 
-// scaled split: planes of (scale * x)
-__global__ void split_scaled_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int rows, int K, float scale) {
-    const int total = rows * K;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        const int r = i / K, k = i % K;
-        const float v = scale * x[i];
+// One-time preparation of the codebook for vq_tc_kernel (one thread per code): bf16 hi/lo planes of -2 e_m, |e_m|^2 with
+// the fp32 kernel's arithmetic (sequential FMA over k), and the 32-byte row of the |e|^2 MMA block.
+__global__ void vq_prepare_kernel(const float* __restrict__ codebook, __nv_bfloat16* __restrict__ planes, float* __restrict__ e2,
+                                  __nv_bfloat16* __restrict__ aug_b) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= VT_M) return;
+    const float* e = codebook + m * VT_D;
+    float s = 0.f;
+    for (int k = 0; k < VT_D; ++k) {
+        const float ev = __ldg(e + k);
+        s = fmaf(ev, ev, s);
+        const float v = -2.0f * ev;
         const __nv_bfloat16 h = __float2bfloat16_rn(v);
-        out[r * 2 * K + k] = h;
-        out[r * 2 * K + K + k] = __float2bfloat16_rn(v - __bfloat162float(h));
+        planes[m * 2 * VT_D + k] = h;
+        planes[m * 2 * VT_D + VT_D + k] = __float2bfloat16_rn(v - __bfloat162float(h));
     }
+    e2[m] = s;
+    const float hs = 0.5f * s;
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(hs);
+    const float r1 = hs - __bfloat162float(h0);
+    const __nv_bfloat16 h1 = __float2bfloat16_rn(r1);
+    const __nv_bfloat16 h2 = __float2bfloat16_rn(r1 - __bfloat162float(h1));
+    __nv_bfloat16* brow = aug_b + m * 16;
+    for (int k = 0; k < 16; ++k) brow[k] = __float2bfloat16_rn(0.f);
+    brow[0] = h0; brow[1] = h1; brow[2] = h2; brow[8] = h0; brow[9] = h1; brow[10] = h2;
 }
 
 typedef CUresult (*PFN_encodeTiled2)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -465,7 +500,9 @@ int vq_lookup_tc(const float* x, const float* codebook, int64_t n, float* q, int
         }
         fn = reinterpret_cast<PFN_encodeTiled2>(fp);
     }
-    split_scaled_kernel<<<64, 256, 0, stream>>>(codebook, static_cast<__nv_bfloat16*>(planes_ws), VT_M, VT_D, -2.0f);
+    float* e2_ws = reinterpret_cast<float*>(static_cast<unsigned char*>(planes_ws) + VT_CB_BYTES);
+    __nv_bfloat16* aug_ws = reinterpret_cast<__nv_bfloat16*>(static_cast<unsigned char*>(planes_ws) + VT_CB_BYTES + VT_M * 4);
+    vq_prepare_kernel<<<VT_M / 64, 64, 0, stream>>>(codebook, static_cast<__nv_bfloat16*>(planes_ws), e2_ws, aug_ws);
     VQ_CUDA(cudaGetLastError());
     count_launch(1);
     CUtensorMap map;
@@ -490,7 +527,7 @@ int vq_lookup_tc(const float* x, const float* codebook, int64_t n, float* q, int
         VQ_CUDA(cudaMalloc(&d_trace, sizeof(long long) * 16 * trace_iters));
         VQ_CUDA(cudaMemsetAsync(d_trace, 0, sizeof(long long) * 16 * trace_iters, stream));
     }
-    VqTcParams p{x, codebook, q, idx, err, static_cast<long long>(n), dbg, d_trace, trace_iters};
+    VqTcParams p{x, codebook, e2_ws, reinterpret_cast<const uint4*>(aug_ws), q, idx, err, static_cast<long long>(n), dbg, d_trace, trace_iters};
     vq_tc_kernel<<<static_cast<unsigned>(n_tiles < sms ? n_tiles : sms), VT_THREADS, VT_SMEM, stream>>>(map, p);
     VQ_CUDA(cudaGetLastError());
     count_launch(1);
@@ -509,6 +546,11 @@ int vq_lookup_tc(const float* x, const float* codebook, int64_t n, float* q, int
                 std::sort(d.begin(), d.end());
                 return d.empty() ? 0LL : d[d.size() / 2];
             };
+            fprintf(stderr, "[vq_tc trace] CTA 0: first tile's epilogue starts %lld cycles after its converter's first stamp; tile starts (epilogue) relative to it:",
+                    h[0 * 16 + 7] - h[0 * 16 + 4]);
+            for (int it = 0; it < iters; it += 8) fprintf(stderr, " t%d=%lld", it, h[it * 16 + 7] - h[0 * 16 + 4]);
+            fprintf(stderr, "\n[vq_tc trace] kernel entry -> first converter stamp %lld cycles; entry -> all roles done %lld cycles (%lld tiles on this CTA)\n",
+                    h[4] - h[14], h[15] - h[14], per_cta);
             fprintf(stderr,
                     "[vq_tc trace, CTA 0, cycles, median of %d tiles]\n"
                     "  tile period (epilogue warp)      %lld\n"
