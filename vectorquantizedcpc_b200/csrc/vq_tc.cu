@@ -323,6 +323,8 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vq_tc_kernel(const __grid_const
         bool ok = true;
         int it = 0;
         const float emax = emax_s;
+        int pend_code = 0;                                  // decided code of this lane's row of the PREVIOUS tile
+        long long pend_fr0 = -1;                            // first frame of this warp's 16 rows of that tile (-1: nothing pending)
         uint32_t keymask;
         asm("mov.u32 %0, 0xfffffe00;" : "=r"(keymask));     // opaque to constant propagation on purpose (see the LOP3 below)
         for (long long tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x, ++it) {
@@ -346,6 +348,22 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vq_tc_kernel(const __grid_const
                 float b1a = INFINITY, b2a = INFINITY, b1b = INFINITY, b2b = INFINITY;
                 uint32_t va[32], vb[32];
                 tc_ld32(tbase, va);
+                // deferred output of the previous tile: its 8 gather loads are issued here and stored after this half's
+                // top-2 pass, so their latency hides behind ~2000 cycles of min/max work instead of ending every tile
+                float4 gq[8];
+                const bool flush_now = (half == 0) && (pend_fr0 >= 0) && !(p.debug & 2);
+                if (flush_now) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const int r = 2 * k + (lane >> 4);                   // row within this warp's 16
+                        const int code = __shfl_sync(0xffffffffu, pend_code, ch * 16 + r);
+                        // volatile asm: the load must be ISSUED here (the compiler would otherwise sink it to its first use,
+                        // the store after the pass, and expose the whole latency again)
+                        const float4* src = reinterpret_cast<const float4*>(p.codebook + code * VT_D) + (lane & 15);
+                        asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];"
+                                     : "=f"(gq[k].x), "=f"(gq[k].y), "=f"(gq[k].z), "=f"(gq[k].w) : "l"(src));
+                    }
+                }
 #pragma unroll
                 for (int cc = 0; cc < 4; ++cc) {
                     if (p.debug & 1) { tc_wait_ld(); break; }
@@ -375,6 +393,15 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vq_tc_kernel(const __grid_const
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty_bar[half]);
+                if (flush_now) {
+                    // one fully coalesced 256-byte row per 16 lanes
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const int r = 2 * k + (lane >> 4);
+                        if (pend_fr0 + r < p.n) reinterpret_cast<float4*>(p.out_q + (pend_fr0 + r) * VT_D)[lane & 15] = gq[k];
+                    }
+                    pend_fr0 = -1;
+                }
                 // fold this half's two chains into the tile's best two, with code indices (local index < 128, col0 a multiple of 128)
                 const float h1 = __uint_as_float(__float_as_uint(fminf(b1a, b1b)) + static_cast<uint32_t>(col0));
                 const float h2 = __uint_as_float(__float_as_uint(fminf(fmaxf(b1a, b1b), fminf(b2a, b2b))) + static_cast<uint32_t>(col0));
@@ -427,20 +454,20 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vq_tc_kernel(const __grid_const
                 p.out_idx[fr] = i1;
             }
             __syncwarp();
-            if (!(p.debug & 2)) {
-                // cooperative gather: per instruction two rows, 16 lanes x 16 B each = one fully coalesced 256-byte row
-                const long long fr0 = tile * VT_TF + quarter * 32 + ch * 16;
+            pend_code = i1;
+            pend_fr0 = tile * VT_TF + quarter * 32 + ch * 16;
+            if (e == 0) { VT_TRACE(13) }
+        }
+        if (pend_fr0 >= 0 && !(p.debug & 2)) {               // output of the last tile
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const int r = 2 * k + (lane >> 4);                       // row within this warp's 16
-                    const int code = __shfl_sync(0xffffffffu, i1, ch * 16 + r);
-                    if (fr0 + r < p.n) {
-                        const float4 v = __ldg(reinterpret_cast<const float4*>(p.codebook + code * VT_D) + (lane & 15));
-                        reinterpret_cast<float4*>(p.out_q + (fr0 + r) * VT_D)[lane & 15] = v;
-                    }
+            for (int k = 0; k < 8; ++k) {
+                const int r = 2 * k + (lane >> 4);
+                const int code = __shfl_sync(0xffffffffu, pend_code, ch * 16 + r);
+                if (pend_fr0 + r < p.n) {
+                    const float4 v = __ldg(reinterpret_cast<const float4*>(p.codebook + code * VT_D) + (lane & 15));
+                    reinterpret_cast<float4*>(p.out_q + (pend_fr0 + r) * VT_D)[lane & 15] = v;
                 }
             }
-            if (e == 0) { VT_TRACE(13) }
         }
     }
 #undef VT_TRACE
