@@ -493,6 +493,7 @@ static int lstm_launch(LstmParams prm, void* ll_mem, cudaStream_t stream) {
 // state, writes h_t into the output sequence and re-splits it into the planes the next step's GEMM reads.
 // ------------------------------------------------------------------------------------------------
 constexpr int LSTM_BATCHED_MIN_B = 64;
+constexpr int LSTM_FUSED_MAX_B = 2048;            // below: fused tcgen05 step kernel; from here on: GEMM + coalesced gate kernel
 
 __global__ void lstm_gate_kernel(const float* __restrict__ gates, const float* __restrict__ table,
                                  const int64_t* __restrict__ idx, int t, int Tp, float* __restrict__ cstate,
@@ -530,11 +531,11 @@ __global__ void lstm_gate_kernel(const float* __restrict__ gates, const float* _
     }
 }
 
-// workspace: [header][table 512x1024][ll][gates B x 1024][cstate B x 256][h planes B x 512 bf16]
+// workspace: [header][table 512x1024][ll][gates B x 1024][cstate B x 256][h planes B x 512 bf16] x 2
 static size_t lstm_batched_bytes(int B) {
     if (B < LSTM_BATCHED_MIN_B) return 0;
     return align_up(sizeof(float) * B * LSTM_G, 256) + align_up(sizeof(float) * B * LSTM_H, 256) +
-           align_up(2 * static_cast<size_t>(B) * 2 * LSTM_H, 256);
+           2 * align_up(2 * static_cast<size_t>(B) * 2 * LSTM_H, 256);      // two h-plane buffers (ping-pong across steps)
 }
 static size_t lstm_ws_bytes(int B) {
     return sizeof(WorkspaceHeader) + align_up(sizeof(float) * VQ_M * LSTM_G, 256) +
@@ -559,23 +560,19 @@ int lstm_forward(const vqcpc_encoder_weights* w, const int64_t* idx, int B, int 
         unsigned char* bb = static_cast<unsigned char*>(ll) + lstm_ll_bytes(LSTM_MAX_GROUPS, LSTM_MAX_NB);
         float* gates = reinterpret_cast<float*>(bb); bb += align_up(sizeof(float) * B * LSTM_G, 256);
         float* cstate = reinterpret_cast<float*>(bb); bb += align_up(sizeof(float) * B * LSTM_H, 256);
-        __nv_bfloat16* hplanes = reinterpret_cast<__nv_bfloat16*>(bb);
+        __nv_bfloat16* hplanes = reinterpret_cast<__nv_bfloat16*>(bb); bb += align_up(2 * static_cast<size_t>(B) * 2 * LSTM_H, 256);
+        __nv_bfloat16* hplanes2 = reinterpret_cast<__nv_bfloat16*>(bb);
         const bool tc = (mode == VQCPC_GEMM_BF16X3) && (w->lstm_whh_p != nullptr);
-        TcPlan plan;
-        if (tc && (rc = gemm_tc_plan(&plan, hplanes, w->lstm_whh_p, nullptr, gates, LSTM_G, B, LSTM_G, LSTM_H, 3, &hdr->status)))
-            return rc;
         const int64_t total = static_cast<int64_t>(B) * (LSTM_H / 4);
         const unsigned grid = static_cast<unsigned>((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
-        for (int t = 0; t < Tp; ++t) {
-            if (t > 0) {
-                if (tc) rc = gemm_tc_run(&plan, stream, true);
-                else rc = gemm_dense(out_c + static_cast<int64_t>(t - 1) * LSTM_H, static_cast<int64_t>(Tp) * LSTM_H, w->lstm_w_hh,
-                                     LSTM_H, nullptr, gates, LSTM_G, B, LSTM_G, LSTM_H, stream);
-                if (rc) return rc;
-            }
-            {
-                // both kernels of a step are launched as programmatic dependents: the prologue of each overlaps the tail
-                // of its predecessor (150 steps x 2 kernel boundaries per utterance batch)
+        if (tc && B >= LSTM_FUSED_MAX_B) {
+            // Large batches: the step's product through the plain tcgen05 GEMM, then the fully coalesced gate kernel (the
+            // fused epilogue below touches 32-byte pieces per thread, which loses to coalesced traffic once the step is
+            // bandwidth- rather than launch-bound: 4096 utterances 14.6 ms unfused vs 16.1 ms fused).
+            TcPlan plan;
+            if ((rc = gemm_tc_plan(&plan, hplanes, w->lstm_whh_p, nullptr, gates, LSTM_G, B, LSTM_G, LSTM_H, 3, &hdr->status))) return rc;
+            for (int t = 0; t < Tp; ++t) {
+                if (t > 0 && (rc = gemm_tc_run(&plan, stream, true))) return rc;
                 cudaLaunchConfig_t cfg{};
                 cfg.gridDim = dim3(grid);
                 cfg.blockDim = dim3(256);
@@ -584,12 +581,38 @@ int lstm_forward(const vqcpc_encoder_weights* w, const int64_t* idx, int B, int 
                 attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
                 attr[0].val.programmaticStreamSerializationAllowed = 1;
                 cfg.attrs = attr;
-                cfg.numAttrs = (tc && t > 0) ? 1 : 0;
+                cfg.numAttrs = t > 0 ? 1 : 0;
                 const float* gates_in = t > 0 ? gates : nullptr;
-                __nv_bfloat16* planes_out = tc ? hplanes : nullptr;
-                VQ_CUDA(cudaLaunchKernelEx(&cfg, lstm_gate_kernel, gates_in, static_cast<const float*>(table), idx, t, Tp, cstate,
-                                           out_c, planes_out, B));
+                VQ_CUDA(cudaLaunchKernelEx(&cfg, lstm_gate_kernel, gates_in, static_cast<const float*>(table), idx, t, Tp, cstate, out_c,
+                                           hplanes, B));
+                count_launch(1);
             }
+            return VQCPC_OK;
+        }
+        if (tc) {
+            // Small / medium batches (launch- and fill-bound steps): step 0 has h = 0 (gate kernel alone, writes the first h
+            // planes); every later step is ONE kernel -- W_hh h_{t-1} on tcgen05 with the LSTM cell fused into its epilogue
+            // -- reading one plane buffer and writing the other, each launched as a programmatic dependent of its
+            // predecessor (512 utterances x 3 s: 3.54 -> 3.40 ms).
+            __nv_bfloat16* pb[2] = {hplanes, hplanes2};
+            TcPlan plan[2];
+            for (int i = 0; i < 2; ++i)
+                if ((rc = gemm_tc_plan_lstm(&plan[i], pb[i], w->lstm_whh_p, B, LSTM_H, &hdr->status))) return rc;
+            lstm_gate_kernel<<<grid, 256, 0, stream>>>(nullptr, table, idx, 0, Tp, cstate, out_c, pb[0], B);
+            VQ_CUDA(cudaGetLastError());
+            count_launch(1);
+            for (int t = 1; t < Tp; ++t)
+                if ((rc = gemm_tc_run_lstm(&plan[(t - 1) & 1], table, idx, cstate, out_c, pb[t & 1], t, Tp, stream, true))) return rc;
+            return VQCPC_OK;
+        }
+        for (int t = 0; t < Tp; ++t) {
+            if (t > 0) {
+                rc = gemm_dense(out_c + static_cast<int64_t>(t - 1) * LSTM_H, static_cast<int64_t>(Tp) * LSTM_H, w->lstm_w_hh,
+                                LSTM_H, nullptr, gates, LSTM_G, B, LSTM_G, LSTM_H, stream);
+                if (rc) return rc;
+            }
+            lstm_gate_kernel<<<grid, 256, 0, stream>>>(t > 0 ? gates : nullptr, table, idx, t, Tp, cstate, out_c, nullptr, B);
+            VQ_CUDA(cudaGetLastError());
             count_launch(1);
         }
         return VQCPC_OK;

@@ -75,7 +75,22 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
           "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
         : "r"(taddr) : "memory");
 }
+__device__ __forceinline__ void tc_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr) : "memory");
+}
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_split_store4(float4 o, __nv_bfloat16* hi, __nv_bfloat16* lo) {
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(o.x), h1 = __float2bfloat16_rn(o.y), h2 = __float2bfloat16_rn(o.z),
+                        h3 = __float2bfloat16_rn(o.w);
+    reinterpret_cast<__nv_bfloat162*>(hi)[0] = __halves2bfloat162(h0, h1);
+    reinterpret_cast<__nv_bfloat162*>(hi)[1] = __halves2bfloat162(h2, h3);
+    reinterpret_cast<__nv_bfloat162*>(lo)[0] = __halves2bfloat162(__float2bfloat16_rn(o.x - __bfloat162float(h0)),
+                                                                   __float2bfloat16_rn(o.y - __bfloat162float(h1)));
+    reinterpret_cast<__nv_bfloat162*>(lo)[1] = __halves2bfloat162(__float2bfloat16_rn(o.z - __bfloat162float(h2)),
+                                                                   __float2bfloat16_rn(o.w - __bfloat162float(h3)));
+}
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start >> 4, LBO = 1 (unused
 // for swizzled K-major), SBO = 1024 B (8 rows x 128 B) >> 4, version = 1 (Blackwell), layout type 2 = SWIZZLE_128B.
@@ -96,6 +111,16 @@ struct TcParams {
     long long ldc;
     int M, N, K;            // K = columns of ONE plane (multiple of 64)
     int nseg;               // 1: plain bf16 product; 3: hi/lo split, planes stored [hi | lo] (2K columns)
+    // Fused LSTM step (lstm_table != nullptr): the product is W_hh h_{t-1} for N = 4 * hidden gate rows.  A column tile of
+    // BN columns holds the four gates of BN/4 hidden units (the producer loads four BN/4-row boxes of W, one per gate), the
+    // epilogue adds the gathered input projection, applies the cell and writes h_t (fp32 into the output sequence and
+    // bf16 hi/lo planes for the next step, into the OTHER plane buffer: this step's A operand is still being read).
+    const float* lstm_table;        // (n_codes, 4 * hidden) = W_ih e + b_ih + b_hh per code
+    const int64_t* lstm_idx;        // (M, Tp) code indices
+    float* lstm_c;                  // (M, hidden) cell state, in place
+    float* lstm_out;                // (M, Tp, hidden)
+    __nv_bfloat16* lstm_planes_out; // (M, 2 * hidden) [hi | lo] of h_t
+    int lstm_t, lstm_Tp;
 };
 
 template <int BN>
@@ -158,7 +183,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     unsigned char* sa = smem + stage * STAGE_BYTES;
                     mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
                     tma_load_2d(sa, &map_a, a_col, tm * TC_BM, &full_bar[stage]);
-                    tma_load_2d(sa + A_BYTES, &map_w, w_col, tn * BN, &full_bar[stage]);
+                    if (p.lstm_table == nullptr) {
+                        tma_load_2d(sa + A_BYTES, &map_w, w_col, tn * BN, &full_bar[stage]);
+                    } else {
+                        // gate g of units tn*BN/4 .. : rows g * hidden + tn * BN/4 of W_hh, BN/4 rows each (the W map's box)
+#pragma unroll
+                        for (int g = 0; g < 4; ++g)
+                            tma_load_2d(sa + A_BYTES + g * (BN / 4) * TC_BK * 2, &map_w, w_col, g * (p.N / 4) + tn * (BN / 4), &full_bar[stage]);
+                    }
                     if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -206,6 +238,57 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             if (!ok) break;
             tc_fence_after();
             const int row = tm * TC_BM + quarter * 32 + lane;
+            if (p.lstm_table != nullptr) {
+                // ---- fused LSTM cell: 8 hidden units at a time, their four gates from four column blocks of the accumulator
+                constexpr int UT = BN / 4;                      // hidden units of this column tile
+                const int hidden = p.N / 4;
+                const uint32_t tb = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
+                const float* trow = nullptr;
+                if (row < p.M) trow = p.lstm_table + __ldg(p.lstm_idx + static_cast<long long>(row) * p.lstm_Tp + p.lstm_t) * p.N;
+#pragma unroll 1
+                for (int ug = 0; ug < UT; ug += 8) {
+                    uint32_t v[4][8];
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) tc_ld8(tb + g * UT + ug, v[g]);
+                    tc_wait_ld();
+                    if (row < p.M) {
+                        const int u0 = tn * UT + ug;
+                        float x[4][8];
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            const float4 a = __ldg(reinterpret_cast<const float4*>(trow + g * hidden + u0));
+                            const float4 b = __ldg(reinterpret_cast<const float4*>(trow + g * hidden + u0) + 1);
+                            x[g][0] = a.x; x[g][1] = a.y; x[g][2] = a.z; x[g][3] = a.w; x[g][4] = b.x; x[g][5] = b.y; x[g][6] = b.z; x[g][7] = b.w;
+                        }
+                        float* cp = p.lstm_c + static_cast<long long>(row) * hidden + u0;
+                        const float4 c0v = *reinterpret_cast<const float4*>(cp), c1v = *(reinterpret_cast<const float4*>(cp) + 1);
+                        float c[8] = {c0v.x, c0v.y, c0v.z, c0v.w, c1v.x, c1v.y, c1v.z, c1v.w};
+                        float h[8];
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            // same expression order as lstm_gate_kernel: table + gates, then the cell
+                            const float gi = x[0][k] + __uint_as_float(v[0][k]), gf = x[1][k] + __uint_as_float(v[1][k]);
+                            const float gg = x[2][k] + __uint_as_float(v[2][k]), go = x[3][k] + __uint_as_float(v[3][k]);
+                            c[k] = sigmoid_fast(gf) * c[k] + sigmoid_fast(gi) * tanh_fast(gg);
+                            h[k] = sigmoid_fast(go) * tanh_fast(c[k]);
+                        }
+                        *reinterpret_cast<float4*>(cp) = make_float4(c[0], c[1], c[2], c[3]);
+                        *(reinterpret_cast<float4*>(cp) + 1) = make_float4(c[4], c[5], c[6], c[7]);
+                        float* op = p.lstm_out + (static_cast<long long>(row) * p.lstm_Tp + p.lstm_t) * hidden + u0;
+                        *reinterpret_cast<float4*>(op) = make_float4(h[0], h[1], h[2], h[3]);
+                        *(reinterpret_cast<float4*>(op) + 1) = make_float4(h[4], h[5], h[6], h[7]);
+                        __nv_bfloat16* pr = p.lstm_planes_out + static_cast<long long>(row) * 2 * hidden + u0;
+                        tc_split_store4(make_float4(h[0], h[1], h[2], h[3]), pr, pr + hidden);
+                        tc_split_store4(make_float4(h[4], h[5], h[6], h[7]), pr + 4, pr + hidden + 4);
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+                acc_phase[acc] ^= 1;
+                acc ^= 1;
+                continue;
+            }
             float* crow = p.C + static_cast<long long>(row) * p.ldc + tn * BN;
 #pragma unroll 1
             for (int c0 = 0; c0 < BN; c0 += 32) {
@@ -542,10 +625,38 @@ int gemm_tc_plan(TcPlan* plan, const void* a_planes, const void* w_planes, const
     return VQCPC_OK;
 }
 
+// Fused LSTM step: plan over (h planes of step t-1, W_hh planes); the W map's box is BN/4 rows (one gate of a tile)
+int gemm_tc_plan_lstm(TcPlan* plan, const void* h_planes, const void* whh_planes, int M, int hidden, int* err_flag) {
+    VQ_ARG(plan && h_planes && whh_planes && err_flag, "gemm_tc(lstm): null pointer");
+    VQ_ARG(M > 0 && hidden % 64 == 0, "gemm_tc(lstm): bad shape M=%d hidden=%d", M, hidden);
+    const int N = 4 * hidden, K = hidden;
+    plan->bn = 256;
+    {
+        long long tiles = static_cast<long long>((M + TC_BM - 1) / TC_BM) * (N / plan->bn);
+        while (plan->bn > 64 && tiles * 2 <= 148) { plan->bn /= 2; tiles *= 2; }
+    }
+    int rc = make_map(reinterpret_cast<CUtensorMap*>(plan->map_a), h_planes, M, 2LL * K, 2LL * K, TC_BM);
+    if (rc) return rc;
+    rc = make_map(reinterpret_cast<CUtensorMap*>(plan->map_w), whh_planes, N, 2LL * K, 2LL * K, plan->bn / 4);
+    if (rc) return rc;
+    plan->C = nullptr; plan->bias = nullptr; plan->err = err_flag; plan->ldc = 0; plan->M = M; plan->N = N; plan->K = K; plan->nseg = 3;
+    return VQCPC_OK;
+}
+int gemm_tc_run_lstm(const TcPlan* plan, const float* table, const int64_t* idx, float* cstate, float* out, void* planes_out, int t,
+                     int Tp, cudaStream_t stream, bool pdl) {
+    const CUtensorMap& ma = *reinterpret_cast<const CUtensorMap*>(plan->map_a);
+    const CUtensorMap& mw = *reinterpret_cast<const CUtensorMap*>(plan->map_w);
+    TcParams p{nullptr, nullptr, plan->err, 0, plan->M, plan->N, plan->K, plan->nseg,
+               table, idx, cstate, out, static_cast<__nv_bfloat16*>(planes_out), t, Tp};
+    if (plan->bn == 256) return launch_tc<256>(ma, mw, p, stream, pdl);
+    if (plan->bn == 128) return launch_tc<128>(ma, mw, p, stream, pdl);
+    return launch_tc<64>(ma, mw, p, stream, pdl);
+}
+
 int gemm_tc_run(const TcPlan* plan, cudaStream_t stream, bool pdl) {
     const CUtensorMap& ma = *reinterpret_cast<const CUtensorMap*>(plan->map_a);
     const CUtensorMap& mw = *reinterpret_cast<const CUtensorMap*>(plan->map_w);
-    TcParams p{plan->C, plan->bias, plan->err, plan->ldc, plan->M, plan->N, plan->K, plan->nseg};
+    TcParams p{plan->C, plan->bias, plan->err, plan->ldc, plan->M, plan->N, plan->K, plan->nseg, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0};
     if (plan->bn == 256) return launch_tc<256>(ma, mw, p, stream, pdl);
     if (plan->bn == 128) return launch_tc<128>(ma, mw, p, stream, pdl);
     return launch_tc<64>(ma, mw, p, stream, pdl);

@@ -21,6 +21,9 @@ struct TcPlan {                      // a tcgen05 GEMM bound to fixed operand bu
 int gemm_tc_plan(TcPlan* plan, const void* a_planes, const void* w_planes, const float* bias, float* C, long long ldc, int M,
                  int N, int K, int nseg, int* err_flag);
 int gemm_tc_run(const TcPlan* plan, cudaStream_t stream, bool pdl = false);   // pdl: programmatic dependent launch
+int gemm_tc_plan_lstm(TcPlan* plan, const void* h_planes, const void* whh_planes, int M, int hidden, int* err_flag);
+int gemm_tc_run_lstm(const TcPlan* plan, const float* table, const int64_t* idx, float* cstate, float* out, void* planes_out, int t,
+                     int Tp, cudaStream_t stream, bool pdl);
 size_t gemm_tc_ln_scratch_bytes(int N);
 bool gemm_tc_ln_supported(int N);
 int gemm_tc_ln(const void* a_planes, const void* w_planes, const float* ln_w, const float* ln_b, void* out_planes,
