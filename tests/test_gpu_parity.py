@@ -423,8 +423,9 @@ def test_vocoder_batched_generate_equals_single_utterance_runs():
 
 
 @pytest.mark.parametrize("B,sel", [
-    (8, [0, 5, 7]),                            # one group (ar_batch_kernel)
-    (21, [0, 10, 11, 20]),
+    (8, [0, 5, 7]),                            # one group (ar_batch_kernel), one utterance tile of 16 in use
+    (21, [0, 10, 11, 20]),                     # two utterance tiles of 16 in use
+    (40, [0, 15, 16, 32, 39]),                 # 33..64 utterances: all four tiles
     (64, [0, 31, 32, 63]),                     # one full group
     (70, [0, 1, 31, 34, 35, 63, 64, 69]),      # two interleaved groups 35 + 35 (ar_batch2_kernel)
     (131, [0, 63, 64, 127, 128, 130]),         # launches of 128 (two groups 64 + 64) and 3
