@@ -174,7 +174,8 @@ int vqcpc_vocoder_logits_tf(const vqcpc_vocoder_weights* w, const float* G, cons
 int vqcpc_debug_set_ar_trace(long long* device_buf, int32_t cta, int32_t first_step, int32_t n_steps);
 /* Tuning of the sample loop's exchanges: bits 0..11 cycles before the first poll round (default 400), bits 12..23
  * cycles between failed rounds (default 0), bits 24..27 cap on utterances interleaved per launch (0 = default 4),
- * bit 28 disables the batched (B >= 8) kernel, bit 29 its two-group (65..128 utterances per launch) variant. */
+ * bit 28 disables the batched (B >= 8) kernel, bit 29 its two-group (65..128 utterances per launch) variant, bit 30 routes
+ * 65..128 utterances through the experimental tcgen05 kernel (csrc/vocoder_batch_tc.cu; correct, currently slower). */
 int vqcpc_debug_set_ar_poll_gap(int32_t packed);
 /* Measures the bare 128-way LL exchange of the sample loop (no compute): mean SM cycles per exchange over `iters`
  * exchanges.  workspace >= 64 KiB.  Three exchanges per step are the latency floor bench.py reports. */

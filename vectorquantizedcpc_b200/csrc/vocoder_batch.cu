@@ -797,11 +797,15 @@ __global__ void __launch_bounds__(AB2_THREADS, 1) ar_batch2_kernel(Ab2Params p) 
 static size_t ab_ws_bytes() {
     return sizeof(float) * (2 * AB_H + AB_FC) * AB_B + sizeof(ll_word) * (AB_B * AB_Q + AB_B + AB_CTAS * 16);
 }
-size_t ar_batch_workspace_bytes() { return 2 * align_up(ab_ws_bytes(), 256); }
+size_t ar_batch_workspace_bytes() {
+    const size_t a = 2 * align_up(ab_ws_bytes(), 256), b = ar_batch_tc_workspace_bytes();
+    return a > b ? a : b;
+}
 
 long long* g_ab_trace = nullptr;
 int g_ab_trace_cta = 0, g_ab_trace_t0 = 0, g_ab_trace_n = 0;
 int g_ab_two_group = 1;      // debug switch (vqcpc_debug_set_ar_poll_gap bit 29 clears it)
+int g_ab_tc = 0;             // debug switch (bit 30 sets it): 65..128 utterances through the tcgen05 kernel (vocoder_batch_tc.cu)
 
 int ar_batch_run(const vqcpc_vocoder_weights* w, const float* G, const float* uniforms, const int64_t* x_in, int B, int T2,
                  int L, void* ws, int* status, float* out_wav, int32_t* out_codes, float* out_logits, cudaStream_t stream) {
@@ -822,13 +826,19 @@ int ar_batch_run(const vqcpc_vocoder_weights* w, const float* G, const float* un
         const int left = B - b0;
         const bool two = g_ab_two_group && left > AB_B;          // 65..128 utterances: two interleaved groups
         const int nb = two ? (left < 2 * AB_B ? left : 2 * AB_B) : (left < AB_B ? left : AB_B);
-        VQ_CUDA(cudaMemsetAsync(ws, 0, ar_batch_workspace_bytes(), stream));
         const float* Gp = G + static_cast<int64_t>(b0) * T2 * AB_G;
         const float* up = uniforms ? uniforms + static_cast<int64_t>(b0) * L : nullptr;
         const int64_t* xp = x_in ? x_in + static_cast<int64_t>(b0) * L : nullptr;
         float* ow = out_wav ? out_wav + static_cast<int64_t>(b0) * L : nullptr;
         int32_t* oc = out_codes ? out_codes + static_cast<int64_t>(b0) * L : nullptr;
         float* ol = out_logits ? out_logits + static_cast<int64_t>(b0) * L * AB_Q : nullptr;
+        if (two && g_ab_tc) {
+            int rc = ar_batch_tc_launch(w, Gp, up, xp, nb, T2, L, ws, status, ow, oc, ol, stream);
+            if (rc) return rc;
+            b0 += nb;
+            continue;
+        }
+        VQ_CUDA(cudaMemsetAsync(ws, 0, 2 * align_up(ab_ws_bytes(), 256), stream));
         if (!two) {
             AbParams p{};
             p.w_hh = w->ar_w_hh; p.b_hh = w->ar_b_hh; p.fc1_w = w->fc1_w; p.fc1_b = w->fc1_b; p.fc2_w = w->fc2_w; p.fc2_b = w->fc2_b;
