@@ -177,6 +177,12 @@ int vqcpc_debug_set_ar_trace(long long* device_buf, int32_t cta, int32_t first_s
  * bit 28 disables the batched (B >= 8) kernel, bit 29 its two-group (65..128 utterances per launch) variant, bit 30 routes
  * 65..128 utterances through the experimental tcgen05 kernel (csrc/vocoder_batch_tc.cu; correct, currently slower). */
 int vqcpc_debug_set_ar_poll_gap(int32_t packed);
+/* The single-utterance sample loop runs by default on the cluster kernel (csrc/vocoder_cluster.cu: 7 clusters of 16 CTAs,
+ * one grid-scope exchange per step, fc1 / fc2 / sampling over DSMEM) whenever the device can co-schedule that grid.
+ * enable = 0 forces the round-1 128-CTA kernel (three grid-scope exchanges per step) for A/B measurements;
+ * first_poll_delay = cycles between a CTA's own publish of h_t and its first L2 poll; poll_mode 0 = one poll round in
+ * flight, 1 = two.  The cluster kernel's trace (vqcpc_debug_set_ar_trace) has 16 slots per step instead of 8. */
+int vqcpc_debug_set_ar_cluster(int32_t enable, int32_t first_poll_delay, int32_t poll_mode);
 /* Measures the bare 128-way LL exchange of the sample loop (no compute): mean SM cycles per exchange over `iters`
  * exchanges.  workspace >= 64 KiB.  Three exchanges per step are the latency floor bench.py reports. */
 int vqcpc_debug_exchange_floor(void* workspace, size_t workspace_bytes, int32_t iters, double* mean_cycles, void* stream);

@@ -82,6 +82,7 @@ SIGNATURES = {
     "vqcpc_check_status": (C.c_int, [_vp, _vp]),
     "vqcpc_debug_set_ar_trace": (C.c_int, [_vp, _i32, _i32, _i32]),
     "vqcpc_debug_set_ar_poll_gap": (C.c_int, [_i32]),
+    "vqcpc_debug_set_ar_cluster": (C.c_int, [_i32, _i32, _i32]),
     "vqcpc_debug_exchange_floor": (C.c_int, [_vp, _sz, _i32, C.POINTER(C.c_double), _vp]),
 }
 

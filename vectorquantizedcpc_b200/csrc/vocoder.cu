@@ -550,6 +550,14 @@ __global__ void __launch_bounds__(32, 1) exchange_floor_kernel(ll_word* buf, int
 int ar_batch_run(const vqcpc_vocoder_weights* w, const float* G, const float* uniforms, const int64_t* x_in, int B, int T2,
                  int L, void* ws, int* status, float* out_wav, int32_t* out_codes, float* out_logits, cudaStream_t stream);
 constexpr int AR_BATCH_MIN_B = 8;     // from this many utterances on, the grid-barrier batched kernel wins
+// vocoder_cluster.cu: the cluster / DSMEM latency kernel (one utterance per launch)
+extern int g_cl_enable;
+int ar_cluster_supported();
+size_t ar_cluster_ll_bytes();
+int ar_cluster_launch(const vqcpc_vocoder_weights* w, const float* G, const float* uniforms, const int64_t* x_in, int L,
+                      ll_word* hbuf, int* status, float* out_wav, int32_t* out_codes, float* out_logits, long long* trace,
+                      int trace_cta, int trace_t0, int trace_n, cudaStream_t stream);
+void ar_cluster_set_poll(int delay, int mode);
 static size_t ar_ws_bytes() {
     const size_t ll = align_up(sizeof(ll_word) * AR_LL_WORDS, 256), ab = ar_batch_workspace_bytes();
     return sizeof(WorkspaceHeader) + (ll > ab ? ll : ab);
@@ -657,7 +665,20 @@ static int ar_run(const vqcpc_vocoder_weights* w, const float* G, const float* u
     if (B >= g_batch_min_b)
         return ar_batch_run(w, G, uniforms, x_in, B, T2, L, base + sizeof(WorkspaceHeader), &hdr->status, out_wav, out_codes,
                             out_logits, stream);
-    // groups of up to NB utterances share one persistent launch (their steps are interleaved inside the kernel)
+    if (g_cl_enable && ar_cluster_supported()) {
+        // one cluster-kernel launch per utterance (7 clusters x 16 CTAs, one grid-scope exchange per step)
+        for (int b = 0; b < B; ++b) {
+            rc = ar_cluster_launch(w, G + static_cast<int64_t>(b) * T2 * AR_G, uniforms ? uniforms + static_cast<int64_t>(b) * L : nullptr,
+                                   x_in ? x_in + static_cast<int64_t>(b) * L : nullptr, L, ll, &hdr->status,
+                                   out_wav ? out_wav + static_cast<int64_t>(b) * L : nullptr,
+                                   out_codes ? out_codes + static_cast<int64_t>(b) * L : nullptr,
+                                   out_logits ? out_logits + static_cast<int64_t>(b) * L * AR_Q : nullptr,
+                                   b == 0 ? g_trace.buf : nullptr, g_trace.cta, g_trace.t0, g_trace.n, stream);
+            if (rc) return rc;
+        }
+        return VQCPC_OK;
+    }
+    // fallback (device cannot co-schedule 7 clusters of 16): groups of up to NB utterances share one persistent launch
     for (int b = 0; b < B;) {
         int nb = B - b < g_nb_cap ? B - b : g_nb_cap;
         VQ_CUDA(cudaMemsetAsync(ll, 0, sizeof(ll_word) * AR_LL_PER_UTT * nb, stream));
@@ -723,6 +744,11 @@ extern "C" int vqcpc_debug_set_ar_poll_gap(int32_t packed) {
     vqcpc::g_batch_min_b = ((packed >> 28) & 1) ? (1 << 30) : vqcpc::AR_BATCH_MIN_B;   // bit 28: disable the batched kernel
     vqcpc::g_ab_two_group = ((packed >> 29) & 1) ? 0 : 1;                                // bit 29: disable its two-group variant
     vqcpc::g_ab_tc = (packed >> 30) & 1;                                                 // bit 30: 65..128 utterances on the tcgen05 kernel
+    return VQCPC_OK;
+}
+extern "C" int vqcpc_debug_set_ar_cluster(int32_t enable, int32_t first_poll_delay, int32_t poll_mode) {
+    vqcpc::g_cl_enable = enable ? 1 : 0;
+    vqcpc::ar_cluster_set_poll(first_poll_delay < 0 ? 0 : first_poll_delay, poll_mode);
     return VQCPC_OK;
 }
 namespace vqcpc { extern long long* g_ab_trace; extern int g_ab_trace_cta, g_ab_trace_t0, g_ab_trace_n; }
