@@ -44,7 +44,7 @@ def main():
         out["sample_match_first_400"] = match
         if enable:
             for cta in (0, 77):
-                buf = torch.zeros(n + 1, 16, dtype=torch.int64, device=dev)
+                buf = torch.zeros(n + 1, 32, dtype=torch.int64, device=dev)
                 lib.vqcpc_debug_set_ar_trace(buf.data_ptr(), cta, t0, n + 1)
                 voc.generate(cd, sdv, uniforms=ud)
                 lib.vqcpc_debug_set_ar_trace(None, 0, 0, 0)
@@ -56,6 +56,10 @@ def main():
                 d["sample->next step start"] = q(ts[1:n + 1, 0] - ts[:n, 7])
                 m = {"publish->M sees flag": q(ts[:n, 8] - ts[:n, 1]), "M poll h (incl. delay)": q(ts[:n, 9] - ts[:n, 8]),
                      "M sts+bar+fc1 rows": q(ts[:n, 10] - ts[:n, 9]), "M wait r+fc2p+W_hh": q(ts[:n, 11] - ts[:n, 10])}
+                m["poll done after publish, per M warp (median)"] = [float(torch.median(ts[:n, 16 + w] - ts[:n, 1])) for w in range(7)]
+                pd = ts[:n, 16:23] - ts[:n, 1:2]
+                m["slowest M warp poll done after publish [min,med,p90,max]"] = q(pd.max(dim=1).values)
+                m["poll rounds per M warp (mean)"] = [float(ts[:n, 24 + w].mean()) for w in range(7)]
                 out[f"cta{cta}"] = {"cycles_per_step[min,med,p90,max]": q(ts[1:n + 1, 0] - ts[:n, 0]), "chain": d, "mwarp0": m}
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with torch.no_grad():
@@ -76,7 +80,7 @@ def main():
         print("   step", [round(v) for v in c["cycles_per_step[min,med,p90,max]"]])
         print("   chain med", {k: round(v[1]) for k, v in c["chain"].items()})
         print("   chain min", {k: round(v[0]) for k, v in c["chain"].items()})
-        print("   mwarp med", {k: round(v[1]) for k, v in c["mwarp0"].items()})
+        print("   mwarp med", {k: (round(v[1]) if len(v) == 4 else [round(x, 2) for x in v]) for k, v in c["mwarp0"].items()})
 
 
 if __name__ == "__main__":

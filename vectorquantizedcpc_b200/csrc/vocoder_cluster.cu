@@ -37,7 +37,7 @@ constexpr int CL_MT = 32 * CL_MW;        // 224
 constexpr int CL_THREADS = CL_MT + 32;   // + the chain warp
 constexpr int CL_CHUNKS = CL_H / 64;     // 14 fc1 column chunks of 64
 constexpr int CL_X_INIT = 128;
-constexpr int CL_TRACE_STRIDE = 16;
+constexpr int CL_TRACE_STRIDE = 32;     // slots 0..7 chain warp, 8..11 M warp 0, 16+q / 24+q: poll-done clock / poll rounds of M warp q
 static_assert(CL_U == 8 && CL_MW * 128 == CL_H && CL_CHUNKS * 16 == CL_MT, "layout");
 
 struct ClParams {
@@ -86,6 +86,14 @@ __device__ __forceinline__ float ex2_approx(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// sigmoid / tanh from ex2.approx / rcp.approx (each ~2^-22 relative): no denormal rescue, no division sequence on the chain
+__device__ __forceinline__ float sigmoid_chain(float x) { return rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * x)); }
+__device__ __forceinline__ float tanh_chain(float x) { return fmaf(-2.0f, rcp_approx(1.0f + ex2_approx(2.8853900817779268f * x)), 1.0f); }
 __device__ __forceinline__ float redux_max(float v) {
     float m;
     asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(m) : "f"(v));
@@ -97,13 +105,12 @@ __device__ __forceinline__ unsigned redux_min(unsigned v) {
     return m;
 }
 
-constexpr int CL_HPAD = 60;                      // h_s: 16 chunks of 56 values, chunk stride 60 floats (conflict-free LDS.128)
 constexpr unsigned CL_XBYTES = CL_Q * 4;         // bytes per exchange phase: 256 fp32 into every CTA
 
 __global__ void __launch_bounds__(CL_THREADS, 1) ar_cluster_kernel(ClParams p) {
     __shared__ __align__(16) float Es[CL_Q * CL_ROWS];        // E'[x][g*8+u] of the own units (24 KB)
-    __shared__ __align__(16) float h_s[16 * CL_HPAD];         // h_t gathered from the grid
-    __shared__ __align__(16) float r_s[CL_FR];
+    __shared__ __align__(16) float h_s[CL_H];                 // h_t gathered from the grid
+    __shared__ __align__(16) float rpart[2 * CL_FR];         // fc1 row sums over the two column halves
     __shared__ __align__(16) float hhpart[CL_MW * CL_ROWS];
     __shared__ __align__(16) float inboxf[2 * CL_S * CL_FR];  // [par][source rank][own logit]: fc2 column-partials
     __shared__ __align__(16) float lgf[2 * CL_Q];             // [par][class]: all 256 logits
@@ -145,59 +152,70 @@ __global__ void __launch_bounds__(CL_THREADS, 1) ar_cluster_kernel(ClParams p) {
     } while (0)
 
     // ---- per-thread weights shared by all 8 warps
-    // fc1: warp w, half h = lane / 16 -> row 2w + h of this CTA's 16 rows; j = lane % 16 -> columns [56 j, 56 j + 56)
-    const int frow = 2 * warp + (lane >> 4), fj = lane & 15;
-    float w1[56];
-    {
-        const float4* row = reinterpret_cast<const float4*>(p.fc1_w + static_cast<int64_t>(rank * CL_FR + frow) * CL_H + 56 * fj);
+    // fc1: warp w -> column half w / 4 (448 columns) and rows 4 (w % 4) .. +3 of this CTA's 16; lane -> 14 of those columns, all
+    // four rows.  Shared memory moves 128 B/clk and an LDS.128 costs four wavefronts per warp whatever it broadcasts, so fc1 is
+    // bound by how often h_t is re-read: every loaded value feeds four rows here (7 LDS.64 per thread = 112 wavefronts per CTA;
+    // the row-per-lane-group layouts needed 448).
+    const int fhalf = warp >> 2, frg = warp & 3;
+    float w1[4][14];
 #pragma unroll
-        for (int k = 0; k < 14; ++k) {
-            const float4 v = __ldg(row + k);
-            w1[4 * k] = v.x; w1[4 * k + 1] = v.y; w1[4 * k + 2] = v.z; w1[4 * k + 3] = v.w;
+    for (int i = 0; i < 4; ++i) {
+        const float2* row = reinterpret_cast<const float2*>(p.fc1_w + static_cast<int64_t>(rank * CL_FR + 4 * frg + i) * CL_H + 448 * fhalf + 14 * lane);
+#pragma unroll
+        for (int k = 0; k < 7; ++k) {
+            const float2 v = __ldg(row + k);
+            w1[i][2 * k] = v.x; w1[i][2 * k + 1] = v.y;
         }
     }
-    const float b1 = __ldg(p.fc1_b + rank * CL_FR + frow);
-    // fc2 column-partial of class `tid` over the 16 own r values
-    float w2[CL_FR];
-    {
-        const float4* row = reinterpret_cast<const float4*>(p.fc2_w + static_cast<int64_t>(tid) * CL_FC + rank * CL_FR);
+    // fc2 column-partials: thread = (output group og = tid / 4 -> classes 4 og .. 4 og + 3, column group cg = tid % 4 -> own r
+    // values 4 cg .. 4 cg + 3); the four column groups meet by shuffles and lane cg == 0 sends ONE 16-byte st.async (a DSMEM
+    // store costs its issue slot per thread, not per byte: 64 operations per CTA instead of 256).
+    const int og = tid >> 2, cg4 = tid & 3;
+    float w2[4][4];
 #pragma unroll
-        for (int k = 0; k < CL_FR / 4; ++k) {
-            const float4 v = __ldg(row + k);
-            w2[4 * k] = v.x; w2[4 * k + 1] = v.y; w2[4 * k + 2] = v.z; w2[4 * k + 3] = v.w;
-        }
+    for (int i = 0; i < 4; ++i) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(p.fc2_w + static_cast<int64_t>(4 * og + i) * CL_FC + rank * CL_FR + 4 * cg4));
+        w2[i][0] = v.x; w2[i][1] = v.y; w2[i][2] = v.z; w2[i][3] = v.w;
     }
-    const unsigned rs_dst = cl_mapa(inbox_a + (rank * CL_FR + (tid & 15)) * 4, static_cast<unsigned>(tid >> 4));
-    const unsigned rs_mbar = cl_mapa(mbar_a, static_cast<unsigned>(tid >> 4));
+    const unsigned rs_dst = cl_mapa(inbox_a + (rank * CL_FR + ((4 * og) & 15)) * 4, static_cast<unsigned>(og >> 2));
+    const unsigned rs_mbar = cl_mapa(mbar_a, static_cast<unsigned>(og >> 2));
+    const float4 b1v = __ldg(reinterpret_cast<const float4*>(p.fc1_b + rank * CL_FR) + cg4);   // biases of the r values fc2 reads
     bool dead = false;
 
-    // relu(fc1 h_t) rows of this CTA -> r_s (all 8 warps; h_t is in h_s)
+    // fc1 h_t: half-row sums of this CTA's 16 rows -> rpart[half][row] (all 8 warps; h_t is in h_s)
     auto fc1_rows = [&]() {
-        const float4* hp = reinterpret_cast<const float4*>(&h_s[CL_HPAD * fj]);
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        const float2* hp = reinterpret_cast<const float2*>(&h_s[448 * fhalf + 14 * lane]);
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int k = 0; k < 14; ++k) {
-            const float4 v = hp[k];
-            a0 = fmaf(w1[4 * k], v.x, a0); a1 = fmaf(w1[4 * k + 1], v.y, a1);
-            a2 = fmaf(w1[4 * k + 2], v.z, a2); a3 = fmaf(w1[4 * k + 3], v.w, a3);
+        for (int k = 0; k < 7; ++k) {
+            const float2 v = hp[k];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[i] = fmaf(w1[i][2 * k + 1], v.y, fmaf(w1[i][2 * k], v.x, acc[i]));
         }
-        float s = (a0 + a1) + (a2 + a3);
-        s += __shfl_xor_sync(0xffffffffu, s, 1);
-        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        // 4 row sums over 32 lanes: two transposing rounds (4 -> 2 -> 1 value per lane), then the 8 lanes of a row
+        const bool b4 = lane & 16, b3 = lane & 8;
+        const float k0 = (b4 ? acc[2] : acc[0]) + __shfl_xor_sync(0xffffffffu, b4 ? acc[0] : acc[2], 16);
+        const float k1 = (b4 ? acc[3] : acc[1]) + __shfl_xor_sync(0xffffffffu, b4 ? acc[1] : acc[3], 16);
+        float s = (b3 ? k1 : k0) + __shfl_xor_sync(0xffffffffu, b3 ? k0 : k1, 8);
+        const float t1 = __shfl_xor_sync(0xffffffffu, s, 1), t2 = __shfl_xor_sync(0xffffffffu, s, 2), t3 = __shfl_xor_sync(0xffffffffu, s, 3);
+        s = (s + t1) + (t2 + t3);
         s += __shfl_xor_sync(0xffffffffu, s, 4);
-        s += __shfl_xor_sync(0xffffffffu, s, 8);
-        if (fj == 0) r_s[frow] = fmaxf(s + b1, 0.f);
+        if ((lane & 7) == 0) rpart[fhalf * CL_FR + 4 * frg + (b4 ? 2 : 0) + (b3 ? 1 : 0)] = s;
     };
     // fc2 column-partial of class tid over the own r values -> the owning rank's inbox
     auto fc2_partial_send = [&](int par) {
-        float s0 = 0.f, s1 = 0.f;
+        const float4 p0 = *reinterpret_cast<const float4*>(&rpart[4 * cg4]), p1 = *reinterpret_cast<const float4*>(&rpart[CL_FR + 4 * cg4]);
+        float4 rv;                                   // relu(fc1 h + b) of the own rows 4 cg4 .. +3
+        rv.x = fmaxf((p0.x + p1.x) + b1v.x, 0.f); rv.y = fmaxf((p0.y + p1.y) + b1v.y, 0.f);
+        rv.z = fmaxf((p0.z + p1.z) + b1v.z, 0.f); rv.w = fmaxf((p0.w + p1.w) + b1v.w, 0.f);
+        float s[4];
 #pragma unroll
-        for (int k = 0; k < CL_FR / 4; ++k) {
-            const float4 rv = *reinterpret_cast<const float4*>(&r_s[4 * k]);
-            s0 = fmaf(w2[4 * k], rv.x, s0); s1 = fmaf(w2[4 * k + 1], rv.y, s1);
-            s0 = fmaf(w2[4 * k + 2], rv.z, s0); s1 = fmaf(w2[4 * k + 3], rv.w, s1);
-        }
-        st_async_f32(rs_dst + par * CL_XBYTES, s0 + s1, rs_mbar + 8 * par);
+        for (int i = 0; i < 4; ++i) s[i] = fmaf(w2[i][3], rv.w, fmaf(w2[i][2], rv.z, fmaf(w2[i][1], rv.y, w2[i][0] * rv.x)));
+#pragma unroll
+        for (int i = 0; i < 4; ++i) s[i] += __shfl_xor_sync(0xffffffffu, s[i], 1);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) s[i] += __shfl_xor_sync(0xffffffffu, s[i], 2);
+        if (cg4 == 0) st_async_v4(rs_dst + par * CL_XBYTES, s[0], s[1], s[2], s[3], rs_mbar + 8 * par);
     };
 
     if (warp < CL_MW) {
@@ -213,7 +231,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) ar_cluster_kernel(ClParams p) {
         }
         const int w0 = 128 * q + 4 * lane;                       // first of this lane's four h words
         const ll_word* hsrc = p.hbuf + w0;
-        float* hdst = &h_s[w0 + 4 * (w0 / 56)];
+        float* hdst = &h_s[w0];
         for (int t = 0; t < L; ++t) {
             const uint32_t tag = static_cast<uint32_t>(t) + 1u;
             const int par = t & 1;
@@ -229,8 +247,10 @@ __global__ void __launch_bounds__(CL_THREADS, 1) ar_cluster_kernel(ClParams p) {
                 const long long t0 = clock64();
                 unsigned n = 0;
                 ll_word a0, a1, b0, b1w;
+                unsigned rounds = 0;
                 if (!pipelined_poll) {
                     for (;;) {
+                        ++rounds;
                         ll_load2(src, a0, a1);
                         ll_load2(src + 2, b0, b1w);
                         const bool ok = ll_tag(a0) == tag && ll_tag(a1) == tag && ll_tag(b0) == tag && ll_tag(b1w) == tag;
@@ -256,12 +276,14 @@ __global__ void __launch_bounds__(CL_THREADS, 1) ar_cluster_kernel(ClParams p) {
                 }
                 hv[0] = ll_val(a0); hv[1] = ll_val(a1); hv[2] = ll_val(b0); hv[3] = ll_val(b1w);
                 *reinterpret_cast<float4*>(hdst) = make_float4(hv[0], hv[1], hv[2], hv[3]);
+                CL_TRACE(16 + q, t)
+                if (tracing && t >= p.trace_t0 && t < p.trace_t0 + p.trace_n) p.trace[(t - p.trace_t0) * CL_TRACE_STRIDE + 24 + q] = rounds;
             }
             if (warp == 0) { CL_TRACE(9, t) }
             bar_sync(1, CL_THREADS);                 // all 896 values of h_t are in h_s
             if (!dead) fc1_rows();
             if (warp == 0) { CL_TRACE(10, t) }
-            bar_sync(3, CL_THREADS);                 // r_s holds the 16 own relu(fc1) values
+            bar_sync(3, CL_THREADS);                 // rpart holds the fc1 half-row sums
             if (!dead) fc2_partial_send(par);
             if (!dead) {
                 // ---- off the critical path: W_hh rows of the own units x h_t (this warp's 128 columns)
@@ -314,6 +336,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) ar_cluster_kernel(ClParams p) {
         }
         const unsigned lg_src = lg_a + 8 * lane * 4;
         float hown = 0.f, hb_r = bh_r, hb_z = bh_z, hb_n = bh_n;      // W_hh h_{-1} = 0
+        float gh_r = 0.f, gh_z = 0.f;                                   // G_r + hb_r, G_z + hb_z: everything but E'[x]
         int x = CL_X_INIT, x_out = -1;
         int x_next = (teacher && L > 0) ? static_cast<int>(__ldg(p.x_in)) & (CL_Q - 1) : 0;
         int frame = 0, frame_left = 0;
@@ -336,15 +359,16 @@ __global__ void __launch_bounds__(CL_THREADS, 1) ar_cluster_kernel(ClParams p) {
                 }
             }
             --frame_left;
+            if (t == 0) { gh_r = __fadd_rn(g_r, hb_r); gh_z = __fadd_rn(g_z, hb_z); }
             CL_TRACE(0, t)
             float u_t = 0.f;
             if (!dead) {
                 // ---- GRU gates of step t for the own units (lanes 0..7; the other lanes mirror them harmlessly)
                 if (teacher) x = x_next;
                 const float* e = &Es[x * CL_ROWS + (lane & 7)];
-                const float r = sigmoid_fast(__fadd_rn(__fadd_rn(e[0], g_r), hb_r));
-                const float z = sigmoid_fast(__fadd_rn(__fadd_rn(e[CL_U], g_z), hb_z));
-                const float n = tanh_fast(__fmaf_rn(r, hb_n, __fadd_rn(e[2 * CL_U], g_n)));
+                const float r = sigmoid_chain(__fadd_rn(e[0], gh_r));
+                const float z = sigmoid_chain(__fadd_rn(e[CL_U], gh_z));
+                const float n = tanh_chain(__fmaf_rn(r, hb_n, __fadd_rn(e[2 * CL_U], g_n)));
                 hown = __fmaf_rn(z, __fsub_rn(hown, n), n);            // (1-z) n + z h
                 if (lane < CL_U) ll_store(p.hbuf + par * CL_H + cta * CL_U + lane, hown, tag);
             }
@@ -364,7 +388,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) ar_cluster_kernel(ClParams p) {
             }
             bar_sync(1, CL_THREADS);                 // all 896 values of h_t are in h_s
             if (!dead) fc1_rows();
-            bar_sync(3, CL_THREADS);                 // r_s complete
+            bar_sync(3, CL_THREADS);                 // rpart complete
             CL_TRACE(2, t)
             float lo[4] = {0.f, 0.f, 0.f, 0.f};
             if (!dead) {
@@ -408,6 +432,10 @@ __global__ void __launch_bounds__(CL_THREADS, 1) ar_cluster_kernel(ClParams p) {
                 hb_r = __fadd_rn(__shfl_sync(0xffffffffu, s, lane & 7), bh_r);
                 hb_z = __fadd_rn(__shfl_sync(0xffffffffu, s, 8 + (lane & 7)), bh_z);
                 hb_n = __fadd_rn(__shfl_sync(0xffffffffu, s, 16 + (lane & 7)), bh_n);
+                // the next step's conditioning frame is already known here
+                const bool nf = (frame_left == 0);
+                gh_r = __fadd_rn(nf ? gn_r : g_r, hb_r);
+                gh_z = __fadd_rn(nf ? gn_z : g_z, hb_z);
             }
             if (!dead && !teacher) {
                 // ---- all-gather of the logits, then softmax + inverse-CDF sample: lane l holds classes 8l..8l+7
@@ -465,7 +493,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) ar_cluster_kernel(ClParams p) {
 }
 
 // ------------------------------------------------------------------------------------------------ host
-static int g_cl_poll_delay = 400, g_cl_poll_mode = 0;
+static int g_cl_poll_delay = 200, g_cl_poll_mode = 0;
 int g_cl_enable = 1;
 
 // 1 = the device can hold the 7 x 16 cluster grid at one CTA per SM, 0 = it cannot (fall back to ar_kernel), cached per device
