@@ -109,12 +109,24 @@ def cpu_generate_sample(n_steps: int, warm: int = 50):
 
 
 def reference_arm(args):
+    """The reference's own CPU path for the headline workload: the restated rnnms generate loop (oracle/vocoder.py) in PyTorch
+    on the host cores.  torchrun exports OMP_NUM_THREADS=1, so the thread count is set EXPLICITLY: the loop is timed with
+    1, 16 and all host threads (small GEMVs do not scale with threads) and the best is reported with its count."""
     import torch
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     n_ar = 800
-    cores = torch.get_num_threads()
+    ncpu = os.cpu_count() or 1
+    counts = sorted({1, min(16, ncpu), ncpu})
+    per_threads = {}
+    for c in counts:
+        torch.set_num_threads(c)
+        cpu_generate_sample(200, warm=20)
+        sps, _ = cpu_generate_sample(n_ar, warm=20)
+        per_threads[c] = sps
+    best = max(per_threads, key=per_threads.get)
+    torch.set_num_threads(best)
     for _ in range(max(args.warmup, 1)):
         cpu_generate_sample(200, warm=20)
     t = []
@@ -123,14 +135,17 @@ def reference_arm(args):
         t.append(dt)
     total = sum(t)
     value = n_ar * args.steps / total
-    sample = f"{n_ar} AR steps of the B=1 generate loop per step (prenet included), restated rnnms loop in PyTorch CPU"
+    sample = (f"{n_ar} AR steps of the B=1 generate loop per step (the 100-step prenet is paid per {n_ar} steps here instead of "
+              "per 16000: a small bias AGAINST the reference), restated rnnms loop in PyTorch CPU")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "vocoder_generate_b1_1s (BASELINE configs[2])", "sample": sample},
         "x_realtime": value / SR,
-        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": best, "kind": "port", "sample": sample,
+                         "samples_per_s_by_threads": {str(k): v for k, v in per_threads.items()}, "host_cpus": ncpu,
+                         "note": "rank 0 only: one host process, not scaled by n_gpus"},
         "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -138,7 +153,7 @@ def reference_arm(args):
 
 
 
-def run_other_workload(args, world, rank, local, dev, timed, peaks, lib):
+def run_other_workload(args, world, rank, local, dev, timed, peaks, lib, workload=None, steps=None, warmup=None):
     """BASELINE configs[3] (batched encode, 4096 x 3 s, STRONG scaling over the ranks) and configs[4] (end-to-end
     convert: encode + generate, 64 x 3 s per GPU, weak scaling).  One JSON line, same contract as the headline."""
     import torch
@@ -153,6 +168,14 @@ def run_other_workload(args, world, rank, local, dev, timed, peaks, lib):
     enc = Encoder(ConfEncoder(channels=768))
     enc.load_state_dict(sd)
     enc = enc.to(dev).eval()
+    import types
+    args = types.SimpleNamespace(**vars(args))
+    if workload is not None:
+        args.workload = workload
+    if steps is not None:
+        args.steps = steps
+    if warmup is not None:
+        args.warmup = warmup
     sampler = ClockSampler(local)
     n0 = lib.vqcpc_launch_count()
     if args.workload == "encode_4096":
@@ -183,6 +206,16 @@ def run_other_workload(args, world, rank, local, dev, timed, peaks, lib):
         t_ms = timed(step_resident, args.steps, args.warmup)
         launches = (lib.vqcpc_launch_count() - n0) * args.steps // (args.steps + args.warmup)
         t_e2e = timed(step_e2e, args.steps, args.warmup)
+        t_c = None
+        if world > 1:
+            # the same pass with the context vectors c gathered as well (629 MB into rank 0 -- the one collective
+            # that could limit this path)
+            def step_gather_c():
+                with torch.no_grad():
+                    _, c, idx = enc.encode(mel_d)
+                gather_idx(idx)
+                vdist.gather_utterances(c, n_total, dst=0)
+            t_c = timed(step_gather_c, args.steps, 1)
         clocks = sampler.stop() if rank == 0 else {}
         frames = n_total * 150
         value, e2e_v = frames * args.steps / (t_ms * 1e-3), frames * args.steps / (t_e2e * 1e-3)
@@ -196,7 +229,9 @@ def run_other_workload(args, world, rank, local, dev, timed, peaks, lib):
                 "e2e": {"value": e2e_v, "unit": "frames/s", "h2d_bytes_per_step": int(mel_h.numel() * 4 * world),
                         "d2h_bytes_per_step": int(idx_h.numel() * 8 * world), "ms_per_step": t_e2e / args.steps},
                 "gpu_launches": int(launches), "clocks": clocks,
-                "roofline": {"kernel": "gemm_tc_kernel", "bound": "tensor", "unit": "TFLOP/s",
+                "with_gather_of_c": None if t_c is None else {"ms_per_step": t_c / args.steps, "value": frames * args.steps / (t_c * 1e-3),
+                                                               "unit": "frames/s", "gathered_bytes": int(n_total * 150 * 256 * 4)},
+                "roofline": {"kernel": "gemm_tc_ln_kernel", "bound": "tensor", "unit": "TFLOP/s",
                              "achieved": flops * args.steps / (t_ms * 1e-3) / 1e12 / world, "peak": peaks["bf16_tflops_sustained"],
                              "frac": flops * args.steps / (t_ms * 1e-3) / 1e12 / world / peaks["bf16_tflops_sustained"],
                              "traffic": None, "note": "per GPU, whole encode step (GEMMs + LN + VQ + LSTM) against the sustained "
@@ -256,8 +291,9 @@ def run_other_workload(args, world, rank, local, dev, timed, peaks, lib):
             "e2e": {"value": e2e_v, "unit": "samples/s", "x_realtime": e2e_v / SR, "h2d_bytes_per_step": int(mel_h.numel() * 4 + B * 8),
                     "d2h_bytes_per_step": int(B * L * 4), "ms_per_step": t_e2e / steps},
             "gpu_launches": int(launches), "clocks": clocks,
-            "roofline": {"kernel": "ar_kernel", "bound": "hbm", "achieved": None, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": None, "traffic": None, "note": "latency-bound persistent kernel, see the headline workload"}}
+            "roofline": {"kernel": "ar_batch_kernel", "bound": "latency", "achieved": 1e3 * t_ms / steps / L, "unit": "us/step",
+                         "peak": None, "frac": None, "traffic": None,
+                         "note": "batched sample loop (64 utterances advance per step), latency-bound; see the headline workload"}}
     if rank == 0 and world == 1 and not args.no_cpu:
         # reference CPU: oracle encode of the 64 utterances + restated generate at B=64 truncated to 200 steps, extrapolated
         codes, spk, u = fixtures.vocoder_inputs(B, 150, seed=0, n_steps=200)
@@ -396,7 +432,7 @@ def main():
     value = samples_per_step * args.steps / (t_ms * 1e-3)
     e2e_value = samples_per_step * args.steps / (t_e2e_ms * 1e-3)
 
-    # ---- dominant kernel alone (ar_kernel): CUDA events around the C-ABI generate call, conditioning excluded
+    # ---- dominant kernel alone (ar_cluster_kernel): CUDA events around the C-ABI generate call, conditioning excluded
     import ctypes as C
     w, _keep = voc.pack_weights()
     with torch.no_grad():
@@ -411,25 +447,32 @@ def main():
                                               _lib.ptr(wav), None, None, _lib.current_stream_ptr()), "generate")
 
     t_ar_ms = timed(ar_only, args.steps, 3) / args.steps / B          # per launch (one utterance per launch)
-    # algorithmic HBM bytes of one launch: weights read once + E' + G + uniforms in + wav out
-    ar_bytes = 4 * (2688 * 896 + 256 * 896 + 256 * 256 + 2688 + 512 + 256 * 2688 + 2 * Tc * 2688 + 2 * L + 256)
-    roofline = {"kernel": "ar_kernel", "bound": "hbm", "achieved": ar_bytes / (t_ar_ms * 1e-3) / 1e9,
-                "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "traffic": 14.87e6 if (B == 1 and L == 16000) else None,   # ncu dram read+write per launch, profiles/r01_ncu_ar_summary.txt
-                "note": "latency-bound persistent kernel: see latency.us_per_step vs the exchange floor (DESIGN.md)",
-                "peak_source": peaks["source"]}
-    roofline["frac"] = roofline["achieved"] / roofline["peak"]
-    # latency floor of the role-warp design: three bare 128-way LL exchanges per step, measured live
+    # The sample loop is latency-bound (its algorithmic HBM traffic is 14.8 MB per 16 000 steps).  SURVEY 8(d) names its
+    # bound: per-step floor = t_smem + ONE empty grid-scope exchange, where t_smem = resident weight bytes touched per step
+    # (10.81 MB fp32) / aggregate on-chip bandwidth (148 SMs x 128 B/clk x SM clock) and the exchange is measured live here
+    # (vqcpc_debug_exchange_floor: 128 CTAs publish and poll, no compute).
     fl_ws = torch.empty(1 << 17, dtype=torch.uint8, device=dev)
     mean_cyc = C.c_double(0.0)
     _lib.check(lib.vqcpc_debug_exchange_floor(_lib.ptr(fl_ws), fl_ws.numel(), 2000, C.byref(mean_cyc),
                                               _lib.current_stream_ptr()), "exchange floor")
     sm_mhz = float(clocks.get("sm_mhz") or 1965.0)      # median SM clock sampled during the timed region
-    floor_us = 3.0 * mean_cyc.value / sm_mhz
-    latency = {"us_per_step": 1e3 * t_ar_ms / L, "x_realtime_kernel_only": (L / (t_ar_ms * 1e-3)) / SR,
-               "target_us_per_step": 1.25, "exchange_cycles": mean_cyc.value, "sm_mhz_used": sm_mhz,
-               "floor_us_per_step": floor_us, "floor_frac": floor_us / (1e3 * t_ar_ms / L),
-               "note": "floor = 3 bare 128-way LL exchanges per step (h, relu(fc1 h), logits), no compute"}
+    us_per_step = 1e3 * t_ar_ms / L
+    t_smem_us = 4.0 * (2688 * 896 + 256 * 896 + 256 * 256) / (148 * 128 * sm_mhz)      # bytes / (bytes per us)
+    t_exch_us = mean_cyc.value / sm_mhz
+    floor_us = t_smem_us + t_exch_us
+    ar_bytes = 4 * (2688 * 896 + 256 * 896 + 256 * 256 + 2688 + 512 + 256 * 2688 + 2 * Tc * 2688 + 2 * L + 256)
+    roofline = {"kernel": "ar_cluster_kernel", "bound": "latency", "unit": "us/step", "achieved": us_per_step, "peak": floor_us,
+                "frac": floor_us / us_per_step,
+                "floor": {"t_smem_us": t_smem_us, "one_empty_grid_exchange_us": t_exch_us, "exchange_cycles": mean_cyc.value,
+                          "sm_mhz_used": sm_mhz},
+                "traffic": None, "algorithmic_hbm_bytes_per_launch": ar_bytes,
+                "hbm_gbs_if_it_were_bandwidth": ar_bytes / (t_ar_ms * 1e-3) / 1e9, "hbm_peak_gbs": peaks["hbm_gbs"],
+                "peak_source": peaks["source"],
+                "note": "latency-bound persistent kernel (lower is better): achieved = measured us per autoregressive step of the "
+                        "dominant kernel alone, peak = SURVEY 8(d)'s floor (t_smem + one measured empty grid exchange), "
+                        "frac = floor / achieved.  One grid-scope exchange per step is what the cluster kernel has "
+                        "(DESIGN.md 4.1); the remaining gap is two DSMEM hops + the serial gate/softmax/sample chain."}
+    latency = {"us_per_step": us_per_step, "x_realtime_kernel_only": (L / (t_ar_ms * 1e-3)) / SR, "target_us_per_step": 1.25}
 
     line = {
         "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
@@ -444,6 +487,16 @@ def main():
                 "ms_per_step": t_e2e_ms / args.steps},
         "gpu_launches": int(launches), "roofline": roofline, "latency": latency, "clocks": clocks,
     }
+
+    # ---- N > 1: BASELINE configs[3] (encode 4096 x 3 s, STRONG scaling, indices gathered; and again with c gathered) and
+    # configs[4] (convert 64 x 3 s per GPU, weak scaling) ride along, so that the driver's scaling run records them
+    if not args.no_extra and world > 1:
+        extra = {}
+        for wl, st, wu in (("encode_4096", 5, 3), ("convert_b64", 2, 1)):
+            sub = run_other_workload(args, world, rank, local, dev, timed, peaks, lib, workload=wl, steps=st, warmup=wu)
+            extra[wl] = {k: sub[k] for k in ("value", "unit", "ms_per_step", "scaling", "steps", "e2e", "gpu_launches", "config",
+                                              "with_gather_of_c", "x_realtime") if k in sub}
+        line["extra"] = extra
 
     # ---- the other BASELINE configs, measured in the same run on rank 0's GPU (N = 1 only)
     if not args.no_extra and world == 1:
@@ -470,12 +523,15 @@ def main():
             xf, cbf = xd.reshape(-1, 64).contiguous(), vq.embedding.contiguous()
             qo, io = torch.empty_like(xf), torch.empty(xf.shape[0], dtype=torch.int64, device=dev)
 
+            vws_bytes = lib.vqcpc_vq_workspace_bytes()
+            vws = torch.empty(vws_bytes, dtype=torch.uint8, device=dev)
+
             def vq_launches():
                 for _ in range(20):
                     _lib.check(lib.vqcpc_vq_lookup(_lib.ptr(xf), _lib.ptr(cbf), xf.shape[0], 512, 64, _lib.ptr(qo), _lib.ptr(io),
-                                                   _lib.current_stream_ptr()), "vq_lookup")
+                                                   _lib.ptr(vws), vws_bytes, _lib.current_stream_ptr()), "vq_lookup")
             kms = timed(vq_launches, 1, 1) / 20
-            _lib.check(lib.vqcpc_vq_check_status(_lib.current_stream_ptr()), "vq_lookup")
+            _lib.check(lib.vqcpc_check_status(_lib.ptr(vws), _lib.current_stream_ptr()), "vq_lookup")
             extra[f"vq_lookup_1M_{kind}"] = {"frames_per_s": 1e6 / (ms * 1e-3), "ms": ms, "kernel_ms": kms,
                                             "roofline": {"kernel": "vq_tc_kernel", "bound": "hbm",
                                                          "achieved": 520e6 / (kms * 1e-3) / 1e9,

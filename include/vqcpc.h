@@ -28,6 +28,8 @@ extern "C" {
 #define VQCPC_ERR_CUDA 2     /* a CUDA runtime call failed */
 #define VQCPC_ERR_DEVICE 3   /* device is not sm_100 / cannot co-schedule the persistent grid */
 #define VQCPC_ERR_TIMEOUT 4  /* a persistent kernel's exchange timed out (see vqcpc_check_status) */
+#define VQCPC_ERR_INDEX 5    /* a code / speaker index was out of range (nn.Embedding would raise IndexError); the gather
+                              * clamps it and vqcpc_check_status reports it -- no host synchronisation before the launch */
 
 const char* vqcpc_last_error(void);
 int vqcpc_abi_version(void);
@@ -115,11 +117,13 @@ int vqcpc_layernorm_relu_f32(float* x, const float* w, const float* b, int64_t r
  * x (n_frames, 64) fp32 -> out_q (n_frames, 64) = codebook[idx], out_idx (n_frames,) int64 = first argmin of
  * |e|^2 - 2 x.e (fp32; the |x|^2 term of model.py:107-110 is argmin-invariant and is not added). */
 int vqcpc_vq_lookup(const float* x, const float* codebook, int64_t n_frames, int32_t n_codes, int32_t dim,
-                    float* out_q, int64_t* out_idx, void* stream);
-/* For n_frames >= 8192 the search runs on the tensor cores (tcgen05 coarse pass over bf16 hi/lo planes, exact fp32
- * re-decision of every frame whose best two candidates are within the coarse error bound), with identical results.
- * vqcpc_vq_check_status synchronises `stream` and returns VQCPC_ERR_TIMEOUT if that pipeline ever timed out. */
-int vqcpc_vq_check_status(void* stream);
+                    float* out_q, int64_t* out_idx, void* workspace, size_t workspace_bytes, void* stream);
+/* workspace == NULL: the exact fp32 SIMT search.  With a workspace of vqcpc_vq_workspace_bytes() bytes (caller-owned, one per
+ * stream in flight -- the library keeps no hidden state) and n_frames >= 8192 the search runs on the tensor cores: tcgen05
+ * coarse pass over bf16 hi/lo planes, and an exact fp32 rescan of all 512 codes for every frame whose best two coarse
+ * scores are within the coarse error bound (any other frame provably has its coarse winner as exact winner), so results are
+ * identical.  vqcpc_check_status(workspace, stream) returns VQCPC_ERR_TIMEOUT if that pipeline timed out. */
+size_t vqcpc_vq_workspace_bytes(void);
 
 /* ------------------------------------------------------------------ Encoder.encode -- model.py:59-70
  * mel (B, 80, T) fp32 -> out_z (B, T', 64) quantised, out_c (B, T', 256), out_idx (B, T') int64,

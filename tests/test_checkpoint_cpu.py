@@ -56,3 +56,24 @@ def test_bare_state_dicts_and_errors():
         assert "epoch" in str(e)
     else:
         raise AssertionError("expected KeyError")
+
+
+class _HParams:            # a non-tensor object a Lightning checkpoint may pickle next to the weights
+    lr = 1e-3
+
+
+def test_files_load_with_the_tensor_only_unpickler_by_default(tmp_path):
+    """Downloaded release checkpoints are untrusted files: the default load must not run pickled code; a checkpoint
+    that really carries arbitrary objects needs the explicit trust_pickle=True."""
+    import pytest
+    vsd = ovoc.init_state_dict(seed=2)
+    safe = tmp_path / "vocoder.pt"
+    torch.save({"vocoder": vsd, "epoch": 1}, safe)
+    voc = checkpoint.load_vocoder(safe)
+    assert torch.equal(voc.state_dict()["rnnms.ar.fc1.bias"], vsd["rnnms.ar.fc1.bias"])
+    unsafe = tmp_path / "lightning.ckpt"
+    torch.save({"state_dict": {"model." + k: v for k, v in vsd.items()}, "hyper_parameters": _HParams()}, unsafe)
+    with pytest.raises(RuntimeError, match="trust_pickle"):
+        checkpoint.load_vocoder(unsafe)
+    voc2 = checkpoint.load_vocoder(unsafe, trust_pickle=True)
+    assert torch.equal(voc2.state_dict()["rnnms.ar.fc1.bias"], vsd["rnnms.ar.fc1.bias"])

@@ -675,3 +675,184 @@ def test_vocoder_argument_errors():
         voc.generate(z, s, uniforms=torch.zeros(1, 5, device=dev()))
     with pytest.raises(ValueError):
         voc.forward(torch.zeros(1, 700, dtype=torch.int64, device=dev()), z, s)
+
+
+# ------------------------------------------------------------------------------------------ round-2 parity hardening
+def _cdf_consistent(ref_logits, x, u, tol=5e-5):
+    cdf = ovoc.cdf_bounds(ref_logits)
+    hi = torch.gather(cdf, 2, x[..., None])[..., 0]
+    lo = torch.where(x > 0, torch.gather(cdf, 2, (x - 1).clamp(min=0)[..., None])[..., 0], torch.zeros_like(hi))
+    return (u.double() >= lo - tol) & (u.double() <= hi + tol)
+
+
+def test_vocoder_full_second_replayed_through_oracle():
+    """BASELINE configs[2] at FULL size (B = 1, 16 000 steps): the GPU's own samples are replayed through the oracle in
+    teacher-forced mode -- every one of the 16 000 logit vectors must match and every sample must be consistent with its
+    injected uniform under the oracle's CDF.  (Free-running equality would only test the first divergence.)"""
+    voc, sd = make_vocoder()
+    codes, spk, u = fixtures.vocoder_inputs(1, 50, seed=0)
+    wav, x, logits = voc.generate(codes.to(dev()), spk.to(dev()), uniforms=u.to(dev()), return_mulaw=True, return_logits=True)
+    wav, x, logits = wav.cpu(), x.cpu(), logits.cpu()
+    assert x.shape == (1, 16000)
+    x_in = torch.cat([torch.full((1, 1), 128, dtype=torch.int64), x[:, :-1]], dim=1)
+    ref = ovoc.forward_teacher_forced(sd, x_in, codes, spk)
+    err = float((logits - ref).abs().max())
+    print(f"[generate 16000 steps, replayed] max |dlogit| = {err:.3e}")
+    assert err < ATOL_LOGITS, err
+    ok = _cdf_consistent(ref, x, u)
+    assert bool(ok.all()), f"{int((~ok).sum())} of 16000 samples inconsistent with their uniform"
+    lut = torch.from_numpy(mulaw.mulaw_decode_lut(8))
+    assert torch.equal(wav, lut[x])
+    # the teacher-forced entry point at full length agrees with the logits the sample loop produced
+    tf = voc.forward(x_in.to(dev()), codes.to(dev()), spk.to(dev())).cpu()
+    assert float((tf - ref).abs().max()) < ATOL_LOGITS
+
+
+def test_vocoder_round1_kernel_teacher_forced_stress_and_agreement():
+    """The 128-CTA kernel (fallback when 7 clusters of 16 CTAs cannot be co-scheduled): a long teacher-forced run with four
+    interleaved utterances must neither time out (the r exchange was WAR-safe only by timing in this mode) nor
+    disagree with the cluster kernel beyond summation-order noise."""
+    voc, sd = make_vocoder()
+    B, Tc = 4, 320                                   # L = 102 400 steps
+    L = 320 * Tc
+    codes, spk, _ = fixtures.vocoder_inputs(B, Tc, seed=41)
+    x = torch.randint(0, 256, (B, L), generator=torch.Generator().manual_seed(42))
+    cd, sdv, xd = codes.to(dev()), spk.to(dev()), x.to(dev())
+    lib = _lib.lib()
+    try:
+        _lib.check(lib.vqcpc_debug_set_ar_cluster(0, 200, 0), "debug")          # round-1 kernel, NB = 4 interleaved
+        a = voc.forward(xd, cd, sdv)
+        b = voc.forward(xd, cd, sdv)
+    finally:
+        _lib.check(lib.vqcpc_debug_set_ar_cluster(1, 200, 0), "debug")
+    assert torch.equal(a, b)
+    c = voc.forward(xd[:, :4000], cd, sdv)                                       # cluster kernel
+    assert float((a[:, :4000] - c).abs().max()) < 1e-5
+    ref = ovoc.forward_teacher_forced(sd, x[:1, :600], codes[:1], spk[:1])
+    assert float((a[:1, :600].cpu() - ref).abs().max()) < ATOL_LOGITS
+
+
+def test_vq_lookup_one_million_frames_against_oracle():
+    """BASELINE configs[1] at full size: 1 M init-like frames (worst case for ties) against the oracle's fp32 argmin and the
+    fp64 truth, in chunks: zero non-near-tie mismatches."""
+    n = 1_000_000
+    x, cb = fixtures.vq_inputs(n, kind="init", seed=1234)
+    q, idx = run_vq(x, cb)
+    idx = idx.reshape(-1)
+    xf = x.reshape(-1, 64)
+    tot = dict(mismatches=0, hard=0)
+    tot64 = dict(mismatches=0, hard=0)
+    for lo in range(0, n, 62_500):
+        xs = xf[lo:lo + 62_500]
+        _, io = oenc.vq_lookup(xs[None], cb)
+        rep = oenc.classify_index_mismatches(xs, cb, idx[lo:lo + 62_500], io.reshape(-1))
+        truth = oenc.vq_scores_exact(xs, cb).argmin(dim=-1)
+        rep64 = oenc.classify_index_mismatches(xs, cb, idx[lo:lo + 62_500], truth)
+        for k in tot:
+            tot[k] += rep[k]
+            tot64[k] += rep64[k]
+    print(f"[vq 1M init-like] vs oracle fp32: {tot}; vs fp64 truth: {tot64}")
+    assert tot["hard"] == 0 and tot64["hard"] == 0
+    assert tot["mismatches"] <= 600 and tot64["mismatches"] <= tot["mismatches"]      # SURVEY 7.2: reference itself ~287 / 1 M off fp64
+    assert torch.equal(q.reshape(-1, 64), cb[idx])
+
+
+def test_vq_duplicated_and_collapsed_codebook_rows():
+    """with three or more codes inside the recheck margin -- duplicated rows, a collapsed codebook -- and negative
+    scores (where the index packed into the low mantissa bits orders backwards) the tensor-core search must still return
+    torch.argmin's first minimum.  Frames flagged by the coarse pass are rescanned exactly over all 512 codes."""
+    g = torch.Generator().manual_seed(77)
+    cb = torch.randn(512, 64, generator=g)
+    dup = [5, 130, 131, 300, 511]
+    cb[dup] = cb[17].clone()                              # six identical rows: 5, 17, 130, 131, 300, 511
+    cb[400:420] = cb[399] + 1e-7 * torch.randn(20, 64, generator=g)       # a collapsed cluster of near-duplicates
+    n = 20000
+    pick = torch.randint(0, 512, (n,), generator=g)
+    x = (cb[pick] * 1.5 + 0.05 * torch.randn(n, 64, generator=g))[None]   # x.e >> |e|^2 / 2: negative scores at the winner
+    q, idx = run_vq(x, cb)
+    idx = idx.reshape(-1)
+    _, io = oenc.vq_lookup(x, cb)
+    rep = oenc.classify_index_mismatches(x, cb, idx, io.reshape(-1))
+    assert rep["hard"] == 0, rep
+    # exact duplicates: the lowest index of the six must win wherever any of them wins
+    hit = torch.isin(io.reshape(-1), torch.tensor(dup + [17]))
+    assert int(hit.sum()) > 100
+    assert bool((idx[hit] == 5).all()) and bool((io.reshape(-1)[hit] == 5).all())
+    # and the exact fp32 SIMT kernel (n < 8192 path) agrees with the tensor-core path frame by frame
+    parts = [run_vq(x[:, lo:lo + 5000], cb)[1].reshape(-1) for lo in range(0, n, 5000)]
+    assert torch.equal(torch.cat(parts), idx)
+
+
+def test_ragged_batches_against_the_oracle_directly():
+    """SURVEY 8f row 2, compared with the ORACLE on the unpadded utterances (not with another CUDA run)."""
+    voc, sd = make_vocoder()
+    lens = [2, 1, 3]
+    B, Tc = len(lens), max(lens)
+    codes, spk, u = fixtures.vocoder_inputs(B, Tc, seed=51)
+    wav, x, logits = voc.generate(codes.to(dev()), spk.to(dev()), uniforms=u.to(dev()), return_mulaw=True, return_logits=True,
+                                  lengths=lens)
+    x, logits = x.cpu(), logits.cpu()
+    for b, n in enumerate(lens):
+        L = 320 * n
+        xb = x[b:b + 1, :L]
+        x_in = torch.cat([torch.full((1, 1), 128, dtype=torch.int64), xb[:, :-1]], dim=1)
+        ref = ovoc.forward_teacher_forced(sd, x_in, codes[b:b + 1, :n], spk[b:b + 1])
+        assert float((logits[b:b + 1, :L] - ref).abs().max()) < ATOL_LOGITS, b
+        assert bool(_cdf_consistent(ref, xb, u[b:b + 1, :L]).all()), b
+    enc, esd = make_encoder(512, True)
+    g = torch.Generator().manual_seed(6)
+    mels = [torch.rand(80, T, generator=g) for T in (120, 57, 200)]
+    out = enc.encode_ragged([m.to(dev()) for m in mels])
+    for m, (z, c, idx) in zip(mels, out):
+        z_o, c_o, idx_o = oenc.encode(esd, m[None])
+        rep = oenc.classify_index_mismatches(oenc.encode(esd, m[None], return_aux=True)[3], esd["codebook.embedding"], idx.cpu(), idx_o)
+        assert rep["hard"] == 0
+        if rep["mismatches"] == 0:
+            assert torch.allclose(z.cpu(), z_o, rtol=RTOL, atol=ATOL_ZPRE) and torch.allclose(c.cpu(), c_o, rtol=RTOL, atol=ATOL_C)
+
+
+def test_checkpoint_containers_run_on_the_gpu_and_match_the_oracle(tmp_path):
+    """each container layout of the reference (train_cpc.py:23-29, convert.py:44, Lightning vocoder.py:41-51)
+    is loaded from a FILE, moved to the GPU and run; results must match the oracle on the same weights."""
+    from vectorquantizedcpc_b200 import checkpoint
+    esd = fixtures.perturb_encoder_state(fixtures.encoder_init_state(512, seed=13))
+    vsd = ovoc.init_state_dict(seed=13)
+    files = {"cpc": tmp_path / "model.ckpt-100.pt", "release": tmp_path / "vocoder.pt", "lightning": tmp_path / "last.ckpt"}
+    torch.save({"encoder": esd, "cpc": {}, "optimizer": {}, "scheduler": {}, "epoch": 100}, files["cpc"])
+    torch.save({"vocoder": vsd, "epoch": 3}, files["release"])
+    torch.save({"state_dict": {**{"model." + k: v for k, v in vsd.items()}, **{"encoder." + k: v for k, v in esd.items()}},
+                "epoch": 1, "global_step": 10}, files["lightning"])
+    mel = fixtures.synthetic_mel(2, 61, seed=8)
+    z_o, c_o, idx_o = oenc.encode(esd, mel)
+    codes, spk, u = fixtures.vocoder_inputs(1, 1, seed=9)
+    xs = torch.randint(0, 256, (1, 200), generator=torch.Generator().manual_seed(10))
+    tf_o = ovoc.forward_teacher_forced(vsd, xs, codes, spk)
+    for name in ("cpc", "lightning"):
+        enc = checkpoint.load_encoder(files[name]).to(dev())
+        z, c, idx = enc.encode(mel.to(dev()))
+        rep = oenc.classify_index_mismatches(oenc.encode(esd, mel, return_aux=True)[3], esd["codebook.embedding"], idx.cpu(), idx_o)
+        assert rep["hard"] == 0, (name, rep)
+        if rep["mismatches"] == 0:
+            assert torch.allclose(z.cpu(), z_o, rtol=RTOL, atol=ATOL_ZPRE) and torch.allclose(c.cpu(), c_o, rtol=RTOL, atol=ATOL_C), name
+    for name in ("release", "lightning"):
+        voc = checkpoint.load_vocoder(files[name]).to(dev())
+        tf = voc.forward(xs.to(dev()), codes.to(dev()), spk.to(dev())).cpu()
+        assert float((tf - tf_o).abs().max()) < ATOL_LOGITS, name
+
+
+def test_lstm_entry_reports_out_of_range_codes():
+    """vqcpc_lstm_forward gathers table[idx] with caller-supplied indices -- they are clamped (memory safety) and an
+    out-of-range value is reported through the workspace status word."""
+    enc, _ = make_encoder(512, False)
+    w, _keep = enc.pack_weights()
+    lib = _lib.lib()
+    B, Tp = 2, 9
+    idx = torch.randint(0, 512, (B, Tp), device=dev())
+    idx[1, 4] = 9999
+    ws_bytes = lib.vqcpc_lstm_workspace_bytes(B, Tp)
+    ws = torch.zeros(ws_bytes, dtype=torch.uint8, device=dev())
+    out = torch.empty(B, Tp, 256, device=dev())
+    _lib.check(lib.vqcpc_lstm_forward(C.byref(w), _lib.ptr(idx), B, Tp, _lib.ptr(ws), ws_bytes, _lib.ptr(out),
+                                      _lib.current_stream_ptr()), "lstm")
+    assert lib.vqcpc_check_status(_lib.ptr(ws), _lib.current_stream_ptr()) == _lib.ERR_ARG
+    assert bool(torch.isfinite(out).all())

@@ -11,7 +11,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libvqcpc_b200.so")
 
-ERR_ARG, ERR_CUDA, ERR_DEVICE, ERR_TIMEOUT = 1, 2, 3, 4
+ERR_ARG, ERR_CUDA, ERR_DEVICE, ERR_TIMEOUT, ERR_INDEX = 1, 2, 3, 4, 5
 GEMM_FP32, GEMM_BF16X3 = 0, 1
 f32p = C.POINTER(C.c_float)
 
@@ -60,8 +60,8 @@ SIGNATURES = {
     "vqcpc_linear_tc": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
     "vqcpc_split_planes": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _vp]),
     "vqcpc_layernorm_relu_f32": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _vp]),
-    "vqcpc_vq_lookup": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp]),
-    "vqcpc_vq_check_status": (C.c_int, [_vp]),
+    "vqcpc_vq_lookup": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _sz, _vp]),
+    "vqcpc_vq_workspace_bytes": (_sz, []),
     "vqcpc_encoder_workspace_bytes": (_sz, [_i32, _i32, _i32]),
     "vqcpc_encoder_forward": (C.c_int, [C.POINTER(EncoderWeights), _vp, _i32, _i32, _vp, _sz, _vp, _vp, _vp, _vp, _vp, _vp]),
     "vqcpc_encoder_workspace_bytes_ex": (_sz, [_i32, _i32, _i32, _i32]),
@@ -118,6 +118,8 @@ def check(status: int, what: str) -> None:
     msg = lib().vqcpc_last_error().decode("utf-8", "replace")
     if status == ERR_ARG:
         raise ValueError(f"{what}: {msg}")
+    if status == ERR_INDEX:
+        raise IndexError(f"{what}: {msg} (nn.Embedding would raise)")
     raise VqcpcError(f"{what}: status {status}: {msg}")
 
 

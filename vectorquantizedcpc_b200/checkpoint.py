@@ -26,22 +26,31 @@ StateDict = Dict[str, Tensor]
 _ENCODER_ROOTS = ("conv.", "encoder.", "codebook.", "rnn.")
 
 
-def _read(ckpt: Union[str, os.PathLike, Mapping[str, Any]]) -> Mapping[str, Any]:
+def _read(ckpt: Union[str, os.PathLike, Mapping[str, Any]], trust_pickle: bool = False) -> Mapping[str, Any]:
     if isinstance(ckpt, Mapping):
         return ckpt
-    # same call as the reference (convert.py:38): tensors stay on the CPU
-    return torch.load(os.fspath(ckpt), map_location=lambda storage, loc: storage, weights_only=False)
+    # Same call as the reference (convert.py:38) -- tensors stay on the CPU -- except that the safe tensor-only unpickler is
+    # the default: release checkpoints are downloaded files and only plain tensor state_dicts are consumed here.  A
+    # Lightning checkpoint that pickles hyper-parameter objects needs ``trust_pickle=True`` (runs arbitrary pickled code).
+    try:
+        return torch.load(os.fspath(ckpt), map_location="cpu", weights_only=not trust_pickle)
+    except Exception as e:  # noqa: BLE001 -- re-raised with the remedy spelled out
+        if trust_pickle:
+            raise
+        raise RuntimeError(f"{os.fspath(ckpt)}: not loadable with the tensor-only unpickler ({type(e).__name__}: {e}).  If the "
+                           "file is trusted (e.g. a Lightning checkpoint carrying non-tensor hyper-parameters), pass "
+                           "trust_pickle=True.") from e
 
 
 def _strip(sd: Mapping[str, Tensor], prefix: str) -> StateDict:
     return {k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)}
 
 
-def extract_state_dicts(ckpt: Union[str, os.PathLike, Mapping[str, Any]]) -> Dict[str, StateDict]:
+def extract_state_dicts(ckpt: Union[str, os.PathLike, Mapping[str, Any]], trust_pickle: bool = False) -> Dict[str, StateDict]:
     """Returns ``{"encoder": sd}`` and/or ``{"vocoder": sd}`` -- whatever the container holds.
 
     Raises ``KeyError`` if neither is found (the message lists the top-level keys seen)."""
-    c = _read(ckpt)
+    c = _read(ckpt, trust_pickle)
     out: Dict[str, StateDict] = {}
     if isinstance(c.get("encoder"), Mapping):
         out["encoder"] = dict(c["encoder"])
@@ -85,17 +94,19 @@ def vocoder_conf_from_state(sd: Mapping[str, Tensor]) -> ConfVocoder:
                        dim_speaker_embedding=spk.shape[1])
 
 
-def load_encoder(ckpt: Union[str, os.PathLike, Mapping[str, Any]], conf: Optional[ConfEncoder] = None) -> Encoder:
+def load_encoder(ckpt: Union[str, os.PathLike, Mapping[str, Any]], conf: Optional[ConfEncoder] = None,
+                 trust_pickle: bool = False) -> Encoder:
     """``Encoder`` in eval mode with the checkpoint's weights (``convert.py:32,39,47`` in one call)."""
-    sd = extract_state_dicts(ckpt)["encoder"]
+    sd = extract_state_dicts(ckpt, trust_pickle)["encoder"]
     enc = Encoder(conf if conf is not None else encoder_conf_from_state(sd))
     enc.load_state_dict(sd)
     return enc.eval()
 
 
-def load_vocoder(ckpt: Union[str, os.PathLike, Mapping[str, Any]], conf: Optional[ConfVocoder] = None) -> Vocoder:
+def load_vocoder(ckpt: Union[str, os.PathLike, Mapping[str, Any]], conf: Optional[ConfVocoder] = None,
+                 trust_pickle: bool = False) -> Vocoder:
     """``Vocoder`` in eval mode with the checkpoint's weights (``convert.py:33,44,48`` in one call)."""
-    sd = extract_state_dicts(ckpt)["vocoder"]
+    sd = extract_state_dicts(ckpt, trust_pickle)["vocoder"]
     voc = Vocoder(conf if conf is not None else vocoder_conf_from_state(sd))
     voc.load_state_dict(sd)
     return voc.eval()

@@ -85,14 +85,18 @@ extern "C" int vqcpc_check_status(void* workspace, void* stream) {
         vqcpc::set_error("check_status: null workspace");
         return VQCPC_ERR_ARG;
     }
-    int status = 0;
+    int hdr[2] = {0, 0};            // WorkspaceHeader: status, index_error
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    VQ_CUDA(cudaMemcpyAsync(&status, workspace, sizeof(int), cudaMemcpyDeviceToHost, s));
+    VQ_CUDA(cudaMemcpyAsync(hdr, workspace, sizeof(hdr), cudaMemcpyDeviceToHost, s));
     VQ_CUDA(cudaStreamSynchronize(s));
+    int status = hdr[0];
+    if (status == 0 && hdr[1] == vqcpc::INDEX_ERROR_MAGIC) status = VQCPC_ERR_INDEX;
     if (status != 0) {
-        VQ_CUDA(cudaMemsetAsync(workspace, 0, sizeof(int), s));
-        vqcpc::set_error("persistent kernel reported status %d (%s)", status,
-                         status == VQCPC_ERR_TIMEOUT ? "LL exchange timed out" : "unknown");
+        VQ_CUDA(cudaMemsetAsync(workspace, 0, sizeof(hdr), s));
+        vqcpc::set_error("device reported status %d (%s)", status,
+                         status == VQCPC_ERR_TIMEOUT ? "an exchange of a persistent kernel timed out"
+                         : status == VQCPC_ERR_INDEX ? "code index or speaker id out of range"
+                         : status == VQCPC_ERR_ARG ? "argument out of range" : "unknown");
     }
     return status;
 }

@@ -9,6 +9,17 @@
 
 namespace vqcpc {
 
+// Code indices come from the caller in the public LSTM entry: gathers clamp them (memory safety) and
+// check_codes_kernel reports an out-of-range index through the workspace status word (vqcpc_check_status).
+__device__ __forceinline__ int64_t clamp_code(int64_t id) { return id < 0 ? 0 : (id > 511 ? 511 : id); }
+__global__ void check_codes_kernel(const int64_t* __restrict__ idx, int64_t n, int* status) {
+    bool bad = false;
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+        bad |= (idx[i] < 0 || idx[i] > 511);
+    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicExch(status, VQCPC_ERR_ARG);
+}
+
+
 // ------------------------------------------------------------------------------------------------
 // relu(LayerNorm(x)) in place, one warp per row  (nn.LayerNorm(C) + nn.ReLU, model.py:47-48,51-52).
 // mean, then biased variance of (x - mean), eps = 1e-5: the oracle's two-pass formula.
@@ -367,7 +378,7 @@ __global__ void __launch_bounds__(256) lstm_kernel(LstmParams p) {
 
         float xp[4] = {0.f, 0.f, 0.f, 0.f};
         if (my_valid) {
-            const int64_t id = p.idx[static_cast<int64_t>(my_b) * p.Tp];
+            const int64_t id = clamp_code(p.idx[static_cast<int64_t>(my_b) * p.Tp]);
             const float* trow = p.table + id * LSTM_G + unit;
 #pragma unroll
             for (int g = 0; g < 4; ++g) xp[g] = __ldg(trow + g * LSTM_H);
@@ -381,7 +392,7 @@ __global__ void __launch_bounds__(256) lstm_kernel(LstmParams p) {
             // prefetch next step's x-projection
             float xn[4] = {0.f, 0.f, 0.f, 0.f};
             if (my_valid && t + 1 < p.Tp) {
-                const int64_t id = p.idx[static_cast<int64_t>(my_b) * p.Tp + t + 1];
+                const int64_t id = clamp_code(p.idx[static_cast<int64_t>(my_b) * p.Tp + t + 1]);
                 const float* trow = p.table + id * LSTM_G + unit;
 #pragma unroll
                 for (int g = 0; g < 4; ++g) xn[g] = __ldg(trow + g * LSTM_H);
@@ -505,7 +516,7 @@ __global__ void lstm_gate_kernel(const float* __restrict__ gates, const float* _
     for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
         const int b = static_cast<int>(i / (LSTM_H / 4)), q = static_cast<int>(i % (LSTM_H / 4));
-        const float4* trow = reinterpret_cast<const float4*>(table + idx[static_cast<int64_t>(b) * Tp + t] * LSTM_G);
+        const float4* trow = reinterpret_cast<const float4*>(table + clamp_code(idx[static_cast<int64_t>(b) * Tp + t]) * LSTM_G);
         float4 g[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -737,35 +748,21 @@ extern "C" int vqcpc_layernorm_relu_f32(float* x, const float* w, const float* b
                                         void* stream) {
     return vqcpc::layernorm_relu(x, w, b, rows, C, static_cast<cudaStream_t>(stream));
 }
-namespace vqcpc {
-// per-device scratch of the standalone VQ entry point: [status int | pad to 1 KB | codebook planes 128 KB]
-static void* vq_scratch() {
-    static void* buf[64] = {nullptr};
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-    if (buf[dev] == nullptr) {
-        if (cudaMalloc(&buf[dev], 1024 + VQ_TC_PLANES_BYTES) != cudaSuccess) return nullptr;
-        cudaMemset(buf[dev], 0, 1024);
-    }
-    return buf[dev];
-}
-}  // namespace vqcpc
+extern "C" size_t vqcpc_vq_workspace_bytes(void) { return 1024 + vqcpc::VQ_TC_PLANES_BYTES; }
+// workspace layout: [status int | pad to 1 KB | codebook planes].  No hidden state: the tensor-core search (n_frames >= 8192)
+// runs only when the caller passes a workspace; its status word is read with vqcpc_check_status(workspace, stream).
 extern "C" int vqcpc_vq_lookup(const float* x, const float* codebook, int64_t n_frames, int32_t n_codes, int32_t dim,
-                               float* out_q, int64_t* out_idx, void* stream) {
+                               float* out_q, int64_t* out_idx, void* workspace, size_t workspace_bytes, void* stream) {
     using namespace vqcpc;
     if (n_frames == 0) return VQCPC_OK;
     VQ_ARG(n_codes == VQ_M && dim == VQ_D, "vq_lookup: only a 512x64 codebook is supported (got %dx%d)", n_codes, dim);
-    unsigned char* s = static_cast<unsigned char*>(vq_scratch());
-    if (s == nullptr) return vq_lookup(x, codebook, n_frames, n_codes, dim, out_q, out_idx, static_cast<cudaStream_t>(stream));
-    return vq_lookup_auto(x, codebook, n_frames, out_q, out_idx, s + 1024, reinterpret_cast<int*>(s),
-                          static_cast<cudaStream_t>(stream));
-}
-// status word of the standalone VQ entry point (synchronises the stream): 0 ok, VQCPC_ERR_TIMEOUT if the tensor-core
-// pipeline timed out since the last check.
-extern "C" int vqcpc_vq_check_status(void* stream) {
-    void* s = vqcpc::vq_scratch();
-    if (s == nullptr) return VQCPC_OK;
-    return vqcpc_check_status(s, stream);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (workspace == nullptr) return vq_lookup(x, codebook, n_frames, n_codes, dim, out_q, out_idx, st);
+    VQ_ARG(workspace_bytes >= vqcpc_vq_workspace_bytes(), "vq_lookup: workspace too small (%zu < %zu)", workspace_bytes,
+           vqcpc_vq_workspace_bytes());
+    unsigned char* s = static_cast<unsigned char*>(workspace);
+    VQ_CUDA(cudaMemsetAsync(s, 0, 2 * sizeof(int), st));        // WorkspaceHeader: status, index_error
+    return vq_lookup_auto(x, codebook, n_frames, out_q, out_idx, s + 1024, reinterpret_cast<int*>(s), st);
 }
 extern "C" size_t vqcpc_encoder_workspace_bytes(int32_t B, int32_t T, int32_t channels) {
     return vqcpc::encoder_ws_bytes(B, T, channels, VQCPC_GEMM_FP32);
@@ -792,5 +789,15 @@ extern "C" size_t vqcpc_lstm_workspace_bytes(int32_t B, int32_t Tp) {
 }
 extern "C" int vqcpc_lstm_forward(const vqcpc_encoder_weights* w, const int64_t* idx, int32_t B, int32_t Tp,
                                   void* workspace, size_t workspace_bytes, float* out_c, void* stream) {
-    return vqcpc::lstm_forward(w, idx, B, Tp, workspace, workspace_bytes, out_c, static_cast<cudaStream_t>(stream));
+    const int rc = vqcpc::lstm_forward(w, idx, B, Tp, workspace, workspace_bytes, out_c, static_cast<cudaStream_t>(stream));
+    if (rc == VQCPC_OK && idx != nullptr && workspace != nullptr && B > 0 && Tp > 0) {
+        // caller-supplied indices: an index outside [0, 512) is clamped by the gathers and reported here (after the run, so that
+        // the workspace header the run resets carries it): vqcpc_check_status(workspace) returns VQCPC_ERR_ARG
+        const int64_t n = static_cast<int64_t>(B) * Tp;
+        vqcpc::check_codes_kernel<<<static_cast<unsigned>((n + 1023) / 1024 < 256 ? (n + 1023) / 1024 : 256), 256, 0,
+                                    static_cast<cudaStream_t>(stream)>>>(idx, n, static_cast<int*>(workspace));
+        if (cudaGetLastError() != cudaSuccess) return VQCPC_ERR_CUDA;
+        vqcpc::count_launch(1);
+    }
+    return rc;
 }

@@ -50,9 +50,13 @@ int ar_batch_tc_launch(const vqcpc_vocoder_weights* w, const float* G, const flo
 int ensure_dyn_smem(const void* func, int bytes);   // per-(kernel, device) opt-in to large dynamic shared memory
 
 // persistent-kernel workspace header (first bytes of every workspace handed to a persistent kernel)
+constexpr int INDEX_ERROR_MAGIC = 0x1DE7BAD5;
 struct WorkspaceHeader {
-    int status;       // 0 ok, else VQCPC_ERR_*
-    int reserved[63];
+    int status;       // 0 ok, else VQCPC_ERR_* (persistent kernels / tensor-core pipelines; reset by the call that launches them)
+    int index_error;  // == INDEX_ERROR_MAGIC: a code / speaker index was out of range (set by the conditioning gather, reset by
+                      // vocoder_condition).  A magic value, not a flag: entry points that do not run the gather leave this word
+                      // alone, and a workspace they are handed may hold uninitialised memory here.
+    int reserved[62];
 };
 
 void count_launch(int n);

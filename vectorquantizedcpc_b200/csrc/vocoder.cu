@@ -27,7 +27,8 @@ constexpr int X_INIT = 128;
 // ------------------------------------------------------------------------------------------------
 __global__ void embed_concat_kernel(const float* __restrict__ code_emb, const float* __restrict__ spk_emb,
                                     const int64_t* __restrict__ codes, const int64_t* __restrict__ speaker,
-                                    float* __restrict__ u, int B, int Tc, int dc, int ds) {
+                                    float* __restrict__ u, int B, int Tc, int dc, int ds, int n_codes, int n_speakers,
+                                    int* __restrict__ index_error) {
     const int width = dc + ds;
     const int64_t total = static_cast<int64_t>(B) * 2 * Tc * (width / 4);
     for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
@@ -37,8 +38,17 @@ __global__ void embed_concat_kernel(const float* __restrict__ code_emb, const fl
         const int t = static_cast<int>(bt % (2 * Tc));
         const int b = static_cast<int>(bt / (2 * Tc));
         float4 v;
-        if (q * 4 < dc) v = __ldg(reinterpret_cast<const float4*>(code_emb + codes[static_cast<int64_t>(b) * Tc + (t >> 1)] * dc) + q);
-        else v = __ldg(reinterpret_cast<const float4*>(spk_emb + speaker[b] * ds) + (q - dc / 4));
+        // out-of-range ids (nn.Embedding raises): clamped for memory safety and reported through the workspace header, so the
+        // host needs no synchronising range check before the launch
+        if (q * 4 < dc) {
+            int64_t c = codes[static_cast<int64_t>(b) * Tc + (t >> 1)];
+            if (c < 0 || c >= n_codes) { *index_error = INDEX_ERROR_MAGIC; c = 0; }
+            v = __ldg(reinterpret_cast<const float4*>(code_emb + c * dc) + q);
+        } else {
+            int64_t sp = speaker[b];
+            if (sp < 0 || sp >= n_speakers) { *index_error = INDEX_ERROR_MAGIC; sp = 0; }
+            v = __ldg(reinterpret_cast<const float4*>(spk_emb + sp * ds) + (q - dc / 4));
+        }
         reinterpret_cast<float4*>(u)[i] = v;
     }
 }
@@ -390,11 +400,9 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_kernel(ArParams p) {
                 const float v = (lane & 1 ? s1 : s0) + (lane & 1 ? b2[1] : b2[0]);
                 if (p.out_logits != nullptr && lane < AR_R)
                     p.out_logits[(static_cast<int64_t>(nb) * L + t) * AR_Q + cta * AR_R + lane] = v;
-                if (!teacher) {
-                    if (lane < AR_R) ll_store(llb + AR_LL_H + AR_LL_R + (par * AR_CTAS + cta) * AR_RSLOT + lane, v, tag);
-                    __syncwarp();
-                    if (lane == 0) seq_o[nb] = t + 1;
-                }
+                if (!teacher && lane < AR_R) ll_store(llb + AR_LL_H + AR_LL_R + (par * AR_CTAS + cta) * AR_RSLOT + lane, v, tag);
+                __syncwarp();
+                if (lane == 0) seq_o[nb] = t + 1;    // teacher-forced mode too: role O throttles on it (see below)
                 AR_TRACE(5, t)
             }
         }
@@ -489,7 +497,14 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_kernel(ArParams p) {
             }
             if (t < L) {
                 // ---- gates of step t for utterance nb
-                if (teacher) x[nb] = static_cast<int>(__ldg(p.x_in + static_cast<int64_t>(nb) * L + t)) & (AR_Q - 1);
+                if (teacher) {
+                    x[nb] = static_cast<int>(__ldg(p.x_in + static_cast<int64_t>(nb) * L + t)) & (AR_Q - 1);
+                    // Teacher-forced mode has no sampling, so nothing in the h -> W_hh -> gates chain waits for role R.  The
+                    // double-buffered r slots are only WAR-safe if no CTA publishes h_t before its own role R has consumed
+                    // r_{t-2}: a CTA that sees every h_t (and may then overwrite its r slot of step t-2 with r_t) knows that
+                    // every role R is past step t-2.
+                    if (t >= 2 && !wait_seq(&seq_o[nb], t - 1, &abort_flag)) { AR_FAIL(); dead = true; continue; }
+                }
                 if (t > 0) bar_sync(2 + 2 * nb, AR_BAR_COUNT);   // quarter sums of W_hh h_{t-1}[nb] are in hhpart[nb][par ^ 1]
                 if (abort_flag) { dead = true; continue; }
                 const uint32_t tag = static_cast<uint32_t>(t) + 1u;
@@ -604,8 +619,10 @@ int vocoder_condition(const vqcpc_vocoder_weights* w, const int64_t* codes, cons
     {
         const int64_t total = rows * 32;
         const unsigned grid = static_cast<unsigned>((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
+        WorkspaceHeader* hdr = reinterpret_cast<WorkspaceHeader*>(base);
+        VQ_CUDA(cudaMemsetAsync(hdr, 0, sizeof(WorkspaceHeader), stream));
         embed_concat_kernel<<<grid, 256, 0, stream>>>(w->code_emb, w->spk_emb, codes, speaker, u, B, Tc, w->dim_code,
-                                                      w->dim_speaker);
+                                                      w->dim_speaker, w->n_codes, w->n_speakers, &hdr->index_error);
         VQ_CUDA(cudaGetLastError());
         count_launch(1);
     }
@@ -661,7 +678,7 @@ static int ar_run(const vqcpc_vocoder_weights* w, const float* G, const float* u
     unsigned char* base = static_cast<unsigned char*>(ws);
     WorkspaceHeader* hdr = reinterpret_cast<WorkspaceHeader*>(base);
     ll_word* ll = reinterpret_cast<ll_word*>(base + sizeof(WorkspaceHeader));
-    VQ_CUDA(cudaMemsetAsync(hdr, 0, sizeof(WorkspaceHeader), stream));
+    VQ_CUDA(cudaMemsetAsync(&hdr->status, 0, sizeof(int), stream));   // index_error of a preceding vocoder_condition survives
     if (B >= g_batch_min_b)
         return ar_batch_run(w, G, uniforms, x_in, B, T2, L, base + sizeof(WorkspaceHeader), &hdr->status, out_wav, out_codes,
                             out_logits, stream);

@@ -13,8 +13,8 @@
 //     argmin epilogue of the other;
 //   * epilogue warps (thread = frame) read the accumulators with tcgen05.ld, add |e|^2 and keep the best two
 //     candidates.  The coarse scores carry an error <= 2^-15 |x| max|e|; a frame whose best two are closer than twice
-//     that is re-decided with exact fp32 scores of both candidates (same arithmetic as the fp32 kernel), ties to
-//     the lower index.  Everything else is exact already, so the result equals the fp32 path's.
+//     that is rescanned: exact fp32 scores of all 512 codes (same arithmetic as the fp32 kernel), first minimum wins.
+//     A frame outside the margin provably has its coarse winner as exact winner, so the result equals the fp32 path's.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <stdlib.h>
@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vq_tc_kernel(const __grid_const
     __shared__ __align__(16) float e2s[VT_M];
     __shared__ float xnorm[2][VT_TF];
     __shared__ float emax_s;
-    __shared__ float2 part[2][2][VT_TF];              // [tile parity][column half][row]: top-2 keys (double buffered)
+    __shared__ float4 part[2][2][VT_TF];              // [tile parity][column half][row]: top-2 keys of the two 128-code subsets
 
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(vt_smem) + 1023) & ~uintptr_t(1023));
     unsigned char* cb_s = smem;                       // [plane][half][256 rows][128 B]
@@ -330,6 +330,7 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vq_tc_kernel(const __grid_const
         for (long long tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x, ++it) {
             const int buf = it & 1;
             float b1 = INFINITY, b2 = INFINITY, xn = 0.f;
+            float hs1[2] = {INFINITY, INFINITY}, hs2[2] = {INFINITY, INFINITY};   // best two of each 128-code subset (half 0 / 1)
             if (e == 0) { VT_TRACE(7) }
             for (int half = 0; half < 2 && ok; ++half) {
                 ok = mbar_wait(&tfull_bar[half], tphase[half], p.err);
@@ -405,54 +406,93 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vq_tc_kernel(const __grid_const
                 // fold this half's two chains into the tile's best two, with code indices (local index < 128, col0 a multiple of 128)
                 const float h1 = __uint_as_float(__float_as_uint(fminf(b1a, b1b)) + static_cast<uint32_t>(col0));
                 const float h2 = __uint_as_float(__float_as_uint(fminf(fmaxf(b1a, b1b), fminf(b2a, b2b))) + static_cast<uint32_t>(col0));
+                hs1[half] = h1; hs2[half] = h2;
                 b2 = fminf(fmaxf(b1, h1), fminf(b2, h2));
                 b1 = fminf(b1, h1);
                 if (e == 0) { if (half == 0) { VT_TRACE(9) } else { VT_TRACE(11) } }
             }
             if (!ok) break;
-            // merge the two column halves: both warps of a row publish their pair, both read the other's, so both know
-            // the row's best two candidates and each takes half of the output work.
-            part[buf][ch][row] = make_float2(b1, b2);
+            // merge the two column halves: both warps of a row publish the best two of their two 128-code subsets, both read
+            // the other's, so both know the row's best two candidates (and the best two of all four subsets) and each takes
+            // half of the output work.
+            part[buf][ch][row] = make_float4(hs1[0], hs2[0], hs1[1], hs2[1]);
             bar_sync(1 + quarter, 64);            // only the two warps of this row quarter meet: a warp delayed by an exact
                                                   // re-decision does not hold up the other six
             if (e == 0) { VT_TRACE(12) }
+            const float4 o = part[buf][ch ^ 1][row];
             {
-                const float2 o = part[buf][ch ^ 1][row];
-                const float n1 = fminf(b1, o.x), n2 = fminf(fmaxf(b1, o.x), fminf(b2, o.y));
+                const float o1 = fminf(o.x, o.z), o2 = fminf(fmaxf(o.x, o.z), fminf(o.y, o.w));
+                const float n1 = fminf(b1, o1), n2 = fminf(fmaxf(b1, o1), fminf(b2, o2));
                 b1 = n1; b2 = n2;
             }
             int i1 = static_cast<int>(__float_as_uint(b1) & 511u);
             const long long fr = tile * VT_TF + row;
             // warp (quarter, ch) finishes rows quarter*32 + ch*16 + [0, 16): lanes ch*16 .. ch*16+15 own them
-            if ((lane >> 4) == ch && fr < p.n && !(p.debug & 2)) {
-                const int i2 = static_cast<int>(__float_as_uint(b2) & 511u);
-                // 2 x (coarse MMA error 2^-15 |x| max|e|  +  index-packing error 2^-14 |score|)
-                const float margin = 6.2e-5f * xn * emax + 1.3e-4f * fmaxf(fabsf(b1), fabsf(b2));
-                if (b2 - b1 <= margin) {
-                    // exact fp32 scores of both candidates (arithmetic of the fp32 kernel); ties -> lower index
-                    // (same summation order as the fp32 kernel; 16-byte loads, 12 in flight per round trip)
-                    const float4* xr = reinterpret_cast<const float4*>(p.x + fr * VT_D);
-                    const float4* ea = reinterpret_cast<const float4*>(p.codebook + i1 * VT_D);
-                    const float4* eb = reinterpret_cast<const float4*>(p.codebook + i2 * VT_D);
-                    float da = 0.f, db = 0.f;
+            const bool owner = (lane >> 4) == ch && fr < p.n && !(p.debug & 2);
+            // 2 x (coarse MMA error 2^-15 |x| max|e|  +  index-packing error 2^-14 |score|) = 2 eps
+            const float margin = 6.2e-5f * xn * emax + 1.3e-4f * fmaxf(fabsf(b1), fabsf(b2));
+            const bool flagged = owner && (b2 - b1 <= margin);
+            // Exactness.  Every coarse score is within eps of its exact fp32 score, so a code k can only beat (or tie) the coarse
+            // winner exactly if c_k <= c_1 + 2 eps.  Not flagged: no such code exists and the coarse winner is the strict exact
+            // winner.  Flagged (near-tie, exact tie, duplicated or collapsed codebook rows -- any NUMBER of codes may sit inside
+            // the margin, and for negative scores the packed index even orders them backwards): the four 128-code subsets whose
+            // best two are known are treated separately.  A subset whose SECOND best is outside the margin contributes at most
+            // its best; a subset whose second best is inside may hide more and is rescanned completely.  All candidates get
+            // exact fp32 scores with the fp32 kernel's arithmetic; the first minimum wins (torch.argmin).  The warp works on one
+            // flagged frame at a time; ~0.1-0.3 % of the frames of an init-like codebook, none of a trained one.
+            unsigned fm = __ballot_sync(0xffffffffu, flagged);
+            while (fm) {
+                const int src = __ffs(fm) - 1;
+                fm &= fm - 1;
+                const float B1 = __shfl_sync(0xffffffffu, b1, src), mg = __shfl_sync(0xffffffffu, margin, src);
+                float f1[4], f2[4];
+                f1[0] = __shfl_sync(0xffffffffu, hs1[0], src); f2[0] = __shfl_sync(0xffffffffu, hs2[0], src);
+                f1[1] = __shfl_sync(0xffffffffu, hs1[1], src); f2[1] = __shfl_sync(0xffffffffu, hs2[1], src);
+                f1[2] = __shfl_sync(0xffffffffu, o.x, src); f2[2] = __shfl_sync(0xffffffffu, o.y, src);
+                f1[3] = __shfl_sync(0xffffffffu, o.z, src); f2[3] = __shfl_sync(0xffffffffu, o.w, src);
+                const float4* xr = reinterpret_cast<const float4*>(p.x + (tile * VT_TF + quarter * 32 + src) * VT_D);
+                float best = INFINITY;
+                int besti = VT_M;
+                auto consider = [&](int code) {
+                    const float4* er = reinterpret_cast<const float4*>(p.codebook + code * VT_D);
+                    float d = 0.f;
 #pragma unroll 1
-                    for (int k4 = 0; k4 < VT_D / 4; k4 += 4) {
-                        float4 xv[4], av[4], bv[4];
+                    for (int k4 = 0; k4 < VT_D / 4; k4 += 8) {
+                        float4 xv[8], ev[8];
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) { xv[u] = __ldg(xr + k4 + u); av[u] = __ldg(ea + k4 + u); bv[u] = __ldg(eb + k4 + u); }
+                        for (int u = 0; u < 8; ++u) { xv[u] = __ldg(xr + k4 + u); ev[u] = __ldg(er + k4 + u); }
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            da = fmaf(xv[u].x, av[u].x, da); db = fmaf(xv[u].x, bv[u].x, db);
-                            da = fmaf(xv[u].y, av[u].y, da); db = fmaf(xv[u].y, bv[u].y, db);
-                            da = fmaf(xv[u].z, av[u].z, da); db = fmaf(xv[u].z, bv[u].z, db);
-                            da = fmaf(xv[u].w, av[u].w, da); db = fmaf(xv[u].w, bv[u].w, db);
+                        for (int u = 0; u < 8; ++u) {
+                            d = fmaf(xv[u].x, ev[u].x, d); d = fmaf(xv[u].y, ev[u].y, d);
+                            d = fmaf(xv[u].z, ev[u].z, d); d = fmaf(xv[u].w, ev[u].w, d);
                         }
                     }
-                    const float sa = fmaf(-2.0f, da, e2s[i1]), sb = fmaf(-2.0f, db, e2s[i2]);
-                    if (sb < sa || (sb == sa && i2 < i1)) i1 = i2;
+                    const float sc = fmaf(-2.0f, d, e2s[code]);
+                    if (sc < best || (sc == best && code < besti)) { best = sc; besti = code; }
+                };
+                // subsets with one candidate inside the margin: lanes 0..3 score them in parallel
+                {
+                    const float mine1 = lane == 0 ? f1[0] : lane == 1 ? f1[1] : lane == 2 ? f1[2] : f1[3];
+                    const float mine2 = lane == 0 ? f2[0] : lane == 1 ? f2[1] : lane == 2 ? f2[2] : f2[3];
+                    if (lane < 4 && mine1 - B1 <= mg && !(mine2 - B1 <= mg)) consider(static_cast<int>(__float_as_uint(mine1) & 511u));
                 }
-                p.out_idx[fr] = i1;
+                // subsets with two (hence possibly more) inside the margin: complete exact rescan, 4 codes per lane
+#pragma unroll 1
+                for (int sset = 0; sset < 4; ++sset) {
+                    if (!(f2[sset] - B1 <= mg)) continue;
+                    const int base = static_cast<int>(__float_as_uint(f1[sset]) & 0x180u);   // subset = 128 consecutive codes
+#pragma unroll 1
+                    for (int i = 0; i < 4; ++i) consider(base + 32 * i + lane);
+                }
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) {
+                    const float ob = __shfl_xor_sync(0xffffffffu, best, off);
+                    const int oi = __shfl_xor_sync(0xffffffffu, besti, off);
+                    if (ob < best || (ob == best && oi < besti)) { best = ob; besti = oi; }
+                }
+                if (lane == src) i1 = besti;
             }
+            if (owner) p.out_idx[fr] = i1;
             __syncwarp();
             pend_code = i1;
             pend_fr0 = tile * VT_TF + quarter * 32 + ch * 16;

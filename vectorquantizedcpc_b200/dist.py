@@ -46,14 +46,28 @@ def gather_utterances(local: torch.Tensor, n_total: int, dst: int = 0) -> Option
 
 def convert_sharded(encoder, vocoder, mel: torch.Tensor, speaker: torch.Tensor, dst: int = 0, **generate_kw):
     """End-to-end conversion of a batch of equal-length utterances (convert.py:72-77) sharded over the ranks:
-    every rank encodes + generates its block; indices and waveforms are gathered on ``dst``."""
+    every rank encodes + generates its block; indices and waveforms are gathered on ``dst``.
+
+    ``generate_kw`` is passed to ``Vocoder.generate``; keywords that change its return type (``return_mulaw``,
+    ``return_logits``) are rejected on EVERY rank before any collective starts (a rank raising inside the gather would
+    leave the others blocked in it).  A per-utterance ``uniforms`` tensor (n, L) is sharded like the inputs."""
+    bad = [k for k in ("return_mulaw", "return_logits") if generate_kw.get(k)]
+    if bad:
+        raise ValueError(f"convert_sharded gathers waveforms only; unsupported generate keywords: {bad}")
     n = mel.shape[0]
     m, s = shard(mel), shard(speaker)
+    kw = dict(generate_kw)
+    if kw.get("uniforms") is not None:
+        kw["uniforms"] = shard(kw["uniforms"])
+    if kw.get("lengths") is not None:
+        kw["lengths"] = shard(torch.as_tensor(kw["lengths"]))
+    Tp = (mel.shape[2] - 2) // 2 + 1
+    up = 2 * int(vocoder.conf.rnnms.upsampling_t)        # samples per code frame: x2 nearest, then the hop (config.py:70,102)
+    L = int(kw["n_steps"]) if kw.get("n_steps") is not None else up * Tp
     if m.shape[0] > 0:
         _, _, idx = encoder.encode(m)
-        wav = vocoder.generate(idx, s, **generate_kw)
-    else:
-        Tp = (mel.shape[2] - 2) // 2 + 1
+        wav = vocoder.generate(idx, s, **kw)
+    else:                                                 # an empty block still takes part in the gathers, with the same shapes
         idx = torch.empty(0, Tp, dtype=torch.int64, device=mel.device)
-        wav = torch.empty(0, 320 * Tp, device=mel.device)
+        wav = torch.empty(0, L, device=mel.device)
     return gather_utterances(idx, n, dst), gather_utterances(wav, n, dst)

@@ -66,12 +66,16 @@ class VQEmbeddingEMA(nn.Module):
         B, T, D = xf.shape
         q = torch.empty_like(xf)
         idx = torch.empty(B, T, dtype=torch.int64, device=xf.device)
+        lib = _lib.lib()
         with torch.cuda.device(xf.device):
-            st = _lib.lib().vqcpc_vq_lookup(_lib.ptr(xf), _lib.ptr(cb), B * T, cb.shape[0], D, _lib.ptr(q),
-                                            _lib.ptr(idx), _lib.current_stream_ptr())
+            tc = B * T >= 8192      # tensor-core pipeline: caller-owned workspace (codebook planes + status word)
+            ws_bytes = lib.vqcpc_vq_workspace_bytes() if tc else 0
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=xf.device) if tc else None
+            st = lib.vqcpc_vq_lookup(_lib.ptr(xf), _lib.ptr(cb), B * T, cb.shape[0], D, _lib.ptr(q), _lib.ptr(idx),
+                                     _lib.ptr(ws), ws_bytes, _lib.current_stream_ptr())
             _lib.check(st, "VQEmbeddingEMA.encode")
-            if B * T >= 8192:       # tensor-core pipeline: surface a device-side timeout instead of returning garbage
-                _lib.check(_lib.lib().vqcpc_vq_check_status(_lib.current_stream_ptr()), "VQEmbeddingEMA.encode")
+            if tc:                  # surface a device-side timeout instead of returning garbage
+                _lib.check(lib.vqcpc_check_status(_lib.ptr(ws), _lib.current_stream_ptr()), "VQEmbeddingEMA.encode")
         return q, idx
 
     def forward(self, x):

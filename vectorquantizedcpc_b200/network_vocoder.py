@@ -213,10 +213,8 @@ class Vocoder(nn.Module):
             raise ValueError("z and speaker must be int64 (LongTensor), as torch.argmin / convert.py:73 produce")
         if z.shape[1] < 1:
             raise ValueError("z needs at least one code frame")
-        if z.numel():
-            bad = ((z < 0) | (z >= self.conf.size_i_codebook)).any() | ((speaker < 0) | (speaker >= self.conf.n_speakers)).any()
-            if bool(bad):
-                raise IndexError("code index or speaker id out of range (nn.Embedding would raise)")
+        # the index range (nn.Embedding raises IndexError) is checked ON THE DEVICE by the gather kernel and surfaces through the
+        # workspace status word at the call's single synchronisation point -- no extra host sync before the launch
 
     def _check_lengths(self, lengths, z: Tensor) -> Tensor:
         """``lengths`` (B,) = valid code frames per utterance of a padded batch -> int32 device tensor."""
@@ -227,6 +225,30 @@ class Vocoder(nn.Module):
             raise ValueError(f"lengths must lie in [1, {z.shape[1]}]")
         return lengths.to(device=z.device, dtype=torch.int32).contiguous()
 
+    def _condition(self, z: Tensor, speaker: Tensor, lengths, ws: Tensor, return_prenet: bool = False):
+        """Launches the conditioning path on workspace ``ws`` (>= vqcpc_vocoder_workspace_bytes(B, Tc)); no status check."""
+        w, _keep = self.pack_weights()
+        B, Tc = z.shape
+        dev = z.device
+        lib = _lib.lib()
+        G = torch.empty(B, 2 * Tc, 3 * 896, device=dev)
+        p = torch.empty(B, 2 * Tc, 256, device=dev) if return_prenet else None
+        zc, sc = z.contiguous(), speaker.contiguous()
+        with torch.cuda.device(dev):
+            if lengths is None:
+                st = lib.vqcpc_vocoder_condition(C.byref(w), _lib.ptr(zc), _lib.ptr(sc), B, Tc, _lib.ptr(ws), ws.numel(),
+                                                 _lib.ptr(G), _lib.ptr(p), _lib.current_stream_ptr())
+            else:
+                st = lib.vqcpc_vocoder_condition_ragged(C.byref(w), _lib.ptr(zc), _lib.ptr(sc), _lib.ptr(lengths), B, Tc,
+                                                        _lib.ptr(ws), ws.numel(), _lib.ptr(G), _lib.ptr(p),
+                                                        _lib.current_stream_ptr())
+            _lib.check(st, "Vocoder.condition")
+        return G, p
+
+    def _workspace(self, z: Tensor) -> Tensor:
+        B, Tc = z.shape
+        return torch.empty(_lib.lib().vqcpc_vocoder_workspace_bytes(B, Tc), dtype=torch.uint8, device=z.device)
+
     def condition(self, z: Tensor, speaker: Tensor, return_prenet: bool = False, lengths=None):
         """Embeddings + x2 nearest + concat (network_vocoder.py:73-77), prenet biGRU, hoisted input projection
         G (B, 2Tc, 2688).  With ``return_prenet`` also the prenet output p (B, 2Tc, 256).  ``lengths`` (B,): ragged
@@ -234,24 +256,11 @@ class Vocoder(nn.Module):
         self._check_inputs(z, speaker)
         if lengths is not None:
             lengths = self._check_lengths(lengths, z)
-        w, _keep = self.pack_weights()
-        B, Tc = z.shape
-        dev = z.device
-        lib = _lib.lib()
-        G = torch.empty(B, 2 * Tc, 3 * 896, device=dev)
-        p = torch.empty(B, 2 * Tc, 256, device=dev) if return_prenet else None
-        ws_bytes = lib.vqcpc_vocoder_workspace_bytes(B, Tc)
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        zc, sc = z.contiguous(), speaker.contiguous()
-        with torch.cuda.device(dev):
-            if lengths is None:
-                st = lib.vqcpc_vocoder_condition(C.byref(w), _lib.ptr(zc), _lib.ptr(sc), B, Tc, _lib.ptr(ws), ws_bytes,
-                                                 _lib.ptr(G), _lib.ptr(p), _lib.current_stream_ptr())
-            else:
-                st = lib.vqcpc_vocoder_condition_ragged(C.byref(w), _lib.ptr(zc), _lib.ptr(sc), _lib.ptr(lengths), B, Tc,
-                                                        _lib.ptr(ws), ws_bytes, _lib.ptr(G), _lib.ptr(p),
-                                                        _lib.current_stream_ptr())
-            _lib.check(st, "Vocoder.condition")
+        ws = self._workspace(z)
+        G, p = self._condition(z, speaker, lengths, ws, return_prenet)
+        if z.numel():
+            with torch.cuda.device(z.device):
+                _lib.check(_lib.lib().vqcpc_check_status(_lib.ptr(ws), _lib.current_stream_ptr()), "Vocoder.condition")
         return (G, p) if return_prenet else G
 
     def generate(self, z: Tensor, speaker: Tensor, uniforms: Optional[Tensor] = None, return_mulaw: bool = False,
@@ -268,7 +277,10 @@ class Vocoder(nn.Module):
         has lengths[b] valid code frames.  Its first 320*lengths[b] samples are exactly what an unpadded call with
         the same uniforms returns; the rest of its row is set to 0 (use ``wav[b, :320*lengths[b]]``)."""
         _check_no_grad()
-        G = self.condition(z, speaker, lengths=lengths)
+        self._check_inputs(z, speaker)
+        len_dev = self._check_lengths(lengths, z) if lengths is not None else None
+        ws = self._workspace(z)               # shared by the conditioning path and the sample loop: ONE status word, one sync
+        G, _ = self._condition(z, speaker, len_dev, ws)
         w, _keep = self.pack_weights()
         B, Tc = z.shape
         dev = z.device
@@ -286,14 +298,12 @@ class Vocoder(nn.Module):
         wav = torch.empty(B, L, device=dev)
         codes = torch.empty(B, L, dtype=torch.int32, device=dev) if return_mulaw else None
         logits = torch.empty(B, L, 256, device=dev) if return_logits else None
-        ws_bytes = lib.vqcpc_vocoder_workspace_bytes(1, 1)
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
             st = lib.vqcpc_vocoder_generate(C.byref(w), _lib.ptr(G), _lib.ptr(uniforms), B, 2 * Tc, L, _lib.ptr(ws),
-                                            ws_bytes, _lib.ptr(wav), _lib.ptr(codes), _lib.ptr(logits),
+                                            ws.numel(), _lib.ptr(wav), _lib.ptr(codes), _lib.ptr(logits),
                                             _lib.current_stream_ptr())
             _lib.check(st, "Vocoder.generate")
-            if B > 0 and L > 0:
+            if B > 0:
                 _lib.check(lib.vqcpc_check_status(_lib.ptr(ws), _lib.current_stream_ptr()), "Vocoder.generate")
         if lengths is not None and B > 0 and L > 0:
             valid = (torch.arange(L, device=dev)[None, :] <
@@ -316,7 +326,10 @@ class Vocoder(nn.Module):
             raise ValueError("x must be (B, L) int64")
         if x.numel() and bool(((x < 0) | (x > 255)).any()):
             raise IndexError("mu-law code out of range [0, 255]")
-        G = self.condition(z, speaker, lengths=lengths)
+        self._check_inputs(z, speaker)
+        len_dev = self._check_lengths(lengths, z) if lengths is not None else None
+        ws = self._workspace(z)
+        G, _ = self._condition(z, speaker, len_dev, ws)
         w, _keep = self.pack_weights()
         B, Tc = z.shape
         L = x.shape[1]
@@ -325,13 +338,11 @@ class Vocoder(nn.Module):
         dev = z.device
         lib = _lib.lib()
         logits = torch.empty(B, L, 256, device=dev)
-        ws_bytes = lib.vqcpc_vocoder_workspace_bytes(1, 1)
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         xc = x.contiguous()
         with torch.cuda.device(dev):
-            st = lib.vqcpc_vocoder_logits_tf(C.byref(w), _lib.ptr(G), _lib.ptr(xc), B, 2 * Tc, L, _lib.ptr(ws), ws_bytes,
+            st = lib.vqcpc_vocoder_logits_tf(C.byref(w), _lib.ptr(G), _lib.ptr(xc), B, 2 * Tc, L, _lib.ptr(ws), ws.numel(),
                                              _lib.ptr(logits), _lib.current_stream_ptr())
             _lib.check(st, "Vocoder.forward")
-            if B > 0 and L > 0:
+            if B > 0:
                 _lib.check(lib.vqcpc_check_status(_lib.ptr(ws), _lib.current_stream_ptr()), "Vocoder.forward")
         return logits
