@@ -67,6 +67,11 @@ typedef struct {
 /* GEMM arithmetic of Encoder.encode */
 #define VQCPC_GEMM_FP32 0     /* fp32 FMA on the CUDA cores: exact-order parity path */
 #define VQCPC_GEMM_BF16X3 1   /* tcgen05 tensor cores, bf16 hi/lo split (hi*hi + hi*lo + lo*hi), fp32 accumulate */
+#define VQCPC_GEMM_BF16 2     /* speed mode: the conv / MLP / projection products in single-pass bf16 (fp32 accumulate, fp32
+                               * LayerNorm); the VQ search stays exact for the z it is given and the LSTM stays bf16x3, so c is
+                               * fp32-grade GIVEN the indices.  Stated bound (tests/test_gpu_parity.py::test_encoder_bf16_mode):
+                               * pre-VQ z within 3e-2 * max|z| of the oracle, >= 97 % of the indices equal on trained-like
+                               * weights. */
 
 /* ---- weights of Vocoder: /root/reference/network_vocoder.py:37-39 + rnnms dims config.py:62-77,199 */
 typedef struct {

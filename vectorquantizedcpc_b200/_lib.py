@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libvqcpc_b200.so")
 
 ERR_ARG, ERR_CUDA, ERR_DEVICE, ERR_TIMEOUT, ERR_INDEX = 1, 2, 3, 4, 5
-GEMM_FP32, GEMM_BF16X3 = 0, 1
+GEMM_FP32, GEMM_BF16X3, GEMM_BF16 = 0, 1, 2
 f32p = C.POINTER(C.c_float)
 
 

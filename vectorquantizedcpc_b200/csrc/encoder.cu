@@ -573,7 +573,7 @@ int lstm_forward(const vqcpc_encoder_weights* w, const int64_t* idx, int B, int 
         float* cstate = reinterpret_cast<float*>(bb); bb += align_up(sizeof(float) * B * LSTM_H, 256);
         __nv_bfloat16* hplanes = reinterpret_cast<__nv_bfloat16*>(bb); bb += align_up(2 * static_cast<size_t>(B) * 2 * LSTM_H, 256);
         __nv_bfloat16* hplanes2 = reinterpret_cast<__nv_bfloat16*>(bb);
-        const bool tc = (mode == VQCPC_GEMM_BF16X3) && (w->lstm_whh_p != nullptr);
+        const bool tc = (mode != VQCPC_GEMM_FP32) && (w->lstm_whh_p != nullptr);   // bf16 mode too: the recurrence stays bf16x3
         const int64_t total = static_cast<int64_t>(B) * (LSTM_H / 4);
         const unsigned grid = static_cast<unsigned>((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
         if (tc && B >= LSTM_FUSED_MAX_B) {
@@ -651,8 +651,8 @@ static size_t encoder_ws_bytes(int B, int T, int C, int mode) {
     const size_t M = static_cast<size_t>(B) * Tp;
     size_t n = align_up(lstm_ws_bytes(B), 256) + 2 * align_up(M * C * sizeof(float), 256) +
                align_up(M * VQ_D * sizeof(float), 256) + align_up(VQ_TC_PLANES_BYTES, 1024);
-    if (mode == VQCPC_GEMM_BF16X3)        // two bf16 plane buffers (ping-pong A operands) + the fused-LN kernel's scratch rows
-        n += 2 * (align_up(M * 2 * (C > 320 ? C : 320) * 2, 256) + 1024) + align_up(gemm_tc_ln_scratch_bytes(C), 256);
+    if (mode != VQCPC_GEMM_FP32)          // two bf16 plane buffers (ping-pong A operands) + the fused-LN kernel's scratch rows
+        n += 2 * (align_up(M * 2 * (C > 320 ? C : 320) * 2, 256) + 1024) + align_up(gemm_ln_pair_scratch_bytes(C), 256);
     return n;
 }
 
@@ -662,7 +662,7 @@ int encoder_forward(const vqcpc_encoder_weights* w, const float* mel, int B, int
     if (B == 0) return VQCPC_OK;
     VQ_ARG(w && mel && ws && out_z && out_c && out_idx, "encoder: null pointer");
     VQ_ARG(B >= 0 && T >= 2, "encoder: bad shape B=%d T=%d (T must be >= 2)", B, T);
-    VQ_ARG(mode == VQCPC_GEMM_FP32 || mode == VQCPC_GEMM_BF16X3, "encoder: unknown gemm_mode %d", mode);
+    VQ_ARG(mode == VQCPC_GEMM_FP32 || mode == VQCPC_GEMM_BF16X3 || mode == VQCPC_GEMM_BF16, "encoder: unknown gemm_mode %d", mode);
     const int C = w->channels;
     VQ_ARG(w->in_channels == 80, "encoder: in_channels must be 80");
     VQ_ARG(C % 128 == 0 && C >= 128 && C <= 1024, "encoder: channels=%d must be a multiple of 128 in [128,1024]", C);
@@ -704,7 +704,9 @@ int encoder_forward(const vqcpc_encoder_weights* w, const float* mel, int B, int
         void* planes = base + off; off += plane_bytes;
         void* planes2 = base + off; off += plane_bytes;
         void* ln_scratch = base + off;
-        const bool fused = gemm_tc_ln_supported(C);
+        const bool fused = gemm_ln_pair_supported(C);
+        const int nseg = mode == VQCPC_GEMM_BF16 ? 1 : 3;                 // single-pass bf16: hi planes only
+        const int out_pitch = nseg == 3 ? 2 * C : C;
         VQ_CUDA(cudaMemsetAsync(hdr, 0, sizeof(WorkspaceHeader), stream));
         {
             const int64_t total = M * 80;
@@ -714,17 +716,20 @@ int encoder_forward(const vqcpc_encoder_weights* w, const float* mel, int B, int
             count_launch(1);
         }
         if (fused) {
-            // every GEMM writes relu(LN(.)) straight as the next GEMM's planes (ping-pong between the two plane buffers)
+            // every layer is ONE kernel on CTA pairs (gemm_pair.cu): GEMM + LayerNorm + ReLU, written straight as the next
+            // layer's bf16 planes (ping-pong between the two plane buffers)
             void* cur = planes;
             void* nxt = planes2;
-            if ((rc = gemm_tc_ln(cur, w->conv_wp, w->ln_w[0], w->ln_b[0], nxt, nullptr, ln_scratch, static_cast<int>(M), C, 320, 3,
-                                 &hdr->status, stream))) return rc;
+            if ((rc = gemm_ln_pair(cur, 640, 320, w->conv_wp, w->ln_w[0], w->ln_b[0], nxt, out_pitch, nullptr, ln_scratch,
+                                   static_cast<int>(M), C, 320, nseg, &hdr->status, stream))) return rc;
             for (int j = 0; j < 4; ++j) {
                 void* t = cur; cur = nxt; nxt = t;
-                if ((rc = gemm_tc_ln(cur, w->fc_wp[j], w->ln_w[j + 1], w->ln_b[j + 1], nxt, j == 3 ? out_hidden : nullptr, ln_scratch,
-                                     static_cast<int>(M), C, C, 3, &hdr->status, stream))) return rc;
+                if ((rc = gemm_ln_pair(cur, out_pitch, C, w->fc_wp[j], w->ln_w[j + 1], w->ln_b[j + 1], nxt, out_pitch,
+                                       j == 3 ? out_hidden : nullptr, ln_scratch, static_cast<int>(M), C, C, nseg, &hdr->status,
+                                       stream))) return rc;
             }
             planes = nxt;
+            if ((rc = gemm_tc(planes, w->proj_wp, w->proj_b, zpre, VQ_D, static_cast<int>(M), VQ_D, C, nseg, &hdr->status, stream))) return rc;
         } else {
             if ((rc = gemm_tc(planes, w->conv_wp, nullptr, act[0], C, static_cast<int>(M), C, 320, 3, &hdr->status, stream))) return rc;
             if ((rc = layernorm_relu_split(act[0], w->ln_w[0], w->ln_b[0], planes, nullptr, M, C, stream))) return rc;
@@ -733,8 +738,8 @@ int encoder_forward(const vqcpc_encoder_weights* w, const float* mel, int B, int
                 if ((rc = layernorm_relu_split(act[0], w->ln_w[j + 1], w->ln_b[j + 1], planes, j == 3 ? out_hidden : nullptr, M, C,
                                                stream))) return rc;
             }
+            if ((rc = gemm_tc(planes, w->proj_wp, w->proj_b, zpre, VQ_D, static_cast<int>(M), VQ_D, C, 3, &hdr->status, stream))) return rc;
         }
-        if ((rc = gemm_tc(planes, w->proj_wp, w->proj_b, zpre, VQ_D, static_cast<int>(M), VQ_D, C, 3, &hdr->status, stream))) return rc;
     }
     // the nearest-code search is exact in both modes (tensor-core coarse pass + exact recheck, or the fp32 kernel)
     if ((rc = vq_lookup_auto(zpre, w->codebook, M, out_z, out_idx, vq_planes, &hdr->status, stream))) return rc;

@@ -19,90 +19,9 @@
 
 #include "common.cuh"
 #include "kernels.cuh"
+#include "tc_ptx.cuh"
 
 namespace vqcpc {
-
-constexpr int TC_BM = 128, TC_BK = 64, TC_STAGES = 4;
-constexpr int TC_THREADS = 192;
-constexpr long long TC_TIMEOUT = 4000000000LL;
-
-// ---------------------------------------------------------------------------------------------- PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    return ok != 0;
-}
-// bounded wait: false on timeout (caller drains)
-__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, int* err) {
-    if (mbar_try_wait(bar, parity)) return true;
-    const long long t0 = clock64();
-    while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > TC_TIMEOUT) { atomicExch(err, VQCPC_ERR_TIMEOUT); return false; }
-    }
-    return true;
-}
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-                 ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile("{ .reg .pred p; setp.ne.b32 p, %4, 0; tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p; }"
-                 ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr) : "memory");
-}
-__device__ __forceinline__ void tc_ld8(uint32_t taddr, uint32_t (&v)[8]) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
-                 : "r"(taddr) : "memory");
-}
-__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tc_split_store4(float4 o, __nv_bfloat16* hi, __nv_bfloat16* lo) {
-    const __nv_bfloat16 h0 = __float2bfloat16_rn(o.x), h1 = __float2bfloat16_rn(o.y), h2 = __float2bfloat16_rn(o.z),
-                        h3 = __float2bfloat16_rn(o.w);
-    reinterpret_cast<__nv_bfloat162*>(hi)[0] = __halves2bfloat162(h0, h1);
-    reinterpret_cast<__nv_bfloat162*>(hi)[1] = __halves2bfloat162(h2, h3);
-    reinterpret_cast<__nv_bfloat162*>(lo)[0] = __halves2bfloat162(__float2bfloat16_rn(o.x - __bfloat162float(h0)),
-                                                                   __float2bfloat16_rn(o.y - __bfloat162float(h1)));
-    reinterpret_cast<__nv_bfloat162*>(lo)[1] = __halves2bfloat162(__float2bfloat16_rn(o.z - __bfloat162float(h2)),
-                                                                   __float2bfloat16_rn(o.w - __bfloat162float(h3)));
-}
-
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start >> 4, LBO = 1 (unused
-// for swizzled K-major), SBO = 1024 B (8 rows x 128 B) >> 4, version = 1 (Blackwell), layout type 2 = SWIZZLE_128B.
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
-    uint64_t d = 0;
-    d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3fff);
-    d |= static_cast<uint64_t>(1) << 16;
-    d |= static_cast<uint64_t>(1024 >> 4) << 32;
-    d |= static_cast<uint64_t>(1) << 46;
-    d |= static_cast<uint64_t>(2) << 61;
-    return d;
-}
 
 struct TcParams {
     float* C;
@@ -575,6 +494,27 @@ static int make_map(CUtensorMap* map, const void* base, long long rows, long lon
     return VQCPC_OK;
 }
 
+int make_map_bf16(void* map, const void* base, long long rows, long long cols, long long ld_elems, int box_rows) {
+    return make_map(static_cast<CUtensorMap*>(map), base, rows, cols, ld_elems, box_rows);
+}
+// general box / swizzle (TMA-store maps of the pair kernel)
+int make_map_bf16_box(void* map, const void* base, long long rows, long long cols, long long ld_elems, int box_cols, int box_rows,
+                      int swizzle_bytes) {
+    PFN_encodeTiled fn = get_encode_fn();
+    if (fn == nullptr) { set_error("gemm_tc: cuTensorMapEncodeTiled is unavailable"); return VQCPC_ERR_CUDA; }
+    cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+    cuuint64_t gstr[1] = {static_cast<cuuint64_t>(ld_elems) * 2};
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
+    cuuint32_t estr[2] = {1, 1};
+    const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                  : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                  : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
+    CUresult r = fn(static_cast<CUtensorMap*>(map), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("gemm_tc: cuTensorMapEncodeTiled failed (%d)", static_cast<int>(r)); return VQCPC_ERR_CUDA; }
+    return VQCPC_OK;
+}
+
 template <int BN>
 static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mw, const TcParams& p, cudaStream_t stream, bool pdl) {
     constexpr size_t smem = TC_STAGES * (TC_BM * TC_BK * 2 + BN * TC_BK * 2) + 1024;
@@ -596,7 +536,8 @@ static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mw, const TcParam
     return VQCPC_OK;
 }
 
-// A planes (M x nplanes*K) bf16, W planes (N x nplanes*K) bf16 with nplanes = (nseg == 3 ? 2 : 1).
+// A planes (M x nplanes*K) bf16 with nplanes = (nseg == 3 ? 2 : 1); W planes are ALWAYS stored (N x 2K) = [hi | lo] (weights are
+// split once at pack time) -- nseg = 1 reads only their hi half.
 // A plan holds the two tensor maps so that a GEMM repeated on the same buffers (the LSTM's per-step product)
 // encodes them once.
 int gemm_tc_plan(TcPlan* plan, const void* a_planes, const void* w_planes, const float* bias, float* C, long long ldc, int M,
@@ -618,8 +559,7 @@ int gemm_tc_plan(TcPlan* plan, const void* a_planes, const void* w_planes, const
     int rc = make_map(reinterpret_cast<CUtensorMap*>(plan->map_a), a_planes, M, static_cast<long long>(planes) * K,
                       static_cast<long long>(planes) * K, TC_BM);
     if (rc) return rc;
-    rc = make_map(reinterpret_cast<CUtensorMap*>(plan->map_w), w_planes, N, static_cast<long long>(planes) * K,
-                  static_cast<long long>(planes) * K, plan->bn);
+    rc = make_map(reinterpret_cast<CUtensorMap*>(plan->map_w), w_planes, N, 2LL * K, 2LL * K, plan->bn);
     if (rc) return rc;
     plan->C = C; plan->bias = bias; plan->err = err_flag; plan->ldc = ldc; plan->M = M; plan->N = N; plan->K = K; plan->nseg = nseg;
     return VQCPC_OK;
@@ -700,7 +640,7 @@ int gemm_tc_ln(const void* a_planes, const void* w_planes, const float* ln_w, co
     CUtensorMap ma, mw;
     int rc = make_map(&ma, a_planes, M, static_cast<long long>(planes) * K, static_cast<long long>(planes) * K, TC_BM);
     if (rc) return rc;
-    rc = make_map(&mw, w_planes, N, static_cast<long long>(planes) * K, static_cast<long long>(planes) * K, 256);
+    rc = make_map(&mw, w_planes, N, 2LL * K, 2LL * K, 256);
     if (rc) return rc;
     static int dbg = -1;
     if (dbg < 0) { const char* e = getenv("VQCPC_LN_DEBUG"); dbg = e ? atoi(e) : 0; }

@@ -28,6 +28,12 @@ size_t gemm_tc_ln_scratch_bytes(int N);
 bool gemm_tc_ln_supported(int N);
 int gemm_tc_ln(const void* a_planes, const void* w_planes, const float* ln_w, const float* ln_b, void* out_planes,
                float* out_f32, void* scratch, int M, int N, int K, int nseg, int* err_flag, cudaStream_t stream);
+// gemm_pair.cu: the same fused layer on CTA pairs (tcgen05 cta_group::2); nseg = 1 is the single-pass bf16 mode
+size_t gemm_ln_pair_scratch_bytes(int N);
+bool gemm_ln_pair_supported(int N);
+int gemm_ln_pair(const void* a_planes, long long a_pitch, int a_lo_col, const void* w_planes, const float* ln_w, const float* ln_b,
+                 void* out_planes, int out_pitch, float* out_f32, void* scratch, int M, int N, int K, int nseg, int* err_flag,
+                 cudaStream_t stream);
 int split_planes(const float* x, long long ld, void* out, long long rows, int K, cudaStream_t stream);
 
 // encoder.cu
