@@ -40,9 +40,11 @@ struct PairParams {
     int out_pitch;               // elements per output row
     int write_lo;                // 1: write the lo plane at column offset N
     int a_lo_col, w_lo_col;      // column offset of the lo plane inside the A / W plane rows (NSEG = 3)
+    int debug;                   // VQCPC_PAIR_DEBUG bit 0: no L2 cache hints, bit 1: no evict_first on the output stores
 };
 
 template <int NT, int NSEG>
+// (10 warps: one scheduler hosts three of them, so 16384 / 3 / 32 = 170 registers per thread is the ceiling)
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PR_THREADS, 1)
 gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                     const __grid_constant__ CUtensorMap map_out, PairParams p) {
@@ -93,6 +95,9 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             uint32_t phase = 0;
             bool ok = true;
             const uint32_t full0 = mapa_u32(smem_u32(&full_bar[0]), 0);          // the leader's full barriers
+            // L2 residency: a row block's A tiles are fetched once per column tile -- keep them until the last one; W is hot
+            const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
+            const bool hints = !(p.debug & 1);
             for (int pb = pair; pb < n_pblocks && ok; pb += n_pairs) {
                 const int row0 = pb * 2 * TC_BM + static_cast<int>(rank) * TC_BM;
                 for (int tn = 0; tn < NT && ok; ++tn) {
@@ -104,10 +109,18 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                         const uint32_t fb = full0 + static_cast<uint32_t>(stage) * 8u;
                         if (leader) mbar_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);     // both CTAs' bytes
                         const int kk = kb * TC_BK;
-                        tma_load_2d_pair(st, &map_a, kk, row0, fb);
-                        if (NSEG == 3) tma_load_2d_pair(st + TILE_BYTES, &map_a, p.a_lo_col + kk, row0, fb);
-                        tma_load_2d_pair(st + NPL * TILE_BYTES, &map_w, kk, wrow0, fb);
-                        if (NSEG == 3) tma_load_2d_pair(st + 3 * TILE_BYTES, &map_w, p.w_lo_col + kk, wrow0, fb);
+                        if (hints) {
+                            const uint64_t pa = tn == NT - 1 ? pol_stream : pol_keep;
+                            tma_load_2d_pair_hint(st, &map_a, kk, row0, fb, pa);
+                            if (NSEG == 3) tma_load_2d_pair_hint(st + TILE_BYTES, &map_a, p.a_lo_col + kk, row0, fb, pa);
+                            tma_load_2d_pair_hint(st + NPL * TILE_BYTES, &map_w, kk, wrow0, fb, pol_keep);
+                            if (NSEG == 3) tma_load_2d_pair_hint(st + 3 * TILE_BYTES, &map_w, p.w_lo_col + kk, wrow0, fb, pol_keep);
+                        } else {
+                            tma_load_2d_pair(st, &map_a, kk, row0, fb);
+                            if (NSEG == 3) tma_load_2d_pair(st + TILE_BYTES, &map_a, p.a_lo_col + kk, row0, fb);
+                            tma_load_2d_pair(st + NPL * TILE_BYTES, &map_w, kk, wrow0, fb);
+                            if (NSEG == 3) tma_load_2d_pair(st + 3 * TILE_BYTES, &map_w, p.w_lo_col + kk, wrow0, fb);
+                        }
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -165,6 +178,7 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         const uint32_t swz = static_cast<uint32_t>((lane >> 1) & 3);
         float4* sc = reinterpret_cast<float4*>(p.scratch) +
                      (static_cast<size_t>(blockIdx.x) * 8 + ew) * (NT > 2 ? NT - 2 : 1) * 32 * 32 + lane;
+        const uint64_t pol_out = l2_policy_evict_first();
         constexpr float NH = static_cast<float>(NT * 128);                              // columns per half-row
         for (int pb = pair; pb < n_pblocks && ok; pb += n_pairs) {
             const int row_base = pb * 2 * TC_BM + static_cast<int>(rank) * TC_BM;
@@ -180,12 +194,16 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 if (!ok) break;
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + half * 128;
-#pragma unroll 1
-                for (int c0 = 0; c0 < 128; c0 += 32) {
-                    uint32_t v[32];
-                    tc_ld32(taddr + c0, v);
+                // software pipelined: the tcgen05.ld of chunk c+1 is in flight while chunk c is summed
+                uint32_t vbuf[2][32];
+                tc_ld32(taddr, vbuf[0]);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t (&v)[32] = vbuf[c & 1];
                     tc_wait_ld();
-                    if (tn == 0 && c0 == 0) shift = __uint_as_float(v[0]);
+                    if (c < 3) tc_ld32(taddr + 32 * (c + 1), vbuf[(c + 1) & 1]);
+                    if (tn == 0 && c == 0) shift = __uint_as_float(v[0]);
+                    if (!(p.debug & 16))
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         const float d = __uint_as_float(v[j]) - shift;
@@ -195,15 +213,16 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     if (tn < NT - 2) {
 #pragma unroll
                         for (int q4 = 0; q4 < 8; ++q4)
-                            sc[((tn * 4 + (c0 >> 5)) * 8 + q4) * 32] = make_float4(__uint_as_float(v[4 * q4]), __uint_as_float(v[4 * q4 + 1]),
-                                                                                    __uint_as_float(v[4 * q4 + 2]), __uint_as_float(v[4 * q4 + 3]));
+                            __stcg(&sc[((tn * 4 + c) * 8 + q4) * 32],                   // L2 only: L1 keeps the LayerNorm weights
+                                   make_float4(__uint_as_float(v[4 * q4]), __uint_as_float(v[4 * q4 + 1]), __uint_as_float(v[4 * q4 + 2]),
+                                               __uint_as_float(v[4 * q4 + 3])));
                     }
                 }
                 tile_acc[tn] = acc;
                 if (tn < NT - 2) {
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive_cluster(tempty0 + static_cast<uint32_t>(acc) * 8u);
+                    if (lane == 0) mbar_arrive_cluster_relaxed(tempty0 + static_cast<uint32_t>(acc) * 8u);
                 }
                 acc_phase[acc] ^= 1;
                 acc ^= 1;
@@ -230,18 +249,19 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             bar_sync(1 + quarter, 64);                                               // both have read before either stages output
             const float nmr = -mean * rstd;
             // normalise + affine + ReLU + split of 32 columns starting at global column gc; TMA store of the two bf16 boxes
-            auto emit = [&](const uint32_t (&v)[32], int gc) {
+            // (the LayerNorm weights of the 32 columns are warp-uniform L1 hits: all 16 loads are issued by the caller BEFORE it
+            // waits for the TMEM / scratch data, so their latency is paid once per chunk, not once per use)
+            auto emit = [&](const uint32_t (&v)[32], const float4 (&w4)[8], const float4 (&b4)[8], int gc) {
+                if (p.debug & 32) return;
                 uint32_t hi[16], lo[16];
 #pragma unroll
                 for (int j4 = 0; j4 < 8; ++j4) {
-                    const float4 w4 = __ldg(reinterpret_cast<const float4*>(p.ln_w + gc) + j4);
-                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.ln_b + gc) + j4);
-                    float o0 = fmaxf(fmaf(fmaf(__uint_as_float(v[4 * j4]), rstd, nmr), w4.x, b4.x), 0.f);
-                    float o1 = fmaxf(fmaf(fmaf(__uint_as_float(v[4 * j4 + 1]), rstd, nmr), w4.y, b4.y), 0.f);
-                    float o2 = fmaxf(fmaf(fmaf(__uint_as_float(v[4 * j4 + 2]), rstd, nmr), w4.z, b4.z), 0.f);
-                    float o3 = fmaxf(fmaf(fmaf(__uint_as_float(v[4 * j4 + 3]), rstd, nmr), w4.w, b4.w), 0.f);
+                    float o0 = fmaxf(fmaf(fmaf(__uint_as_float(v[4 * j4]), rstd, nmr), w4[j4].x, b4[j4].x), 0.f);
+                    float o1 = fmaxf(fmaf(fmaf(__uint_as_float(v[4 * j4 + 1]), rstd, nmr), w4[j4].y, b4[j4].y), 0.f);
+                    float o2 = fmaxf(fmaf(fmaf(__uint_as_float(v[4 * j4 + 2]), rstd, nmr), w4[j4].z, b4[j4].z), 0.f);
+                    float o3 = fmaxf(fmaf(fmaf(__uint_as_float(v[4 * j4 + 3]), rstd, nmr), w4[j4].w, b4[j4].w), 0.f);
                     if (p.out_f32 != nullptr && row < p.M)
-                        *(reinterpret_cast<float4*>(p.out_f32 + static_cast<size_t>(row) * N + gc) + j4) = make_float4(o0, o1, o2, o3);
+                        __stcs(reinterpret_cast<float4*>(p.out_f32 + static_cast<size_t>(row) * N + gc) + j4, make_float4(o0, o1, o2, o3));
                     const __nv_bfloat162 h0 = __floats2bfloat162_rn(o0, o1), h1 = __floats2bfloat162_rn(o2, o3);
                     const uint32_t hb0 = *reinterpret_cast<const uint32_t*>(&h0), hb1 = *reinterpret_cast<const uint32_t*>(&h1);
                     hi[2 * j4] = hb0; hi[2 * j4 + 1] = hb1;
@@ -261,9 +281,14 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 }
                 fence_proxy_async_smem();
                 __syncwarp();
-                if (lane == 0) {
-                    tma_store_2d(&map_out, stg, gc, row_w);
-                    if (p.write_lo) tma_store_2d(&map_out, stg + 2048, N + gc, row_w);
+                if (lane == 0 && !(p.debug & 8)) {
+                    if (p.debug & 2) {
+                        tma_store_2d(&map_out, stg, gc, row_w);
+                        if (p.write_lo) tma_store_2d(&map_out, stg + 2048, N + gc, row_w);
+                    } else {
+                        tma_store_2d_hint(&map_out, stg, gc, row_w, pol_out);
+                        if (p.write_lo) tma_store_2d_hint(&map_out, stg + 2048, N + gc, row_w, pol_out);
+                    }
                     bulk_commit();
                 }
             };
@@ -273,27 +298,44 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             for (int k = 0; k < 2; ++k) {
                 const int tn = (NT >= 2) ? (k == 0 ? NT - 2 : NT - 1) : 0;
                 const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + tile_acc[tn] * BN + half * 128;
-#pragma unroll 1
-                for (int c0 = 0; c0 < 128; c0 += 32) {
-                    uint32_t v[32];
-                    tc_ld32(taddr + c0, v);
+                uint32_t vbuf[2][32];
+                tc_ld32(taddr, vbuf[0]);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    float4 w4[8], b4[8];
+                    const int gc = tn * BN + half * 128 + 32 * c;
+#pragma unroll
+                    for (int j4 = 0; j4 < 8; ++j4) {
+                        if (p.debug & 4) { w4[j4] = make_float4(1.f, 1.f, 1.f, 1.f); b4[j4] = make_float4(0.f, 0.f, 0.f, 0.f); continue; }
+                        w4[j4] = __ldg(reinterpret_cast<const float4*>(p.ln_w + gc) + j4);
+                        b4[j4] = __ldg(reinterpret_cast<const float4*>(p.ln_b + gc) + j4);
+                    }
                     tc_wait_ld();
-                    emit(v, tn * BN + half * 128 + c0);
+                    if (c < 3) tc_ld32(taddr + 32 * (c + 1), vbuf[(c + 1) & 1]);      // in flight while chunk c is processed
+                    emit(vbuf[c & 1], w4, b4, gc);
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(tempty0 + static_cast<uint32_t>(tile_acc[tn]) * 8u);
+                if (lane == 0) mbar_arrive_cluster_relaxed(tempty0 + static_cast<uint32_t>(tile_acc[tn]) * 8u);
             }
 #pragma unroll 1
             for (int g = 0; g < (NT - 2) * 4; ++g) {
                 uint32_t v[32];
+                float4 w4[8], b4[8], y4[8];
+                const int gc = (g >> 2) * BN + half * 128 + (g & 3) * 32;
+#pragma unroll
+                for (int q4 = 0; q4 < 8; ++q4) y4[q4] = __ldcg(&sc[(g * 8 + q4) * 32]);
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4) {
+                    w4[j4] = __ldg(reinterpret_cast<const float4*>(p.ln_w + gc) + j4);
+                    b4[j4] = __ldg(reinterpret_cast<const float4*>(p.ln_b + gc) + j4);
+                }
 #pragma unroll
                 for (int q4 = 0; q4 < 8; ++q4) {
-                    const float4 y = sc[(g * 8 + q4) * 32];
-                    v[4 * q4] = __float_as_uint(y.x); v[4 * q4 + 1] = __float_as_uint(y.y);
-                    v[4 * q4 + 2] = __float_as_uint(y.z); v[4 * q4 + 3] = __float_as_uint(y.w);
+                    v[4 * q4] = __float_as_uint(y4[q4].x); v[4 * q4 + 1] = __float_as_uint(y4[q4].y);
+                    v[4 * q4 + 2] = __float_as_uint(y4[q4].z); v[4 * q4 + 3] = __float_as_uint(y4[q4].w);
                 }
-                emit(v, (g >> 2) * BN + half * 128 + (g & 3) * 32);
+                emit(v, w4, b4, gc);
             }
         }
         if (lane == 0) bulk_wait_all();
@@ -348,8 +390,10 @@ int gemm_ln_pair(const void* a_planes, long long a_pitch, int a_lo_col, const vo
     if (rc) return rc;
     rc = make_map_bf16_box(&mo, out_planes, M, out_pitch, out_pitch, 32, 32, 64);     // 32 x 32 bf16 boxes, SWIZZLE_64B
     if (rc) return rc;
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("VQCPC_PAIR_DEBUG"); dbg = e ? atoi(e) : 0; }
     PairParams p{ln_w, ln_b, static_cast<__nv_bfloat16*>(out_planes), out_f32, static_cast<float*>(scratch), err_flag, M, K,
-                 out_pitch, out_pitch == 2 * N ? 1 : 0, a_lo_col, K};
+                 out_pitch, out_pitch == 2 * N ? 1 : 0, a_lo_col, K, dbg};
     if (N == 768) return nseg == 3 ? launch_pair<3, 3>(ma, mw, mo, p, stream) : launch_pair<3, 1>(ma, mw, mo, p, stream);
     return nseg == 3 ? launch_pair<2, 3>(ma, mw, mo, p, stream) : launch_pair<2, 1>(ma, mw, mo, p, stream);
 }

@@ -123,11 +123,36 @@ __device__ __forceinline__ void cluster_sync_all() {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// the same without memory ordering: for hand-offs whose payload is not memory (a drained TMEM accumulator: tcgen05.wait::ld has
+// completed the reads, tcgen05.fence::before_thread_sync orders them) -- avoids the MEMBAR a release at cluster scope costs
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 // TMA load of a CTA pair: the data lands in THIS CTA's shared memory, the transaction bytes complete on `bar_cluster_addr`,
 // which may be the peer's (the leader's) mbarrier
 __device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* map, int c0, int c1, uint32_t bar_cluster_addr) {
     asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                  ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(bar_cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair_hint(void* dst, const CUtensorMap* map, int c0, int c1, uint32_t bar_cluster_addr,
+                                                      uint64_t policy) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+                 "[%0], [%1, {%2, %3}], [%4], %5;"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(bar_cluster_addr), "l"(policy) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d_hint(const CUtensorMap* map, const void* src, int c0, int c1, uint64_t policy) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;"
+                 ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "l"(policy) : "memory");
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
 }
 // completion of all prior MMAs of the pair -> one arrival on the barrier at this shared-memory offset in BOTH CTAs
 __device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {
