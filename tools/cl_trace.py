@@ -14,8 +14,12 @@ sys.path.insert(0, ROOT)
 from oracle import fixtures, vocoder as ovoc  # noqa: E402
 from vectorquantizedcpc_b200 import Vocoder, _lib  # noqa: E402
 
-C_PHASES = ["gates+publish", "grid hop+fc1 rows", "fc2 partial+send", "RS hop", "RS sum+logits out+AG send",
-            "hh presum+AG hop", "softmax+sample"]
+# chain-warp stamps (each taken when the named value is available): slot -> meaning
+C_SLOTS = {0: "step start (x known)", 1: "h published", 2: "bar3 released + r ready", 3: "fc2 partials sent", 4: "RS arrived",
+           5: "RS summed (AG sent next)", 6: "W_hh presum done", 7: "AG arrived", 12: "sampled"}
+C_ORDER = [0, 1, 2, 3, 4, 5, 6, 7, 12]
+M_ORDER = [(8, "bar5 released"), (9, "poll done"), (10, "fc1 partials + butterfly done"), (13, "bar3 released + r ready"),
+           (14, "fc2 partials sent"), (11, "W_hh done")]
 
 
 def main():
@@ -51,11 +55,13 @@ def main():
                 ts = buf.cpu().double()
                 q = lambda v: [float(x) for x in torch.quantile(v.double(), torch.tensor([0.0, 0.5, 0.9, 1.0], dtype=torch.float64))]
                 d = {}
-                for k in range(7):
-                    d[C_PHASES[k]] = q(ts[:n, k + 1] - ts[:n, k])
-                d["sample->next step start"] = q(ts[1:n + 1, 0] - ts[:n, 7])
-                m = {"publish->M sees flag": q(ts[:n, 8] - ts[:n, 1]), "M poll h (incl. delay)": q(ts[:n, 9] - ts[:n, 8]),
-                     "M sts+bar+fc1 rows": q(ts[:n, 10] - ts[:n, 9]), "M wait r+fc2p+W_hh": q(ts[:n, 11] - ts[:n, 10])}
+                for a_, b_ in zip(C_ORDER[:-1], C_ORDER[1:]):
+                    d[f"{C_SLOTS[a_]} -> {C_SLOTS[b_]}"] = q(ts[:n, b_] - ts[:n, a_])
+                d["sampled -> next step start"] = q(ts[1:n + 1, 0] - ts[:n, 12])
+                m = {"h published (chain) -> bar5 released (M warp 0)": q(ts[:n, 8] - ts[:n, 1])}
+                for (a_, an), (b_, bn) in zip(M_ORDER[:-1], M_ORDER[1:]):
+                    m[f"{an} -> {bn}"] = q(ts[:n, b_] - ts[:n, a_])
+                m["M W_hh done -> chain presum done"] = q(ts[:n, 6] - ts[:n, 11])
                 m["poll done after publish, per M warp (median)"] = [float(torch.median(ts[:n, 16 + w] - ts[:n, 1])) for w in range(7)]
                 pd = ts[:n, 16:23] - ts[:n, 1:2]
                 m["slowest M warp poll done after publish [min,med,p90,max]"] = q(pd.max(dim=1).values)
@@ -78,9 +84,13 @@ def main():
     if enable:
         c = out["cta77"]
         print("   step", [round(v) for v in c["cycles_per_step[min,med,p90,max]"]])
-        print("   chain med", {k: round(v[1]) for k, v in c["chain"].items()})
-        print("   chain min", {k: round(v[0]) for k, v in c["chain"].items()})
-        print("   mwarp med", {k: (round(v[1]) if len(v) == 4 else [round(x, 2) for x in v]) for k, v in c["mwarp0"].items()})
+        for k, v in c["chain"].items():
+            print(f"   chain  {k:58s} min {round(v[0]):5d} med {round(v[1]):5d} p90 {round(v[2]):5d}")
+        for k, v in c["mwarp0"].items():
+            if len(v) == 4:
+                print(f"   mwarp0 {k:58s} min {round(v[0]):5d} med {round(v[1]):5d} p90 {round(v[2]):5d}")
+            else:
+                print(f"   mwarp0 {k}: {[round(x, 2) for x in v]}")
 
 
 if __name__ == "__main__":

@@ -9,14 +9,16 @@
 //
 //   grid   : 7 clusters x 16 CTAs = 112 CTAs x 256 threads; CTA c owns hidden units 8c..8c+7
 //   step t : C warp   gates_t(x_{t-1})  ->  publish h_t[8c..8c+7] as LL words (L2)                       [grid hop]
-//            M warps  poll their 128-word segment of h_t -> smem -> fc1 rows 16*rank..+15 of this cluster
-//                     (thread = row x 64-column chunk)     -> C warp sums the chunks, ReLU -> r[16 own]
-//            all      fc2 column-partials over the 16 own r values for all 256 classes -> reduce-scatter into
-//                     the owning rank's inbox (DSMEM LL words)                                           [DSMEM hop]
+//            M warps  poll their 128-word segment of h_t (4 words per lane) and, straight from those registers, form
+//                     the partial sums of this CTA's 16 fc1 rows over the lane's 4 columns (packed FFMA2: two rows per
+//                     instruction), reduce them over the warp with a transposing butterfly -> fpart[warp][16]
+//            all      r = relu(sum of the 7 warps' partials + b) -> fc2 column-partials over the 16 own r values for
+//                     all 256 classes -> reduce-scatter into the owning rank's inbox (st.async)          [DSMEM hop]
 //            C warp   sums 16 partials -> its 16 logits -> all-gather to the 16 ranks (DSMEM LL words)   [DSMEM hop]
 //                     softmax + inverse-CDF sample x_t (every CTA redundantly, bit-identical) -> gates_{t+1}
 //            M warps  (off the critical path) W_hh rows of the own units x h_t -> shared memory for gates_{t+1}
-// All weights live in registers: per M-warp lane 24 W_hh rows x 4 columns, 64 fc1 and 16 fc2 weights.
+// All weights live in registers: per M-warp lane 24 W_hh rows x 4 columns and 16 fc1 rows x 4 columns (as row pairs for
+// fma.rn.f32x2), 16 fc2 weights per thread.  h_t never goes through shared memory.
 #include <cooperative_groups.h>
 
 #include "common.cuh"
@@ -105,12 +107,23 @@ __device__ __forceinline__ unsigned redux_min(unsigned v) {
     return m;
 }
 
+// packed fp32 FMA (FFMA2 on sm_100a): two independent round-to-nearest FMAs per instruction -- bit-identical to two fmaf
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(*reinterpret_cast<unsigned long long*>(&a)),
+        "l"(*reinterpret_cast<unsigned long long*>(&b)), "l"(*reinterpret_cast<unsigned long long*>(&c)));
+    return *reinterpret_cast<float2*>(&r);
+}
+
 constexpr unsigned CL_XBYTES = CL_Q * 4;         // bytes per exchange phase: 256 fp32 into every CTA
 
+// TRACE = true is the instrumented build (tools/cl_trace.py): every trace point reads the clock only after the value named as
+// its dependency is available, so the stamps mark COMPLETION of a phase (a bare clock read issues in order right after the
+// previous instruction issues, and bar.sync does not block at issue).  The production instantiation contains none of it.
+template <bool TRACE>
 __global__ void __launch_bounds__(CL_THREADS, 1) ar_cluster_kernel(ClParams p) {
     __shared__ __align__(16) float Es[CL_Q * CL_ROWS];        // E'[x][g*8+u] of the own units (24 KB)
-    __shared__ __align__(16) float h_s[CL_H];                 // h_t gathered from the grid
-    __shared__ __align__(16) float rpart[2 * CL_FR];         // fc1 row sums over the two column halves
+    __shared__ __align__(16) float fpart[CL_MW * CL_FR];      // fc1: partial sums of the 16 own rows over each M warp's 128 columns
     __shared__ __align__(16) float hhpart[CL_MW * CL_ROWS];
     __shared__ __align__(16) float inboxf[2 * CL_S * CL_FR];  // [par][source rank][own logit]: fc2 column-partials
     __shared__ __align__(16) float lgf[2 * CL_Q];             // [par][class]: all 256 logits
@@ -118,7 +131,9 @@ __global__ void __launch_bounds__(CL_THREADS, 1) ar_cluster_kernel(ClParams p) {
     __shared__ volatile int abort_flag;
 
     cg::cluster_group cluster = cg::this_cluster();
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // the warp index goes through a shuffle so that the compiler knows it is warp-uniform: code under `if (warp < ...)` is then
+    // convergent and every later __shfl_sync / redux compiles to the bare instruction (no WARPSYNC.COLLECTIVE slow-path check)
+    const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const int cta = blockIdx.x, rank = static_cast<int>(cluster.block_rank());
     const int L = p.L;
 
@@ -140,33 +155,25 @@ __global__ void __launch_bounds__(CL_THREADS, 1) ar_cluster_kernel(ClParams p) {
     const unsigned lg_a = static_cast<unsigned>(__cvta_generic_to_shared(&lgf[0]));
     const bool teacher = (p.x_in != nullptr);
     const bool pipelined_poll = (p.poll_mode & 1) != 0;
-    const bool tracing = (p.trace != nullptr) && (cta == p.trace_cta) && (lane == 0);
-#define CL_TRACE(k, tt)                                                                        \
-    if (tracing && (tt) >= p.trace_t0 && (tt) < p.trace_t0 + p.trace_n)                        \
-        p.trace[((tt) - p.trace_t0) * CL_TRACE_STRIDE + (k)] = clock64();
+    const bool tracing = TRACE && (p.trace != nullptr) && (cta == p.trace_cta) && (lane == 0);
+#define CL_TRACE(k, tt, dep)                                                                   \
+    if constexpr (TRACE) {                                                                     \
+        long long clk_;                                                                        \
+        asm volatile("mov.u64 %0, %%clock64; // after %1" : "=l"(clk_) : "r"(dep) : "memory"); \
+        if (tracing && (tt) >= p.trace_t0 && (tt) < p.trace_t0 + p.trace_n)                    \
+            p.trace[((tt) - p.trace_t0) * CL_TRACE_STRIDE + (k)] = clk_;                       \
+    }
+#define FU(v) __float_as_uint(v)
+    // A timed-out wait sets the CTA's abort flag and the status word; from then on every wait of this CTA falls through at its
+    // first probe, the arithmetic runs on with garbage (the host raises VQCPC_ERR_TIMEOUT and discards the outputs) and all
+    // barriers keep being served -- no thread-divergent `dead` state, so the compute stays provably convergent.
 #define CL_FAIL()                                                          \
     do {                                                                   \
         abort_flag = 1;                                                    \
         if (lane == 0) atomicExch(p.status, VQCPC_ERR_TIMEOUT);            \
-        dead = true;                                                       \
     } while (0)
 
     // ---- per-thread weights shared by all 8 warps
-    // fc1: warp w -> column half w / 4 (448 columns) and rows 4 (w % 4) .. +3 of this CTA's 16; lane -> 14 of those columns, all
-    // four rows.  Shared memory moves 128 B/clk and an LDS.128 costs four wavefronts per warp whatever it broadcasts, so fc1 is
-    // bound by how often h_t is re-read: every loaded value feeds four rows here (7 LDS.64 per thread = 112 wavefronts per CTA;
-    // the row-per-lane-group layouts needed 448).
-    const int fhalf = warp >> 2, frg = warp & 3;
-    float w1[4][14];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const float2* row = reinterpret_cast<const float2*>(p.fc1_w + static_cast<int64_t>(rank * CL_FR + 4 * frg + i) * CL_H + 448 * fhalf + 14 * lane);
-#pragma unroll
-        for (int k = 0; k < 7; ++k) {
-            const float2 v = __ldg(row + k);
-            w1[i][2 * k] = v.x; w1[i][2 * k + 1] = v.y;
-        }
-    }
     // fc2 column-partials: thread = (output group og = tid / 4 -> classes 4 og .. 4 og + 3, column group cg = tid % 4 -> own r
     // values 4 cg .. 4 cg + 3); the four column groups meet by shuffles and lane cg == 0 sends ONE 16-byte st.async (a DSMEM
     // store costs its issue slot per thread, not per byte: 64 operations per CTA instead of 256).
@@ -180,34 +187,21 @@ __global__ void __launch_bounds__(CL_THREADS, 1) ar_cluster_kernel(ClParams p) {
     const unsigned rs_dst = cl_mapa(inbox_a + (rank * CL_FR + ((4 * og) & 15)) * 4, static_cast<unsigned>(og >> 2));
     const unsigned rs_mbar = cl_mapa(mbar_a, static_cast<unsigned>(og >> 2));
     const float4 b1v = __ldg(reinterpret_cast<const float4*>(p.fc1_b + rank * CL_FR) + cg4);   // biases of the r values fc2 reads
-    bool dead = false;
 
-    // fc1 h_t: half-row sums of this CTA's 16 rows -> rpart[half][row] (all 8 warps; h_t is in h_s)
-    auto fc1_rows = [&]() {
-        const float2* hp = reinterpret_cast<const float2*>(&h_s[448 * fhalf + 14 * lane]);
-        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    // r = relu(fc1 h_t + b) of the own rows 4 cg4 .. +3: the seven M warps' partial sums meet here
+    auto fc1_r = [&]() -> float4 {
+        float4 pq[CL_MW];
 #pragma unroll
-        for (int k = 0; k < 7; ++k) {
-            const float2 v = hp[k];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) acc[i] = fmaf(w1[i][2 * k + 1], v.y, fmaf(w1[i][2 * k], v.x, acc[i]));
-        }
-        // 4 row sums over 32 lanes: two transposing rounds (4 -> 2 -> 1 value per lane), then the 8 lanes of a row
-        const bool b4 = lane & 16, b3 = lane & 8;
-        const float k0 = (b4 ? acc[2] : acc[0]) + __shfl_xor_sync(0xffffffffu, b4 ? acc[0] : acc[2], 16);
-        const float k1 = (b4 ? acc[3] : acc[1]) + __shfl_xor_sync(0xffffffffu, b4 ? acc[1] : acc[3], 16);
-        float s = (b3 ? k1 : k0) + __shfl_xor_sync(0xffffffffu, b3 ? k0 : k1, 8);
-        const float t1 = __shfl_xor_sync(0xffffffffu, s, 1), t2 = __shfl_xor_sync(0xffffffffu, s, 2), t3 = __shfl_xor_sync(0xffffffffu, s, 3);
-        s = (s + t1) + (t2 + t3);
-        s += __shfl_xor_sync(0xffffffffu, s, 4);
-        if ((lane & 7) == 0) rpart[fhalf * CL_FR + 4 * frg + (b4 ? 2 : 0) + (b3 ? 1 : 0)] = s;
+        for (int q = 0; q < CL_MW; ++q) pq[q] = *reinterpret_cast<const float4*>(&fpart[q * CL_FR + 4 * cg4]);
+        float4 rv;
+        rv.x = fmaxf((((pq[0].x + pq[1].x) + (pq[2].x + pq[3].x)) + ((pq[4].x + pq[5].x) + pq[6].x)) + b1v.x, 0.f);
+        rv.y = fmaxf((((pq[0].y + pq[1].y) + (pq[2].y + pq[3].y)) + ((pq[4].y + pq[5].y) + pq[6].y)) + b1v.y, 0.f);
+        rv.z = fmaxf((((pq[0].z + pq[1].z) + (pq[2].z + pq[3].z)) + ((pq[4].z + pq[5].z) + pq[6].z)) + b1v.z, 0.f);
+        rv.w = fmaxf((((pq[0].w + pq[1].w) + (pq[2].w + pq[3].w)) + ((pq[4].w + pq[5].w) + pq[6].w)) + b1v.w, 0.f);
+        return rv;
     };
-    // fc2 column-partial of class tid over the own r values -> the owning rank's inbox
-    auto fc2_partial_send = [&](int par) {
-        const float4 p0 = *reinterpret_cast<const float4*>(&rpart[4 * cg4]), p1 = *reinterpret_cast<const float4*>(&rpart[CL_FR + 4 * cg4]);
-        float4 rv;                                   // relu(fc1 h + b) of the own rows 4 cg4 .. +3
-        rv.x = fmaxf((p0.x + p1.x) + b1v.x, 0.f); rv.y = fmaxf((p0.y + p1.y) + b1v.y, 0.f);
-        rv.z = fmaxf((p0.z + p1.z) + b1v.z, 0.f); rv.w = fmaxf((p0.w + p1.w) + b1v.w, 0.f);
+    // fc2 column-partials of classes 4 og .. +3 over those four r values -> the owning rank's inbox; returns s[0] (trace dependency)
+    auto fc2_partial_send = [&](const float4 rv, int par) -> float {
         float s[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) s[i] = fmaf(w2[i][3], rv.w, fmaf(w2[i][2], rv.z, fmaf(w2[i][1], rv.y, w2[i][0] * rv.x)));
@@ -216,22 +210,34 @@ __global__ void __launch_bounds__(CL_THREADS, 1) ar_cluster_kernel(ClParams p) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) s[i] += __shfl_xor_sync(0xffffffffu, s[i], 2);
         if (cg4 == 0) st_async_v4(rs_dst + par * CL_XBYTES, s[0], s[1], s[2], s[3], rs_mbar + 8 * par);
+        return s[0];
     };
 
     if (warp < CL_MW) {
         // =============================================================== M warps
         const int q = warp;
-        float whh[CL_ROWS][4];
+        // W_hh rows (r, r + 12) and fc1 rows (i, i + 8) of this CTA as register pairs: one FFMA2 advances both rows
+        float2 whp[CL_ROWS / 2][4], f1p[CL_FR / 2][4];
 #pragma unroll
-        for (int r = 0; r < CL_ROWS; ++r) {
-            const int g = r / CL_U, u = r % CL_U;
-            const float4 v = __ldg(reinterpret_cast<const float4*>(
-                p.w_hh + static_cast<int64_t>(g * CL_H + cta * CL_U + u) * CL_H + 128 * q + 4 * lane));
-            whh[r][0] = v.x; whh[r][1] = v.y; whh[r][2] = v.z; whh[r][3] = v.w;
+        for (int r = 0; r < CL_ROWS / 2; ++r) {
+            const int ra = r, rb = r + CL_ROWS / 2;
+            const float4 va = __ldg(reinterpret_cast<const float4*>(
+                p.w_hh + static_cast<int64_t>((ra / CL_U) * CL_H + cta * CL_U + ra % CL_U) * CL_H + 128 * q + 4 * lane));
+            const float4 vb = __ldg(reinterpret_cast<const float4*>(
+                p.w_hh + static_cast<int64_t>((rb / CL_U) * CL_H + cta * CL_U + rb % CL_U) * CL_H + 128 * q + 4 * lane));
+            whp[r][0] = make_float2(va.x, vb.x); whp[r][1] = make_float2(va.y, vb.y);
+            whp[r][2] = make_float2(va.z, vb.z); whp[r][3] = make_float2(va.w, vb.w);
+        }
+#pragma unroll
+        for (int i = 0; i < CL_FR / 2; ++i) {
+            const float4 va = __ldg(reinterpret_cast<const float4*>(p.fc1_w + static_cast<int64_t>(rank * CL_FR + i) * CL_H + 128 * q + 4 * lane));
+            const float4 vb = __ldg(reinterpret_cast<const float4*>(p.fc1_w + static_cast<int64_t>(rank * CL_FR + i + CL_FR / 2) * CL_H + 128 * q + 4 * lane));
+            f1p[i][0] = make_float2(va.x, vb.x); f1p[i][1] = make_float2(va.y, vb.y);
+            f1p[i][2] = make_float2(va.z, vb.z); f1p[i][3] = make_float2(va.w, vb.w);
         }
         const int w0 = 128 * q + 4 * lane;                       // first of this lane's four h words
         const ll_word* hsrc = p.hbuf + w0;
-        float* hdst = &h_s[w0];
+        const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
         for (int t = 0; t < L; ++t) {
             const uint32_t tag = static_cast<uint32_t>(t) + 1u;
             const int par = t & 1;
@@ -239,10 +245,9 @@ __global__ void __launch_bounds__(CL_THREADS, 1) ar_cluster_kernel(ClParams p) {
             // this CTA publishes h_t at (about) the same time as everybody else: do not poll L2 before that.  A hardware
             // barrier, not a shared-memory spin: seven spinning warps would steal issue and LDS slots from the chain warp.
             bar_sync(5, CL_THREADS);
-            if (abort_flag) dead = true;
-            if (warp == 0) { CL_TRACE(8, t) }
-            if (!dead && p.poll_delay) { const long long t1 = clock64(); while (clock64() - t1 < p.poll_delay) {} }
-            if (!dead) {
+            if (TRACE && warp == 0) { CL_TRACE(8, t, static_cast<unsigned>(abort_flag)) }
+            if (p.poll_delay) { const long long t1 = clock64(); while (clock64() - t1 < p.poll_delay) {} }
+            {
                 const ll_word* src = hsrc + par * CL_H;
                 const long long t0 = clock64();
                 unsigned n = 0;
@@ -275,30 +280,50 @@ __global__ void __launch_bounds__(CL_THREADS, 1) ar_cluster_kernel(ClParams p) {
                     }
                 }
                 hv[0] = ll_val(a0); hv[1] = ll_val(a1); hv[2] = ll_val(b0); hv[3] = ll_val(b1w);
-                *reinterpret_cast<float4*>(hdst) = make_float4(hv[0], hv[1], hv[2], hv[3]);
-                CL_TRACE(16 + q, t)
+                CL_TRACE(16 + q, t, FU(hv[0]))
                 if (tracing && t >= p.trace_t0 && t < p.trace_t0 + p.trace_n) p.trace[(t - p.trace_t0) * CL_TRACE_STRIDE + 24 + q] = rounds;
             }
-            if (warp == 0) { CL_TRACE(9, t) }
-            bar_sync(1, CL_THREADS);                 // all 896 values of h_t are in h_s
-            if (!dead) fc1_rows();
-            if (warp == 0) { CL_TRACE(10, t) }
-            bar_sync(3, CL_THREADS);                 // rpart holds the fc1 half-row sums
-            if (!dead) fc2_partial_send(par);
-            if (!dead) {
-                // ---- off the critical path: W_hh rows of the own units x h_t (this warp's 128 columns)
-                float acc[CL_ROWS];
+            if (TRACE && warp == 0) { CL_TRACE(9, t, FU(hv[3])) }
+            const float2 hd[4] = {make_float2(hv[0], hv[0]), make_float2(hv[1], hv[1]), make_float2(hv[2], hv[2]), make_float2(hv[3], hv[3])};
+            {
+                // ---- critical path: fc1 partials of the 16 own rows over this lane's 4 columns, then the warp-wide sums
+                float2 fa[CL_FR / 2];
 #pragma unroll
-                for (int r = 0; r < CL_ROWS; ++r)
-                    acc[r] = fmaf(whh[r][3], hv[3], fmaf(whh[r][2], hv[2], fmaf(whh[r][1], hv[1], whh[r][0] * hv[0])));
+                for (int i = 0; i < CL_FR / 2; ++i)
+                    fa[i] = ffma2(f1p[i][3], hd[3], ffma2(f1p[i][2], hd[2], ffma2(f1p[i][1], hd[1], ffma2(f1p[i][0], hd[0], make_float2(0.f, 0.f)))));
+                // transposing butterfly: 16 -> 8 -> 4 -> 2 -> 1 values per lane, then one plain round: lane pair l/2 holds row l/2
+                float v8[8], v4[4], v2[2];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v8[i] = (b4 ? fa[i].y : fa[i].x) + __shfl_xor_sync(0xffffffffu, b4 ? fa[i].x : fa[i].y, 16);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) v4[i] = (b3 ? v8[i + 4] : v8[i]) + __shfl_xor_sync(0xffffffffu, b3 ? v8[i] : v8[i + 4], 8);
+#pragma unroll
+                for (int i = 0; i < 2; ++i) v2[i] = (b2 ? v4[i + 2] : v4[i]) + __shfl_xor_sync(0xffffffffu, b2 ? v4[i] : v4[i + 2], 4);
+                float v1 = (b1 ? v2[1] : v2[0]) + __shfl_xor_sync(0xffffffffu, b1 ? v2[0] : v2[1], 2);
+                v1 += __shfl_xor_sync(0xffffffffu, v1, 1);
+                if (!(lane & 1)) fpart[q * CL_FR + (lane >> 1)] = v1;
+                if (TRACE && warp == 0) { CL_TRACE(10, t, FU(v1)) }
+            }
+            bar_sync(3, CL_THREADS);                 // fpart holds all seven warps' fc1 partial sums
+            {
+                const float4 rv = fc1_r();
+                if (TRACE && warp == 0) { CL_TRACE(13, t, FU(rv.x)) }
+                const float s0 = fc2_partial_send(rv, par);
+                if (TRACE && warp == 0) { CL_TRACE(14, t, FU(s0)) }
+                // W_hh below must not be scheduled in front of the send: its inputs pass through an ordered no-op
+                asm volatile("" : "+f"(hv[0]), "+f"(hv[1]), "+f"(hv[2]), "+f"(hv[3]));
+            }
+            const float2 hd2[4] = {make_float2(hv[0], hv[0]), make_float2(hv[1], hv[1]), make_float2(hv[2], hv[2]), make_float2(hv[3], hv[3])};
+            {
+                // ---- off the critical path: W_hh rows of the own units x h_t (this warp's 128 columns)
+                float2 acc[CL_ROWS / 2];
+#pragma unroll
+                for (int r = 0; r < CL_ROWS / 2; ++r)
+                    acc[r] = ffma2(whp[r][3], hd2[3], ffma2(whp[r][2], hd2[2], ffma2(whp[r][1], hd2[1], ffma2(whp[r][0], hd2[0], make_float2(0.f, 0.f)))));
                 // transposing butterfly: 24 -> 12 -> 6 -> 3 values per lane, then two plain rounds
-                const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
                 float v12[12], v6[6], v3[3];
 #pragma unroll
-                for (int i = 0; i < 12; ++i) {
-                    const float send = b4 ? acc[i] : acc[i + 12];
-                    v12[i] = (b4 ? acc[i + 12] : acc[i]) + __shfl_xor_sync(0xffffffffu, send, 16);
-                }
+                for (int i = 0; i < 12; ++i) v12[i] = (b4 ? acc[i].y : acc[i].x) + __shfl_xor_sync(0xffffffffu, b4 ? acc[i].x : acc[i].y, 16);
 #pragma unroll
                 for (int i = 0; i < 6; ++i) {
                     const float send = b3 ? v12[i] : v12[i + 6];
@@ -319,7 +344,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) ar_cluster_kernel(ClParams p) {
                 if (sel < 3) hhpart[q * CL_ROWS + base + sel] = sel == 0 ? v3[0] : (sel == 1 ? v3[1] : v3[2]);
             }
             bar_arrive(4, CL_THREADS);               // -> C warp: this warp's share of W_hh h_t is in hhpart
-            if (warp == 0) { CL_TRACE(11, t) }
+            if (TRACE && warp == 0) { CL_TRACE(11, t, 0u) }
         }
     } else {
         // =============================================================== C warp: the sequential chain
@@ -334,7 +359,6 @@ __global__ void __launch_bounds__(CL_THREADS, 1) ar_cluster_kernel(ClParams p) {
             ag_dst[j] = cl_mapa(lg_a + (rank * CL_FR + 4 * (lane & 3)) * 4, static_cast<unsigned>((lane >> 2) + 8 * j));
             ag_mbar[j] = cl_mapa(mbar_a + 16, static_cast<unsigned>((lane >> 2) + 8 * j));
         }
-        const unsigned lg_src = lg_a + 8 * lane * 4;
         float hown = 0.f, hb_r = bh_r, hb_z = bh_z, hb_n = bh_n;      // W_hh h_{-1} = 0
         float gh_r = 0.f, gh_z = 0.f;                                   // G_r + hb_r, G_z + hb_z: everything but E'[x]
         int x = CL_X_INIT, x_out = -1;
@@ -360,9 +384,9 @@ __global__ void __launch_bounds__(CL_THREADS, 1) ar_cluster_kernel(ClParams p) {
             }
             --frame_left;
             if (t == 0) { gh_r = __fadd_rn(g_r, hb_r); gh_z = __fadd_rn(g_z, hb_z); }
-            CL_TRACE(0, t)
+            CL_TRACE(0, t, static_cast<unsigned>(x))
             float u_t = 0.f;
-            if (!dead) {
+            {
                 // ---- GRU gates of step t for the own units (lanes 0..7; the other lanes mirror them harmlessly)
                 if (teacher) x = x_next;
                 const float* e = &Es[x * CL_ROWS + (lane & 7)];
@@ -373,8 +397,8 @@ __global__ void __launch_bounds__(CL_THREADS, 1) ar_cluster_kernel(ClParams p) {
                 if (lane < CL_U) ll_store(p.hbuf + par * CL_H + cta * CL_U + lane, hown, tag);
             }
             bar_arrive(5, CL_THREADS);               // M warps: h_t is on its way, start polling
-            if (!dead) {
-                CL_TRACE(1, t)
+            {
+                CL_TRACE(1, t, FU(hown))
                 if (lane == 0) {                       // arm this step's exchange phases (each receives 256 fp32)
                     mbar_expect_tx(mbar_a + 8 * par, CL_XBYTES);
                     if (!teacher) mbar_expect_tx(mbar_a + 16 + 8 * par, CL_XBYTES);
@@ -386,14 +410,13 @@ __global__ void __launch_bounds__(CL_THREADS, 1) ar_cluster_kernel(ClParams p) {
                     if (p.out_codes) p.out_codes[t - 1] = x_out;
                 }
             }
-            bar_sync(1, CL_THREADS);                 // all 896 values of h_t are in h_s
-            if (!dead) fc1_rows();
-            bar_sync(3, CL_THREADS);                 // rpart complete
-            CL_TRACE(2, t)
+            bar_sync(3, CL_THREADS);                 // fpart complete
             float lo[4] = {0.f, 0.f, 0.f, 0.f};
-            if (!dead) {
-                fc2_partial_send(par);
-                CL_TRACE(3, t)
+            {
+                const float4 rv = fc1_r();
+                CL_TRACE(2, t, FU(rv.x))
+                const float s0 = fc2_partial_send(rv, par);
+                CL_TRACE(3, t, FU(s0))
                 // ---- reduce-scatter: 16 ranks x 16 own logits of column-partials
                 const long long t0 = clock64();
                 unsigned n = 0;
@@ -401,9 +424,10 @@ __global__ void __launch_bounds__(CL_THREADS, 1) ar_cluster_kernel(ClParams p) {
                     if (abort_flag || ((++n & 63u) == 0 && clock64() - t0 > LL_TIMEOUT_CYCLES)) { CL_FAIL(); break; }
                 }
             }
-            if (!dead) {
+            {
                 const float4 pa = *reinterpret_cast<const float4*>(&inboxf[0] + (rs_src - inbox_a) / 4 + par * CL_Q);
                 const float4 pb = *reinterpret_cast<const float4*>(&inboxf[0] + (rs_src - inbox_a) / 4 + par * CL_Q + 8 * CL_FR);
+                CL_TRACE(4, t, FU(pa.x))
                 lo[0] = pa.x + pb.x; lo[1] = pa.y + pb.y; lo[2] = pa.z + pb.z; lo[3] = pa.w + pb.w;
 #pragma unroll
                 for (int o = 4; o <= 16; o <<= 1) {
@@ -411,7 +435,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) ar_cluster_kernel(ClParams p) {
                     for (int i = 0; i < 4; ++i) lo[i] += __shfl_xor_sync(0xffffffffu, lo[i], o);
                 }
                 lo[0] += b2.x; lo[1] += b2.y; lo[2] += b2.z; lo[3] += b2.w;   // logits of classes 16 rank + 4 (lane % 4) + {0..3}
-                CL_TRACE(4, t)
+                CL_TRACE(5, t, FU(lo[0]))
                 if (p.out_logits != nullptr && cta < CL_S && lane < 4)
                     *reinterpret_cast<float4*>(p.out_logits + static_cast<int64_t>(t) * CL_Q + rank * CL_FR + 4 * lane) =
                         make_float4(lo[0], lo[1], lo[2], lo[3]);
@@ -419,10 +443,9 @@ __global__ void __launch_bounds__(CL_THREADS, 1) ar_cluster_kernel(ClParams p) {
 #pragma unroll
                     for (int j = 0; j < 2; ++j) st_async_v4(ag_dst[j] + par * CL_XBYTES, lo[0], lo[1], lo[2], lo[3], ag_mbar[j] + 8 * par);
                 }
-                CL_TRACE(5, t)
             }
             bar_sync(4, CL_THREADS);                 // W_hh h_t partial sums of the 7 M warps are in hhpart
-            if (!dead) {
+            {
                 float s = 0.f;
                 if (lane < CL_ROWS) {
                     s = hhpart[lane];
@@ -436,19 +459,20 @@ __global__ void __launch_bounds__(CL_THREADS, 1) ar_cluster_kernel(ClParams p) {
                 const bool nf = (frame_left == 0);
                 gh_r = __fadd_rn(nf ? gn_r : g_r, hb_r);
                 gh_z = __fadd_rn(nf ? gn_z : g_z, hb_z);
+                CL_TRACE(6, t, FU(gh_z))
             }
-            if (!dead && !teacher) {
+            if (!teacher) {
                 // ---- all-gather of the logits, then softmax + inverse-CDF sample: lane l holds classes 8l..8l+7
                 const long long t0 = clock64();
                 unsigned n = 0;
                 while (!mbar_try_wait(mbar_a + 16 + 8 * par, phase)) {
                     if (abort_flag || ((++n & 63u) == 0 && clock64() - t0 > LL_TIMEOUT_CYCLES)) { CL_FAIL(); break; }
                 }
-                if (!dead) {
+                {
                     const float4 oa = *reinterpret_cast<const float4*>(&lgf[par * CL_Q + 8 * lane]);
                     const float4 ob = *reinterpret_cast<const float4*>(&lgf[par * CL_Q + 8 * lane + 4]);
                     const float o[8] = {oa.x, oa.y, oa.z, oa.w, ob.x, ob.y, ob.z, ob.w};
-                    CL_TRACE(6, t)
+                    CL_TRACE(7, t, FU(oa.x))
                     constexpr float LOG2E = 1.4426950408889634f;
                     const float m = redux_max(fmaxf(fmaxf(fmaxf(o[0], o[1]), fmaxf(o[2], o[3])), fmaxf(fmaxf(o[4], o[5]), fmaxf(o[6], o[7]))));
                     const float ml = -m * LOG2E;
@@ -477,23 +501,24 @@ __global__ void __launch_bounds__(CL_THREADS, 1) ar_cluster_kernel(ClParams p) {
                     cand = redux_min(cand);
                     x = cand < CL_Q ? static_cast<int>(cand) : CL_Q - 1;
                     x_out = x;
-                    CL_TRACE(7, t)
+                    CL_TRACE(12, t, static_cast<unsigned>(x))
                 }
             }
         }
-        if (!dead && cta == 0 && lane == 0 && x_out >= 0 && L > 0) {
+        if (!abort_flag && cta == 0 && lane == 0 && x_out >= 0 && L > 0) {
             if (p.out_wav) p.out_wav[L - 1] = __ldg(p.lut + x_out);
             if (p.out_codes) p.out_codes[L - 1] = x_out;
         }
     }
 #undef CL_TRACE
+#undef FU
 #undef CL_FAIL
     __syncthreads();
     cluster.sync();      // nobody's shared memory disappears while a peer may still store into it
 }
 
 // ------------------------------------------------------------------------------------------------ host
-static int g_cl_poll_delay = 200, g_cl_poll_mode = 0;
+static int g_cl_poll_delay = 300, g_cl_poll_mode = 0;
 int g_cl_enable = 1;
 
 // 1 = the device can hold the 7 x 16 cluster grid at one CTA per SM, 0 = it cannot (fall back to ar_kernel), cached per device
@@ -504,7 +529,8 @@ int ar_cluster_supported() {
     if (cache[dev]) return cache[dev] == 1;
     int ok = 0;
     do {
-        if (cudaFuncSetAttribute(ar_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) break;
+        if (cudaFuncSetAttribute(ar_cluster_kernel<false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) break;
+        if (cudaFuncSetAttribute(ar_cluster_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) break;
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(CL_CTAS); cfg.blockDim = dim3(CL_THREADS); cfg.dynamicSmemBytes = 0;
         cudaLaunchAttribute attr[1];
@@ -512,7 +538,7 @@ int ar_cluster_supported() {
         attr[0].val.clusterDim.x = CL_S; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
         int ncl = 0;
-        if (cudaOccupancyMaxActiveClusters(&ncl, ar_cluster_kernel, &cfg) != cudaSuccess) break;
+        if (cudaOccupancyMaxActiveClusters(&ncl, ar_cluster_kernel<false>, &cfg) != cudaSuccess) break;
         ok = ncl >= CL_K;
     } while (0);
     cudaGetLastError();
@@ -543,7 +569,11 @@ int ar_cluster_launch(const vqcpc_vocoder_weights* w, const float* G, const floa
     attr[1].id = cudaLaunchAttributeCooperative;      // all 112 CTAs co-resident, or the launch fails (never a silent hang)
     attr[1].val.cooperative = 1;
     cfg.attrs = attr; cfg.numAttrs = 2;
-    VQ_CUDA(cudaLaunchKernelEx(&cfg, ar_cluster_kernel, p));
+    if (trace != nullptr) {
+        VQ_CUDA(cudaLaunchKernelEx(&cfg, ar_cluster_kernel<true>, p));
+    } else {
+        VQ_CUDA(cudaLaunchKernelEx(&cfg, ar_cluster_kernel<false>, p));
+    }
     count_launch(1);
     return VQCPC_OK;
 }
