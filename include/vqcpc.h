@@ -189,8 +189,8 @@ int vqcpc_debug_set_ar_poll_gap(int32_t packed);
 /* The single-utterance sample loop runs by default on the cluster kernel (csrc/vocoder_cluster.cu: 7 clusters of 16 CTAs,
  * one grid-scope exchange per step, fc1 / fc2 / sampling over DSMEM) whenever the device can co-schedule that grid.
  * enable = 0 forces the round-1 128-CTA kernel (three grid-scope exchanges per step) for A/B measurements;
- * first_poll_delay = cycles between a CTA's own publish of h_t and its first L2 poll; poll_mode 0 = one poll round in
- * flight, 1 = two.  The cluster kernel's trace (vqcpc_debug_set_ar_trace) has 32 slots per step instead of 8. */
+ * first_poll_delay = cycles between a CTA's own publish of h_t and its first L2 poll; poll_mode is reserved (0): probes in flight beyond one were measured slower.
+ * The cluster kernel's trace (vqcpc_debug_set_ar_trace) has 32 slots per step instead of 8. */
 int vqcpc_debug_set_ar_cluster(int32_t enable, int32_t first_poll_delay, int32_t poll_mode);
 /* Measures the bare 128-way LL exchange of the sample loop (no compute): mean SM cycles per exchange over `iters`
  * exchanges.  workspace >= 64 KiB.  Three exchanges per step are the latency floor bench.py reports. */

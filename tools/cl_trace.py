@@ -15,11 +15,10 @@ from oracle import fixtures, vocoder as ovoc  # noqa: E402
 from vectorquantizedcpc_b200 import Vocoder, _lib  # noqa: E402
 
 # chain-warp stamps (each taken when the named value is available): slot -> meaning
-C_SLOTS = {0: "step start (x known)", 1: "h published", 2: "bar3 released + r ready", 3: "fc2 partials sent", 4: "RS arrived",
-           5: "RS summed (AG sent next)", 6: "W_hh presum done", 7: "AG arrived", 12: "sampled"}
-C_ORDER = [0, 1, 2, 3, 4, 5, 6, 7, 12]
-M_ORDER = [(8, "bar5 released"), (9, "poll done"), (10, "fc1 partials + butterfly done"), (13, "bar3 released + r ready"),
-           (14, "fc2 partials sent"), (11, "W_hh done")]
+C_SLOTS = {0: "step start (x known)", 1: "h published", 2: "own fc1 rows done", 3: "fc2 partials sent", 4: "RS arrived",
+           5: "RS summed (AG sent next)", 6: "hb read, gh ready", 7: "AG arrived", 12: "sampled"}
+C_ORDER = [0, 1, 2, 3, 4, 5, 7, 12, 6]
+M_ORDER = [(8, "bar5 released"), (9, "poll done"), (10, "W_hh dots done"), (11, "W_hh reduced, hb stored")]
 
 
 def main():
@@ -57,11 +56,13 @@ def main():
                 d = {}
                 for a_, b_ in zip(C_ORDER[:-1], C_ORDER[1:]):
                     d[f"{C_SLOTS[a_]} -> {C_SLOTS[b_]}"] = q(ts[:n, b_] - ts[:n, a_])
-                d["sampled -> next step start"] = q(ts[1:n + 1, 0] - ts[:n, 12])
+                d["hb read, gh ready -> next step start"] = q(ts[1:n + 1, 0] - ts[:n, 6])
                 m = {"h published (chain) -> bar5 released (M warp 0)": q(ts[:n, 8] - ts[:n, 1])}
                 for (a_, an), (b_, bn) in zip(M_ORDER[:-1], M_ORDER[1:]):
                     m[f"{an} -> {bn}"] = q(ts[:n, b_] - ts[:n, a_])
-                m["M W_hh done -> chain presum done"] = q(ts[:n, 6] - ts[:n, 11])
+                m["h published (chain) -> F warp 4 fc1 rows done"] = q(ts[:n, 13] - ts[:n, 1])
+                m["F warp 4: fc1 rows done -> fc2 partials sent"] = q(ts[:n, 14] - ts[:n, 13])
+                m["W warp 0 hb stored -> chain sampled (positive = slack)"] = q(ts[:n, 12] - ts[:n, 11])
                 m["poll done after publish, per M warp (median)"] = [float(torch.median(ts[:n, 16 + w] - ts[:n, 1])) for w in range(7)]
                 pd = ts[:n, 16:23] - ts[:n, 1:2]
                 m["slowest M warp poll done after publish [min,med,p90,max]"] = q(pd.max(dim=1).values)

@@ -79,6 +79,10 @@ __device__ __forceinline__ bool mbar_try_wait(unsigned mbar, unsigned parity) {
 __device__ __forceinline__ void st_async_f32(unsigned dst, float v, unsigned mbar_remote) {
     asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.f32 [%0], %1, [%2];" ::"r"(dst), "f"(v), "r"(mbar_remote) : "memory");
 }
+__device__ __forceinline__ void st_async_v2(unsigned dst, float a, float b, unsigned mbar_remote) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];" ::"r"(dst), "f"(a), "f"(b),
+                 "r"(mbar_remote) : "memory");
+}
 __device__ __forceinline__ void st_async_v4(unsigned dst, float a, float b, float c, float d, unsigned mbar_remote) {
     asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(dst), "f"(a), "f"(b),
                  "f"(c), "f"(d), "r"(mbar_remote) : "memory");
@@ -123,8 +127,9 @@ constexpr unsigned CL_XBYTES = CL_Q * 4;         // bytes per exchange phase: 25
 template <bool TRACE>
 __global__ void __launch_bounds__(CL_THREADS, 1) ar_cluster_kernel(ClParams p) {
     __shared__ __align__(16) float Es[CL_Q * CL_ROWS];        // E'[x][g*8+u] of the own units (24 KB)
-    __shared__ __align__(16) float fpart[CL_MW * CL_FR];      // fc1: partial sums of the 16 own rows over each M warp's 128 columns
-    __shared__ __align__(16) float hhpart[CL_MW * CL_ROWS];
+    __shared__ __align__(16) float h_s[CL_H];                 // h_t gathered from the grid
+    __shared__ __align__(16) float r_s[CL_FR];                // relu(fc1 h_t + b) of the 16 own rows
+    __shared__ __align__(16) float hb_s[CL_ROWS];             // W_hh h_t + b_hh of the own 24 rows, gate-major
     __shared__ __align__(16) float inboxf[2 * CL_S * CL_FR];  // [par][source rank][own logit]: fc2 column-partials
     __shared__ __align__(16) float lgf[2 * CL_Q];             // [par][class]: all 256 logits
     __shared__ __align__(8) unsigned long long mbars[4];      // reduce-scatter par 0/1, all-gather par 0/1
@@ -141,7 +146,6 @@ __global__ void __launch_bounds__(CL_THREADS, 1) ar_cluster_kernel(ClParams p) {
         const int x = i / CL_ROWS, j = i % CL_ROWS, g = j / CL_U, u = j % CL_U;
         Es[i] = __ldg(p.eprime + static_cast<int64_t>(x) * CL_G + g * CL_H + cta * CL_U + u);
     }
-    for (int i = tid; i < CL_MW * CL_ROWS; i += CL_THREADS) hhpart[i] = 0.f;
     const unsigned mbar_a = static_cast<unsigned>(__cvta_generic_to_shared(&mbars[0]));
     if (tid == 0) {
         abort_flag = 0;
@@ -151,10 +155,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) ar_cluster_kernel(ClParams p) {
     __syncthreads();
     cluster.sync();      // every CTA of the cluster is running and its mbarriers exist
 
-    const unsigned inbox_a = static_cast<unsigned>(__cvta_generic_to_shared(&inboxf[0]));
-    const unsigned lg_a = static_cast<unsigned>(__cvta_generic_to_shared(&lgf[0]));
     const bool teacher = (p.x_in != nullptr);
-    const bool pipelined_poll = (p.poll_mode & 1) != 0;
     const bool tracing = TRACE && (p.trace != nullptr) && (cta == p.trace_cta) && (lane == 0);
 #define CL_TRACE(k, tt, dep)                                                                   \
     if constexpr (TRACE) {                                                                     \
@@ -173,193 +174,223 @@ __global__ void __launch_bounds__(CL_THREADS, 1) ar_cluster_kernel(ClParams p) {
         if (lane == 0) atomicExch(p.status, VQCPC_ERR_TIMEOUT);            \
     } while (0)
 
-    // ---- per-thread weights shared by all 8 warps
-    // fc2 column-partials: thread = (output group og = tid / 4 -> classes 4 og .. 4 og + 3, column group cg = tid % 4 -> own r
-    // values 4 cg .. 4 cg + 3); the four column groups meet by shuffles and lane cg == 0 sends ONE 16-byte st.async (a DSMEM
-    // store costs its issue slot per thread, not per byte: 64 operations per CTA instead of 256).
-    const int og = tid >> 2, cg4 = tid & 3;
-    float w2[4][4];
+    // ---- roles.  Everything on an SM is bound by how many instructions its four schedulers issue (tools/sm_microbench.cu:
+    // SHFL 4.7 cycles of a scheduler each, FFMA2 2.65, FFMA 1.5, BAR ~40, LDS 30 latency), so the critical fc1 / fc2 work runs on
+    // ONE warp per scheduler (warps 4..7, the highest warp ids: the arbiter prefers them), whole rows per warp so that a row
+    // needs 5 shuffle rounds once instead of a 7-warp partial-sum tree, and the W_hh rows for the NEXT step's gates run on
+    // warps 0..3 underneath, in the issue slots the critical warps leave free.
+    //   warps 0..6 : poll the 128-word segment `warp` of h_t (4 words per lane) -> h_s
+    //   warps 4..7 : fc1 rows 4 (warp-4) .. +3 of this CTA's 16 (lane: 28 columns of all four rows), then fc2 column-partials of
+    //                classes 64 (warp-4) + 2 lane + {0,1} over the 16 own r values -> 8-byte st.async into the owning rank's inbox
+    //   warps 0..3 : W_hh rows 6 warp .. +5 of the CTA's 24 (lane: 28 columns of all six rows) + b_hh -> hb_s
+    //   warp 7     : additionally the sequential chain (gates, reduce-scatter sum, all-gather, softmax, sample)
+    const bool is_f = warp >= 4;
+    const int fw = warp - 4;
+    bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+    // fc1 / W_hh weights: row-major pairs of adjacent columns, columns 128 j + 4 lane + {0,1 | 2,3}, j = 0..6 (conflict-free LDS.128)
+    float2 wrow[6][14];
+    {
+        const int nrow = is_f ? 4 : 6;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(p.fc2_w + static_cast<int64_t>(4 * og + i) * CL_FC + rank * CL_FR + 4 * cg4));
-        w2[i][0] = v.x; w2[i][1] = v.y; w2[i][2] = v.z; w2[i][3] = v.w;
+        for (int r = 0; r < 6; ++r) {
+            const float* src;
+            if (is_f) {
+                src = p.fc1_w + static_cast<int64_t>(rank * CL_FR + 4 * fw + (r < 4 ? r : 0)) * CL_H;
+            } else {
+                const int row = 6 * warp + r, g = row / CL_U, u = row % CL_U;
+                src = p.w_hh + static_cast<int64_t>(g * CL_H + cta * CL_U + u) * CL_H;
+            }
+#pragma unroll
+            for (int j = 0; j < 7; ++j) {
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (r < nrow) v = __ldg(reinterpret_cast<const float4*>(src + 128 * j + 4 * lane));
+                wrow[r][2 * j] = make_float2(v.x, v.y); wrow[r][2 * j + 1] = make_float2(v.z, v.w);
+            }
+        }
     }
-    const unsigned rs_dst = cl_mapa(inbox_a + (rank * CL_FR + ((4 * og) & 15)) * 4, static_cast<unsigned>(og >> 2));
-    const unsigned rs_mbar = cl_mapa(mbar_a, static_cast<unsigned>(og >> 2));
-    const float4 b1v = __ldg(reinterpret_cast<const float4*>(p.fc1_b + rank * CL_FR) + cg4);   // biases of the r values fc2 reads
+    // fc2 (warps 4..7): classes c0 = 64 fw + 2 lane and c0 + 1 over the own r values k = 0..15, as (c0, c0 + 1) pairs
+    float2 w2p[CL_FR];
+    float2 b1p[2];                      // fc1 bias of the two rows this lane's 8-lane group finishes (see below) -- only [0] used
+    unsigned rs_dst = 0, rs_mbar = 0;
+    const unsigned inbox_a = static_cast<unsigned>(__cvta_generic_to_shared(&inboxf[0]));
+    const unsigned lg_a = static_cast<unsigned>(__cvta_generic_to_shared(&lgf[0]));
+    float fc1_bias = 0.f;
+    if (is_f) {
+        const int c0 = 64 * fw + 2 * lane;
+#pragma unroll
+        for (int k = 0; k < CL_FR; ++k)
+            w2p[k] = make_float2(__ldg(p.fc2_w + static_cast<int64_t>(c0) * CL_FC + rank * CL_FR + k),
+                                 __ldg(p.fc2_w + static_cast<int64_t>(c0 + 1) * CL_FC + rank * CL_FR + k));
+        const unsigned dst_rank = static_cast<unsigned>(c0 >> 4);
+        rs_dst = cl_mapa(inbox_a + (rank * CL_FR + (c0 & 15)) * 4, dst_rank);
+        rs_mbar = cl_mapa(mbar_a, dst_rank);
+        fc1_bias = __ldg(p.fc1_b + rank * CL_FR + 4 * fw + (b4 ? 2 : 0) + (b3 ? 1 : 0));
+    } else {
+#pragma unroll
+        for (int k = 0; k < CL_FR; ++k) w2p[k] = make_float2(0.f, 0.f);
+    }
+    (void)b1p;
+    float whh_bias = 0.f;               // W warps: b_hh of the row this lane's 4-lane group finishes
+    {
+        const int row = 6 * (warp & 3) + (b4 ? 4 : 0) + (b3 ? 2 : 0) + (b2 ? 1 : 0);
+        if (!is_f && row < 6 * (warp & 3) + 6) whh_bias = __ldg(p.b_hh + (row / CL_U) * CL_H + cta * CL_U + row % CL_U);
+    }
 
-    // r = relu(fc1 h_t + b) of the own rows 4 cg4 .. +3: the seven M warps' partial sums meet here
-    auto fc1_r = [&]() -> float4 {
-        float4 pq[CL_MW];
-#pragma unroll
-        for (int q = 0; q < CL_MW; ++q) pq[q] = *reinterpret_cast<const float4*>(&fpart[q * CL_FR + 4 * cg4]);
-        float4 rv;
-        rv.x = fmaxf((((pq[0].x + pq[1].x) + (pq[2].x + pq[3].x)) + ((pq[4].x + pq[5].x) + pq[6].x)) + b1v.x, 0.f);
-        rv.y = fmaxf((((pq[0].y + pq[1].y) + (pq[2].y + pq[3].y)) + ((pq[4].y + pq[5].y) + pq[6].y)) + b1v.y, 0.f);
-        rv.z = fmaxf((((pq[0].z + pq[1].z) + (pq[2].z + pq[3].z)) + ((pq[4].z + pq[5].z) + pq[6].z)) + b1v.z, 0.f);
-        rv.w = fmaxf((((pq[0].w + pq[1].w) + (pq[2].w + pq[3].w)) + ((pq[4].w + pq[5].w) + pq[6].w)) + b1v.w, 0.f);
-        return rv;
+    // ---- h_t : poll this warp's segment and put it into shared memory (warps 0..6)
+    const ll_word* hsrc = p.hbuf + 128 * warp + 4 * lane;
+    auto poll_h = [&](int t) {
+        const uint32_t tag = static_cast<uint32_t>(t) + 1u;
+        const ll_word* src = hsrc + (t & 1) * CL_H;
+        if (p.poll_delay) { const long long t1 = clock64(); while (clock64() - t1 < p.poll_delay) {} }
+        const long long t0 = clock64();
+        unsigned n = 0, rounds = 0;
+        ll_word a0, a1, c0, c1;
+        // one probe in flight.  Measured alternatives, both slower: back-to-back probes (r02 v2) and a second probe staggered
+        // 100-200 cycles behind the first (2.21 vs 1.88 us/step) -- loads pending on a line delay the stores they wait for.
+        for (;;) {
+            ++rounds;
+            ll_load2(src, a0, a1);
+            ll_load2(src + 2, c0, c1);
+            const bool ok = ll_tag(a0) == tag && ll_tag(a1) == tag && ll_tag(c0) == tag && ll_tag(c1) == tag;
+            if (__all_sync(0xffffffffu, ok)) break;
+            if (abort_flag || ((++n & 255u) == 0 && clock64() - t0 > LL_TIMEOUT_CYCLES)) { CL_FAIL(); break; }
+        }
+        const float4 hv = make_float4(ll_val(a0), ll_val(a1), ll_val(c0), ll_val(c1));
+        *reinterpret_cast<float4*>(&h_s[128 * warp + 4 * lane]) = hv;
+        CL_TRACE(16 + warp, t, FU(hv.x))
+        if constexpr (TRACE) {
+            if (tracing && t >= p.trace_t0 && t < p.trace_t0 + p.trace_n) p.trace[(t - p.trace_t0) * CL_TRACE_STRIDE + 24 + warp] = rounds;
+        }
+        return hv.w;
     };
-    // fc2 column-partials of classes 4 og .. +3 over those four r values -> the owning rank's inbox; returns s[0] (trace dependency)
-    auto fc2_partial_send = [&](const float4 rv, int par) -> float {
-        float s[4];
+    // ---- NR row sums of (wrow . h_t) over this lane's 28 columns
+    auto row_dots = [&](float (&s)[8], const int nr) {
+        float2 acc[6];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) s[i] = fmaf(w2[i][3], rv.w, fmaf(w2[i][2], rv.z, fmaf(w2[i][1], rv.y, w2[i][0] * rv.x)));
+        for (int r = 0; r < 6; ++r) acc[r] = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) s[i] += __shfl_xor_sync(0xffffffffu, s[i], 1);
+        for (int j = 0; j < 7; ++j) {
+            const float4 hv = *reinterpret_cast<const float4*>(&h_s[128 * j + 4 * lane]);
+            const float2 h01 = make_float2(hv.x, hv.y), h23 = make_float2(hv.z, hv.w);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) s[i] += __shfl_xor_sync(0xffffffffu, s[i], 2);
-        if (cg4 == 0) st_async_v4(rs_dst + par * CL_XBYTES, s[0], s[1], s[2], s[3], rs_mbar + 8 * par);
-        return s[0];
-    };
-
-    if (warp < CL_MW) {
-        // =============================================================== M warps
-        const int q = warp;
-        // W_hh rows (r, r + 12) and fc1 rows (i, i + 8) of this CTA as register pairs: one FFMA2 advances both rows
-        float2 whp[CL_ROWS / 2][4], f1p[CL_FR / 2][4];
-#pragma unroll
-        for (int r = 0; r < CL_ROWS / 2; ++r) {
-            const int ra = r, rb = r + CL_ROWS / 2;
-            const float4 va = __ldg(reinterpret_cast<const float4*>(
-                p.w_hh + static_cast<int64_t>((ra / CL_U) * CL_H + cta * CL_U + ra % CL_U) * CL_H + 128 * q + 4 * lane));
-            const float4 vb = __ldg(reinterpret_cast<const float4*>(
-                p.w_hh + static_cast<int64_t>((rb / CL_U) * CL_H + cta * CL_U + rb % CL_U) * CL_H + 128 * q + 4 * lane));
-            whp[r][0] = make_float2(va.x, vb.x); whp[r][1] = make_float2(va.y, vb.y);
-            whp[r][2] = make_float2(va.z, vb.z); whp[r][3] = make_float2(va.w, vb.w);
+            for (int r = 0; r < 6; ++r) {
+                if (r < nr) acc[r] = ffma2(wrow[r][2 * j + 1], h23, ffma2(wrow[r][2 * j], h01, acc[r]));
+            }
         }
 #pragma unroll
-        for (int i = 0; i < CL_FR / 2; ++i) {
-            const float4 va = __ldg(reinterpret_cast<const float4*>(p.fc1_w + static_cast<int64_t>(rank * CL_FR + i) * CL_H + 128 * q + 4 * lane));
-            const float4 vb = __ldg(reinterpret_cast<const float4*>(p.fc1_w + static_cast<int64_t>(rank * CL_FR + i + CL_FR / 2) * CL_H + 128 * q + 4 * lane));
-            f1p[i][0] = make_float2(va.x, vb.x); f1p[i][1] = make_float2(va.y, vb.y);
-            f1p[i][2] = make_float2(va.z, vb.z); f1p[i][3] = make_float2(va.w, vb.w);
+        for (int r = 0; r < 8; ++r) s[r] = (r < nr) ? acc[r < 6 ? r : 0].x + acc[r < 6 ? r : 0].y : 0.f;
+    };
+    // ---- fc1 rows of this warp (4 values per lane -> transposing butterfly: 16, 8, then plain 4, 2, 1), ReLU -> r_s
+    auto fc1_rows = [&]() -> float {
+        float s[8];
+        row_dots(s, 4);
+        float v2[2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) v2[i] = (b4 ? s[i + 2] : s[i]) + __shfl_xor_sync(0xffffffffu, b4 ? s[i] : s[i + 2], 16);
+        float v1 = (b3 ? v2[1] : v2[0]) + __shfl_xor_sync(0xffffffffu, b3 ? v2[0] : v2[1], 8);
+        v1 += __shfl_xor_sync(0xffffffffu, v1, 4);
+        v1 += __shfl_xor_sync(0xffffffffu, v1, 2);
+        v1 += __shfl_xor_sync(0xffffffffu, v1, 1);
+        const float r = fmaxf(v1 + fc1_bias, 0.f);
+        if ((lane & 7) == 0) r_s[4 * fw + (b4 ? 2 : 0) + (b3 ? 1 : 0)] = r;
+        return r;
+    };
+    // ---- fc2 column-partials of this lane's two classes over the 16 own r values -> the owning rank's inbox
+    auto fc2_partial_send = [&](int par) -> float {
+        const float4 r0 = *reinterpret_cast<const float4*>(&r_s[0]), r1 = *reinterpret_cast<const float4*>(&r_s[4]);
+        const float4 r2 = *reinterpret_cast<const float4*>(&r_s[8]), r3 = *reinterpret_cast<const float4*>(&r_s[12]);
+        const float rr[16] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w, r3.x, r3.y, r3.z, r3.w};
+        float2 a[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) a[c] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < CL_FR; ++k) a[k & 3] = ffma2(w2p[k], make_float2(rr[k], rr[k]), a[k & 3]);
+        const float sx = (a[0].x + a[1].x) + (a[2].x + a[3].x), sy = (a[0].y + a[1].y) + (a[2].y + a[3].y);
+        st_async_v2(rs_dst + par * CL_XBYTES, sx, sy, rs_mbar + 8 * par);
+        return sx;
+    };
+
+    // ---- reduce-scatter sum + all-gather send (warps 4..7, each redundantly -- they sit on four different schedulers): wait for
+    // the 16 ranks' column-partials of the 16 own logits, sum them (lane: sources lane/4 and lane/4 + 8, logit quad lane % 4),
+    // and send the 16 logits to ranks 4 fw .. 4 fw + 3 only: a DSMEM store occupies the LSU per active lane, so one warp sending
+    // to all 16 ranks (64 lane-operations) took ~250 cycles; four warps x 16 lanes take ~64.
+    const float4 b2q = is_f ? __ldg(reinterpret_cast<const float4*>(p.fc2_b + rank * CL_FR) + (lane & 3)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const unsigned ag_dst = cl_mapa(lg_a + (rank * CL_FR + 4 * (lane & 3)) * 4, static_cast<unsigned>(4 * (fw & 3) + ((lane >> 2) & 3)));
+    const unsigned ag_mbar = cl_mapa(mbar_a + 16, static_cast<unsigned>(4 * (fw & 3) + ((lane >> 2) & 3)));
+    auto rs_sum_ag_send = [&](int t, float (&lo)[4]) {
+        const int par = t & 1;
+        const unsigned phase = (static_cast<unsigned>(t) >> 1) & 1u;
+        const long long t0 = clock64();
+        unsigned n = 0;
+        while (!mbar_try_wait(mbar_a + 8 * par, phase)) {
+            if (abort_flag || ((++n & 63u) == 0 && clock64() - t0 > LL_TIMEOUT_CYCLES)) { CL_FAIL(); break; }
         }
-        const int w0 = 128 * q + 4 * lane;                       // first of this lane's four h words
-        const ll_word* hsrc = p.hbuf + w0;
-        const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
+        const float* ib = &inboxf[par * CL_Q + (lane >> 2) * CL_FR + 4 * (lane & 3)];
+        const float4 pa = *reinterpret_cast<const float4*>(ib);
+        const float4 pb = *reinterpret_cast<const float4*>(ib + 8 * CL_FR);
+        if (TRACE && warp == 7) { CL_TRACE(4, t, FU(pa.x)) }
+        lo[0] = pa.x + pb.x; lo[1] = pa.y + pb.y; lo[2] = pa.z + pb.z; lo[3] = pa.w + pb.w;
+        // (reading four sources per lane to save a shuffle round was measured slower: 225 vs 200 cycles)
+#pragma unroll
+        for (int o = 4; o <= 16; o <<= 1) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) lo[i] += __shfl_xor_sync(0xffffffffu, lo[i], o);
+        }
+        lo[0] += b2q.x; lo[1] += b2q.y; lo[2] += b2q.z; lo[3] += b2q.w;   // logits of classes 16 rank + 4 (lane % 4) + {0..3}
+        if (TRACE && warp == 7) { CL_TRACE(5, t, FU(lo[0])) }
+        if (!teacher && lane < 16) st_async_v4(ag_dst + par * CL_XBYTES, lo[0], lo[1], lo[2], lo[3], ag_mbar + 8 * par);
+    };
+
+    if (warp < 4) {
+        // =============================================================== W warps: poll, then W_hh rows for the next step's gates
         for (int t = 0; t < L; ++t) {
-            const uint32_t tag = static_cast<uint32_t>(t) + 1u;
-            const int par = t & 1;
-            float hv[4] = {0.f, 0.f, 0.f, 0.f};
             // this CTA publishes h_t at (about) the same time as everybody else: do not poll L2 before that.  A hardware
-            // barrier, not a shared-memory spin: seven spinning warps would steal issue and LDS slots from the chain warp.
+            // barrier, not a shared-memory spin: spinning warps would steal issue and LDS slots from the chain warp.
             bar_sync(5, CL_THREADS);
             if (TRACE && warp == 0) { CL_TRACE(8, t, static_cast<unsigned>(abort_flag)) }
-            if (p.poll_delay) { const long long t1 = clock64(); while (clock64() - t1 < p.poll_delay) {} }
-            {
-                const ll_word* src = hsrc + par * CL_H;
-                const long long t0 = clock64();
-                unsigned n = 0;
-                ll_word a0, a1, b0, b1w;
-                unsigned rounds = 0;
-                if (!pipelined_poll) {
-                    for (;;) {
-                        ++rounds;
-                        ll_load2(src, a0, a1);
-                        ll_load2(src + 2, b0, b1w);
-                        const bool ok = ll_tag(a0) == tag && ll_tag(a1) == tag && ll_tag(b0) == tag && ll_tag(b1w) == tag;
-                        if (__all_sync(0xffffffffu, ok)) break;
-                        if (abort_flag || ((++n & 255u) == 0 && clock64() - t0 > LL_TIMEOUT_CYCLES)) { CL_FAIL(); break; }
-                    }
-                } else {
-                    // two poll rounds in flight (measured: slower -- the extra polls delay the stores they wait for)
-                    ll_word c0, c1, d0, d1;
-                    ll_load2(src, a0, a1);
-                    ll_load2(src + 2, b0, b1w);
-                    for (;;) {
-                        ll_load2(src, c0, c1);
-                        ll_load2(src + 2, d0, d1);
-                        bool ok = ll_tag(a0) == tag && ll_tag(a1) == tag && ll_tag(b0) == tag && ll_tag(b1w) == tag;
-                        if (__all_sync(0xffffffffu, ok)) break;
-                        ll_load2(src, a0, a1);
-                        ll_load2(src + 2, b0, b1w);
-                        ok = ll_tag(c0) == tag && ll_tag(c1) == tag && ll_tag(d0) == tag && ll_tag(d1) == tag;
-                        if (__all_sync(0xffffffffu, ok)) { a0 = c0; a1 = c1; b0 = d0; b1w = d1; break; }
-                        if (abort_flag || ((++n & 255u) == 0 && clock64() - t0 > LL_TIMEOUT_CYCLES)) { CL_FAIL(); break; }
-                    }
-                }
-                hv[0] = ll_val(a0); hv[1] = ll_val(a1); hv[2] = ll_val(b0); hv[3] = ll_val(b1w);
-                CL_TRACE(16 + q, t, FU(hv[0]))
-                if (tracing && t >= p.trace_t0 && t < p.trace_t0 + p.trace_n) p.trace[(t - p.trace_t0) * CL_TRACE_STRIDE + 24 + q] = rounds;
+            const float hw = poll_h(t);
+            if (TRACE && warp == 0) { CL_TRACE(9, t, FU(hw)) }
+            bar_sync(1, CL_THREADS);                 // all 896 values of h_t are in h_s
+            bar_sync(6, CL_THREADS);                 // the critical warps have sent their logits: the schedulers are free now
+            float s[8];
+            row_dots(s, 6);
+            if (TRACE && warp == 0) { CL_TRACE(10, t, FU(s[0])) }
+            // 8 slots (rows 6, 7 are zero padding): transposing butterfly 16, 8, 4, then plain 2, 1
+            float v4[4], v2[2];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) v4[i] = (b4 ? s[i + 4] : s[i]) + __shfl_xor_sync(0xffffffffu, b4 ? s[i] : s[i + 4], 16);
+#pragma unroll
+            for (int i = 0; i < 2; ++i) v2[i] = (b3 ? v4[i + 2] : v4[i]) + __shfl_xor_sync(0xffffffffu, b3 ? v4[i] : v4[i + 2], 8);
+            float v1 = (b2 ? v2[1] : v2[0]) + __shfl_xor_sync(0xffffffffu, b2 ? v2[0] : v2[1], 4);
+            v1 += __shfl_xor_sync(0xffffffffu, v1, 2);
+            v1 += __shfl_xor_sync(0xffffffffu, v1, 1);
+            const int slot = (b4 ? 4 : 0) + (b3 ? 2 : 0) + (b2 ? 1 : 0);
+            if ((lane & 3) == 0 && slot < 6) hb_s[6 * warp + slot] = v1 + whh_bias;
+            bar_arrive(4, 160);                      // -> chain warp: W_hh h_t + b_hh of this warp's six rows is in hb_s
+            if (TRACE && warp == 0) { CL_TRACE(11, t, FU(v1)) }
+        }
+    } else if (warp < CL_MW) {
+        // =============================================================== F warps 4..6: poll, fc1 rows, fc2 partials
+        for (int t = 0; t < L; ++t) {
+            bar_sync(5, CL_THREADS);
+            poll_h(t);
+            bar_sync(1, CL_THREADS);
+            const float r = fc1_rows();
+            if (TRACE && warp == 4) { CL_TRACE(13, t, FU(r)) }
+            bar_sync(3, 128);                        // r_s holds all 16 relu(fc1) values of this CTA
+            const float s0 = fc2_partial_send(t & 1);
+            if (TRACE && warp == 4) { CL_TRACE(14, t, FU(s0)) }
+            if (!teacher) {
+                float lo[4];
+                rs_sum_ag_send(t, lo);
             }
-            if (TRACE && warp == 0) { CL_TRACE(9, t, FU(hv[3])) }
-            const float2 hd[4] = {make_float2(hv[0], hv[0]), make_float2(hv[1], hv[1]), make_float2(hv[2], hv[2]), make_float2(hv[3], hv[3])};
-            {
-                // ---- critical path: fc1 partials of the 16 own rows over this lane's 4 columns, then the warp-wide sums
-                float2 fa[CL_FR / 2];
-#pragma unroll
-                for (int i = 0; i < CL_FR / 2; ++i)
-                    fa[i] = ffma2(f1p[i][3], hd[3], ffma2(f1p[i][2], hd[2], ffma2(f1p[i][1], hd[1], ffma2(f1p[i][0], hd[0], make_float2(0.f, 0.f)))));
-                // transposing butterfly: 16 -> 8 -> 4 -> 2 -> 1 values per lane, then one plain round: lane pair l/2 holds row l/2
-                float v8[8], v4[4], v2[2];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) v8[i] = (b4 ? fa[i].y : fa[i].x) + __shfl_xor_sync(0xffffffffu, b4 ? fa[i].x : fa[i].y, 16);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) v4[i] = (b3 ? v8[i + 4] : v8[i]) + __shfl_xor_sync(0xffffffffu, b3 ? v8[i] : v8[i + 4], 8);
-#pragma unroll
-                for (int i = 0; i < 2; ++i) v2[i] = (b2 ? v4[i + 2] : v4[i]) + __shfl_xor_sync(0xffffffffu, b2 ? v4[i] : v4[i + 2], 4);
-                float v1 = (b1 ? v2[1] : v2[0]) + __shfl_xor_sync(0xffffffffu, b1 ? v2[0] : v2[1], 2);
-                v1 += __shfl_xor_sync(0xffffffffu, v1, 1);
-                if (!(lane & 1)) fpart[q * CL_FR + (lane >> 1)] = v1;
-                if (TRACE && warp == 0) { CL_TRACE(10, t, FU(v1)) }
-            }
-            bar_sync(3, CL_THREADS);                 // fpart holds all seven warps' fc1 partial sums
-            {
-                const float4 rv = fc1_r();
-                if (TRACE && warp == 0) { CL_TRACE(13, t, FU(rv.x)) }
-                const float s0 = fc2_partial_send(rv, par);
-                if (TRACE && warp == 0) { CL_TRACE(14, t, FU(s0)) }
-                // W_hh below must not be scheduled in front of the send: its inputs pass through an ordered no-op
-                asm volatile("" : "+f"(hv[0]), "+f"(hv[1]), "+f"(hv[2]), "+f"(hv[3]));
-            }
-            const float2 hd2[4] = {make_float2(hv[0], hv[0]), make_float2(hv[1], hv[1]), make_float2(hv[2], hv[2]), make_float2(hv[3], hv[3])};
-            {
-                // ---- off the critical path: W_hh rows of the own units x h_t (this warp's 128 columns)
-                float2 acc[CL_ROWS / 2];
-#pragma unroll
-                for (int r = 0; r < CL_ROWS / 2; ++r)
-                    acc[r] = ffma2(whp[r][3], hd2[3], ffma2(whp[r][2], hd2[2], ffma2(whp[r][1], hd2[1], ffma2(whp[r][0], hd2[0], make_float2(0.f, 0.f)))));
-                // transposing butterfly: 24 -> 12 -> 6 -> 3 values per lane, then two plain rounds
-                float v12[12], v6[6], v3[3];
-#pragma unroll
-                for (int i = 0; i < 12; ++i) v12[i] = (b4 ? acc[i].y : acc[i].x) + __shfl_xor_sync(0xffffffffu, b4 ? acc[i].x : acc[i].y, 16);
-#pragma unroll
-                for (int i = 0; i < 6; ++i) {
-                    const float send = b3 ? v12[i] : v12[i + 6];
-                    v6[i] = (b3 ? v12[i + 6] : v12[i]) + __shfl_xor_sync(0xffffffffu, send, 8);
-                }
-#pragma unroll
-                for (int i = 0; i < 3; ++i) {
-                    const float send = b2 ? v6[i] : v6[i + 3];
-                    v3[i] = (b2 ? v6[i + 3] : v6[i]) + __shfl_xor_sync(0xffffffffu, send, 4);
-                }
-#pragma unroll
-                for (int i = 0; i < 3; ++i) {
-                    v3[i] += __shfl_xor_sync(0xffffffffu, v3[i], 2);
-                    v3[i] += __shfl_xor_sync(0xffffffffu, v3[i], 1);
-                }
-                const int base = (b4 ? 12 : 0) + (b3 ? 6 : 0) + (b2 ? 3 : 0);
-                const int sel = lane & 3;
-                if (sel < 3) hhpart[q * CL_ROWS + base + sel] = sel == 0 ? v3[0] : (sel == 1 ? v3[1] : v3[2]);
-            }
-            bar_arrive(4, CL_THREADS);               // -> C warp: this warp's share of W_hh h_t is in hhpart
-            if (TRACE && warp == 0) { CL_TRACE(11, t, 0u) }
+            bar_arrive(6, CL_THREADS);
         }
     } else {
-        // =============================================================== C warp: the sequential chain
+        // =============================================================== C warp: the sequential chain (+ its share of fc1 / fc2)
         const int gu = cta * CL_U + (lane & 7);
-        const float bh_r = __ldg(p.b_hh + gu), bh_z = __ldg(p.b_hh + CL_H + gu), bh_n = __ldg(p.b_hh + 2 * CL_H + gu);
-        const float4 b2 = __ldg(reinterpret_cast<const float4*>(p.fc2_b + rank * CL_FR) + (lane & 3));
-        // reduce-scatter read: source ranks lane/4 + 8j, own logits 4 (lane%4) .. +3 ; all-gather send: piece lane%4 -> ranks lane/4 + 8j
-        const unsigned rs_src = inbox_a + (((lane >> 2) * CL_FR) + 4 * (lane & 3)) * 4;
-        unsigned ag_dst[2], ag_mbar[2];
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            ag_dst[j] = cl_mapa(lg_a + (rank * CL_FR + 4 * (lane & 3)) * 4, static_cast<unsigned>((lane >> 2) + 8 * j));
-            ag_mbar[j] = cl_mapa(mbar_a + 16, static_cast<unsigned>((lane >> 2) + 8 * j));
-        }
-        float hown = 0.f, hb_r = bh_r, hb_z = bh_z, hb_n = bh_n;      // W_hh h_{-1} = 0
+        float hown = 0.f;
+        float hb_r = __ldg(p.b_hh + gu), hb_z = __ldg(p.b_hh + CL_H + gu), hb_n = __ldg(p.b_hh + 2 * CL_H + gu);   // W_hh h_{-1} = 0
         float gh_r = 0.f, gh_z = 0.f;                                   // G_r + hb_r, G_z + hb_z: everything but E'[x]
         int x = CL_X_INIT, x_out = -1;
         int x_next = (teacher && L > 0) ? static_cast<int>(__ldg(p.x_in)) & (CL_Q - 1) : 0;
@@ -370,6 +401,11 @@ __global__ void __launch_bounds__(CL_THREADS, 1) ar_cluster_kernel(ClParams p) {
             const float* g = p.G + gu;
             gn_r = __ldg(g); gn_z = __ldg(g + CL_H); gn_n = __ldg(g + 2 * CL_H);
         }
+        // W_hh h_t + b_hh of the own units for the next step's gates (hb_s is written by warps 0..3 while the logits travel)
+        auto hb_load = [&]() {
+            bar_sync(4, 160);
+            hb_r = hb_s[lane & 7]; hb_z = hb_s[CL_U + (lane & 7)]; hb_n = hb_s[2 * CL_U + (lane & 7)];
+        };
         for (int t = 0; t < L; ++t) {
             const uint32_t tag = static_cast<uint32_t>(t) + 1u;
             const int par = t & 1;
@@ -396,7 +432,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) ar_cluster_kernel(ClParams p) {
                 hown = __fmaf_rn(z, __fsub_rn(hown, n), n);            // (1-z) n + z h
                 if (lane < CL_U) ll_store(p.hbuf + par * CL_H + cta * CL_U + lane, hown, tag);
             }
-            bar_arrive(5, CL_THREADS);               // M warps: h_t is on its way, start polling
+            bar_arrive(5, CL_THREADS);               // polling warps: h_t is on its way
             {
                 CL_TRACE(1, t, FU(hown))
                 if (lane == 0) {                       // arm this step's exchange phases (each receives 256 fp32)
@@ -410,57 +446,22 @@ __global__ void __launch_bounds__(CL_THREADS, 1) ar_cluster_kernel(ClParams p) {
                     if (p.out_codes) p.out_codes[t - 1] = x_out;
                 }
             }
-            bar_sync(3, CL_THREADS);                 // fpart complete
+            bar_sync(1, CL_THREADS);                 // all 896 values of h_t are in h_s
             float lo[4] = {0.f, 0.f, 0.f, 0.f};
             {
-                const float4 rv = fc1_r();
-                CL_TRACE(2, t, FU(rv.x))
-                const float s0 = fc2_partial_send(rv, par);
+                const float r = fc1_rows();
+                CL_TRACE(2, t, FU(r))
+                bar_sync(3, 128);                    // r_s complete
+                const float s0 = fc2_partial_send(par);
                 CL_TRACE(3, t, FU(s0))
-                // ---- reduce-scatter: 16 ranks x 16 own logits of column-partials
-                const long long t0 = clock64();
-                unsigned n = 0;
-                while (!mbar_try_wait(mbar_a + 8 * par, phase)) {
-                    if (abort_flag || ((++n & 63u) == 0 && clock64() - t0 > LL_TIMEOUT_CYCLES)) { CL_FAIL(); break; }
-                }
             }
             {
-                const float4 pa = *reinterpret_cast<const float4*>(&inboxf[0] + (rs_src - inbox_a) / 4 + par * CL_Q);
-                const float4 pb = *reinterpret_cast<const float4*>(&inboxf[0] + (rs_src - inbox_a) / 4 + par * CL_Q + 8 * CL_FR);
-                CL_TRACE(4, t, FU(pa.x))
-                lo[0] = pa.x + pb.x; lo[1] = pa.y + pb.y; lo[2] = pa.z + pb.z; lo[3] = pa.w + pb.w;
-#pragma unroll
-                for (int o = 4; o <= 16; o <<= 1) {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) lo[i] += __shfl_xor_sync(0xffffffffu, lo[i], o);
-                }
-                lo[0] += b2.x; lo[1] += b2.y; lo[2] += b2.z; lo[3] += b2.w;   // logits of classes 16 rank + 4 (lane % 4) + {0..3}
-                CL_TRACE(5, t, FU(lo[0]))
+                rs_sum_ag_send(t, lo);
                 if (p.out_logits != nullptr && cta < CL_S && lane < 4)
                     *reinterpret_cast<float4*>(p.out_logits + static_cast<int64_t>(t) * CL_Q + rank * CL_FR + 4 * lane) =
                         make_float4(lo[0], lo[1], lo[2], lo[3]);
-                if (!teacher) {
-#pragma unroll
-                    for (int j = 0; j < 2; ++j) st_async_v4(ag_dst[j] + par * CL_XBYTES, lo[0], lo[1], lo[2], lo[3], ag_mbar[j] + 8 * par);
-                }
             }
-            bar_sync(4, CL_THREADS);                 // W_hh h_t partial sums of the 7 M warps are in hhpart
-            {
-                float s = 0.f;
-                if (lane < CL_ROWS) {
-                    s = hhpart[lane];
-#pragma unroll
-                    for (int q = 1; q < CL_MW; ++q) s += hhpart[q * CL_ROWS + lane];
-                }
-                hb_r = __fadd_rn(__shfl_sync(0xffffffffu, s, lane & 7), bh_r);
-                hb_z = __fadd_rn(__shfl_sync(0xffffffffu, s, 8 + (lane & 7)), bh_z);
-                hb_n = __fadd_rn(__shfl_sync(0xffffffffu, s, 16 + (lane & 7)), bh_n);
-                // the next step's conditioning frame is already known here
-                const bool nf = (frame_left == 0);
-                gh_r = __fadd_rn(nf ? gn_r : g_r, hb_r);
-                gh_z = __fadd_rn(nf ? gn_z : g_z, hb_z);
-                CL_TRACE(6, t, FU(gh_z))
-            }
+            bar_arrive(6, CL_THREADS);               // W warps: go
             if (!teacher) {
                 // ---- all-gather of the logits, then softmax + inverse-CDF sample: lane l holds classes 8l..8l+7
                 const long long t0 = clock64();
@@ -494,6 +495,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) ar_cluster_kernel(ClParams p) {
                     }
                     const float excl = v - c[7];
                     const float thr = u_t * __shfl_sync(0xffffffffu, v, 31);
+                    hb_load();      // issued under the last shuffle's latency; the W warps finished during the all-gather hop
                     unsigned hit = 0;
 #pragma unroll
                     for (int i = 0; i < 8; ++i) hit |= (excl + c[i] > thr) ? (1u << i) : 0u;
@@ -503,6 +505,14 @@ __global__ void __launch_bounds__(CL_THREADS, 1) ar_cluster_kernel(ClParams p) {
                     x_out = x;
                     CL_TRACE(12, t, static_cast<unsigned>(x))
                 }
+            }
+            if (teacher) hb_load();
+            {
+                // the next step's conditioning frame is already known here
+                const bool nf = (frame_left == 0);
+                gh_r = __fadd_rn(nf ? gn_r : g_r, hb_r);
+                gh_z = __fadd_rn(nf ? gn_z : g_z, hb_z);
+                CL_TRACE(6, t, FU(gh_z))
             }
         }
         if (!abort_flag && cta == 0 && lane == 0 && x_out >= 0 && L > 0) {
