@@ -192,8 +192,10 @@ int vqcpc_debug_set_ar_poll_gap(int32_t packed);
  * first_poll_delay = cycles between a CTA's own publish of h_t and its first L2 poll; poll_mode is reserved (0): probes in flight beyond one were measured slower.
  * The cluster kernel's trace (vqcpc_debug_set_ar_trace) has 32 slots per step instead of 8. */
 int vqcpc_debug_set_ar_cluster(int32_t enable, int32_t first_poll_delay, int32_t poll_mode);
-/* Measures the bare 128-way LL exchange of the sample loop (no compute): mean SM cycles per exchange over `iters`
- * exchanges.  workspace >= 64 KiB.  Three exchanges per step are the latency floor bench.py reports. */
+/* Measures the bare grid-scope exchange of the sample loop that generate runs on this device, with no compute in between:
+ * mean SM cycles per exchange over `iters` exchanges.  Cluster kernel (default): 112 CTAs publish 8 LL words each and poll
+ * all 896 with the kernel's own first-probe delay -- ONE of these per step (floor = t_smem + one exchange).
+ * Round-1 kernel (vqcpc_debug_set_ar_cluster(0, ..)): the 128-way padded-slot exchange, three per step.  workspace >= 64 KiB. */
 int vqcpc_debug_exchange_floor(void* workspace, size_t workspace_bytes, int32_t iters, double* mean_cycles, void* stream);
 /* ---- log-mel front-end: the step before Encoder.encode.
  * Replaces wave_to_mel, /root/reference/preprocess.py:53-75 (the same arithmetic is inline in convert.py:54-70):

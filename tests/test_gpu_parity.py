@@ -363,6 +363,24 @@ def test_lstm_matches_oracle(B, Tp):
     assert torch.allclose(out.cpu(), ref, rtol=RTOL, atol=ATOL_C), float((out.cpu() - ref).abs().max())
 
 
+@pytest.mark.parametrize("B,T", [(64, 40), (130, 61), (600, 24), (2400, 12)])
+def test_persistent_batched_lstm_matches_oracle(B, T):
+    """Tensor-core modes run the whole recurrence of a batch of >= 64 utterances in ONE persistent tcgen05 launch
+    (csrc/lstm_persist.cu; unit slices of 8 / 16 / 32 hidden units, ragged last row tile, two row tiles per CTA at 2400): the
+    context must equal the oracle's LSTM on the code indices the GPU itself produced."""
+    enc, sd = make_encoder(512, True)
+    enc.gemm_mode = "bf16x3"
+    mel = fixtures.synthetic_mel(B, T, seed=B)
+    with torch.no_grad():
+        z, c, idx = enc.encode(mel.to(dev()))
+    sel = torch.cat([torch.arange(0, 6), torch.arange(B // 2, B // 2 + 6), torch.arange(B - 6, B)])
+    ref = oenc.lstm(sd["codebook.embedding"][idx[sel].cpu()], sd["rnn.weight_ih_l0"], sd["rnn.weight_hh_l0"],
+                    sd["rnn.bias_ih_l0"], sd["rnn.bias_hh_l0"])
+    err = float((c[sel].cpu() - ref).abs().max())
+    print(f"[persistent LSTM B={B}] max |c - oracle| = {err:.2e}")
+    assert torch.allclose(c[sel].cpu(), ref, rtol=RTOL, atol=ATOL_C), err
+
+
 # ------------------------------------------------------------------------------------------ vocoder
 def test_vocoder_conditioning_matches_oracle():
     voc, sd = make_vocoder()

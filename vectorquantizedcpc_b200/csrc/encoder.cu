@@ -542,6 +542,12 @@ __global__ void lstm_gate_kernel(const float* __restrict__ gates, const float* _
     }
 }
 
+static bool lstm_persist_enabled() {          // VQCPC_LSTM_PERSIST=0 selects the per-step-launch paths (A/B measurements)
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("VQCPC_LSTM_PERSIST"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v == 1;
+}
+
 // workspace: [header][table 512x1024][ll][gates B x 1024][cstate B x 256][h planes B x 512 bf16] x 2
 static size_t lstm_batched_bytes(int B) {
     if (B < LSTM_BATCHED_MIN_B) return 0;
@@ -576,6 +582,11 @@ int lstm_forward(const vqcpc_encoder_weights* w, const int64_t* idx, int B, int 
         const bool tc = (mode != VQCPC_GEMM_FP32) && (w->lstm_whh_p != nullptr);   // bf16 mode too: the recurrence stays bf16x3
         const int64_t total = static_cast<int64_t>(B) * (LSTM_H / 4);
         const unsigned grid = static_cast<unsigned>((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
+        if (tc && lstm_persist_enabled()) {
+            // one persistent launch for all T' steps (lstm_persist.cu); the gates buffer doubles as its counter scratch
+            return lstm_persist(table, idx, w->lstm_whh_p, B, Tp, hplanes, hplanes2, reinterpret_cast<unsigned*>(gates), out_c,
+                                &hdr->status, stream);
+        }
         if (tc && B >= LSTM_FUSED_MAX_B) {
             // Large batches: the step's product through the plain tcgen05 GEMM, then the fully coalesced gate kernel (the
             // fused epilogue below touches 32-byte pieces per thread, which loses to coalesced traffic once the step is

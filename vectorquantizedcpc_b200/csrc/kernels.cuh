@@ -34,6 +34,9 @@ bool gemm_ln_pair_supported(int N);
 int gemm_ln_pair(const void* a_planes, long long a_pitch, int a_lo_col, const void* w_planes, const float* ln_w, const float* ln_b,
                  void* out_planes, int out_pitch, float* out_f32, void* scratch, int M, int N, int K, int nseg, int* err_flag,
                  cudaStream_t stream);
+// lstm_persist.cu: the whole batched LSTM recurrence in one persistent tcgen05 launch (W_hh slices resident in shared memory)
+int lstm_persist(const float* table, const int64_t* idx, const void* whh_planes, int B, int Tp, void* planes0, void* planes1,
+                 unsigned* counters, float* out, int* err_flag, cudaStream_t stream);
 int split_planes(const float* x, long long ld, void* out, long long rows, int K, cudaStream_t stream);
 
 // encoder.cu

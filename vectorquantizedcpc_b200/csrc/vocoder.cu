@@ -573,6 +573,7 @@ int ar_cluster_launch(const vqcpc_vocoder_weights* w, const float* G, const floa
                       ll_word* hbuf, int* status, float* out_wav, int32_t* out_codes, float* out_logits, long long* trace,
                       int trace_cta, int trace_t0, int trace_n, cudaStream_t stream);
 void ar_cluster_set_poll(int delay, int mode);
+int ar_cluster_exchange_floor(void* workspace, size_t workspace_bytes, int iters, double* mean_cycles, cudaStream_t s);
 static size_t ar_ws_bytes() {
     const size_t ll = align_up(sizeof(ll_word) * AR_LL_WORDS, 256), ab = ar_batch_workspace_bytes();
     return sizeof(WorkspaceHeader) + (ll > ab ? ll : ab);
@@ -732,6 +733,9 @@ extern "C" int vqcpc_debug_exchange_floor(void* workspace, size_t workspace_byte
                                           void* stream) {
     using namespace vqcpc;
     VQ_ARG(workspace && mean_cycles && iters > 0, "exchange_floor: bad arguments");
+    // the exchange of the kernel generate actually runs: the cluster kernel's 112-CTA all-gather of h_t when it is in use
+    if (g_cl_enable && ar_cluster_supported())
+        return ar_cluster_exchange_floor(workspace, workspace_bytes, iters, mean_cycles, static_cast<cudaStream_t>(stream));
     const size_t need = sizeof(ll_word) * AR_LL_R + sizeof(long long) * AR_CTAS;
     VQ_ARG(workspace_bytes >= need, "exchange_floor: workspace too small");
     if (device_sm_count() < AR_CTAS) { set_error("exchange_floor: needs %d SMs", AR_CTAS); return VQCPC_ERR_DEVICE; }

@@ -527,6 +527,44 @@ __global__ void __launch_bounds__(CL_THREADS, 1) ar_cluster_kernel(ClParams p) {
     cluster.sync();      // nobody's shared memory disappears while a peer may still store into it
 }
 
+// ------------------------------------------------------------------------------------------------
+// Exchange floor of THIS kernel (diagnostic, bench.py): the bare grid-scope all-gather of a step -- every CTA publishes its 8
+// LL words, warps 0..6 poll the 896 words after the same first-probe delay, one CTA barrier -- with no compute in between.
+// per-step floor = t_smem + ONE such exchange.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(CL_THREADS, 1) exchange_floor_cluster_kernel(ll_word* buf, int iters, int poll_delay, long long* cycles) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), cta = blockIdx.x;
+    __shared__ int fail;
+    if (tid == 0) fail = 0;
+    __syncthreads();
+    const long long t0 = clock64();
+    for (int it = 1; it <= iters; ++it) {
+        const int par = it & 1;
+        if (warp == CL_MW) {
+            if (lane < CL_U) ll_store(buf + par * CL_H + cta * CL_U + lane, 0.f, static_cast<uint32_t>(it));
+            bar_arrive(5, CL_THREADS);
+        } else {
+            bar_sync(5, CL_THREADS);
+            if (poll_delay) { const long long t1 = clock64(); while (clock64() - t1 < poll_delay) {} }
+            const ll_word* src = buf + par * CL_H + 128 * warp + 4 * lane;
+            const long long ts = clock64();
+            for (;;) {
+                ll_word a0, a1, c0, c1;
+                ll_load2(src, a0, a1);
+                ll_load2(src + 2, c0, c1);
+                const uint32_t tag = static_cast<uint32_t>(it);
+                const bool ok = ll_tag(a0) == tag && ll_tag(a1) == tag && ll_tag(c0) == tag && ll_tag(c1) == tag;
+                if (__all_sync(0xffffffffu, ok)) break;
+                if (fail || clock64() - ts > LL_TIMEOUT_CYCLES) { fail = 1; break; }
+            }
+        }
+        bar_sync(1, CL_THREADS);
+    }
+    if (tid == 0) cycles[cta] = fail ? -1 : clock64() - t0;
+}
+
+int ar_cluster_exchange_floor(void* workspace, size_t workspace_bytes, int iters, double* mean_cycles, cudaStream_t s);
+
 // ------------------------------------------------------------------------------------------------ host
 static int g_cl_poll_delay = 300, g_cl_poll_mode = 0;
 int g_cl_enable = 1;
@@ -589,5 +627,28 @@ int ar_cluster_launch(const vqcpc_vocoder_weights* w, const float* G, const floa
 }
 
 void ar_cluster_set_poll(int delay, int mode) { g_cl_poll_delay = delay; g_cl_poll_mode = mode; }
+
+int ar_cluster_exchange_floor(void* workspace, size_t workspace_bytes, int iters, double* mean_cycles, cudaStream_t s) {
+    const size_t need = sizeof(ll_word) * 2 * CL_H + sizeof(long long) * CL_CTAS;
+    VQ_ARG(workspace_bytes >= need, "exchange_floor: workspace too small");
+    if (device_sm_count() < CL_CTAS) { set_error("exchange_floor: needs %d SMs", CL_CTAS); return VQCPC_ERR_DEVICE; }
+    ll_word* buf = static_cast<ll_word*>(workspace);
+    long long* cyc = reinterpret_cast<long long*>(buf + 2 * CL_H);
+    int delay = g_cl_poll_delay;
+    VQ_CUDA(cudaMemsetAsync(workspace, 0, need, s));
+    void* args[] = {&buf, &iters, &delay, &cyc};
+    VQ_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(exchange_floor_cluster_kernel), dim3(CL_CTAS), dim3(CL_THREADS), args, 0, s));
+    count_launch(1);
+    long long host[CL_CTAS];
+    VQ_CUDA(cudaMemcpyAsync(host, cyc, sizeof(host), cudaMemcpyDeviceToHost, s));
+    VQ_CUDA(cudaStreamSynchronize(s));
+    double sum = 0;
+    for (int i = 0; i < CL_CTAS; ++i) {
+        if (host[i] < 0) { set_error("exchange_floor: timed out"); return VQCPC_ERR_TIMEOUT; }
+        sum += static_cast<double>(host[i]);
+    }
+    *mean_cycles = sum / CL_CTAS / iters;
+    return VQCPC_OK;
+}
 
 }  // namespace vqcpc
