@@ -183,8 +183,7 @@ int vqcpc_vocoder_logits_tf(const vqcpc_vocoder_weights* w, const float* G, cons
 int vqcpc_debug_set_ar_trace(long long* device_buf, int32_t cta, int32_t first_step, int32_t n_steps);
 /* Tuning of the sample loop's exchanges: bits 0..11 cycles before the first poll round (default 400), bits 12..23
  * cycles between failed rounds (default 0), bits 24..27 cap on utterances interleaved per launch (0 = default 4),
- * bit 28 disables the batched (B >= 8) kernel, bit 29 its two-group (65..128 utterances per launch) variant, bit 30 routes
- * 65..128 utterances through the experimental tcgen05 kernel (csrc/vocoder_batch_tc.cu; correct, currently slower). */
+ * bit 28 disables the batched (B >= 8) kernel, bit 29 its two-group (65..128 utterances per launch) variant. */
 int vqcpc_debug_set_ar_poll_gap(int32_t packed);
 /* The single-utterance sample loop runs by default on the cluster kernel (csrc/vocoder_cluster.cu: 7 clusters of 16 CTAs,
  * one grid-scope exchange per step, fc1 / fc2 / sampling over DSMEM) whenever the device can co-schedule that grid.

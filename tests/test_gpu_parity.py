@@ -511,40 +511,6 @@ def test_vocoder_large_batch_kernel_matches_oracle(B, sel):
     assert float((tf[sel] - ref).abs().max()) < ATOL_LOGITS
 
 
-def test_vocoder_tcgen05_batched_kernel_matches_oracle():
-    """The experimental tcgen05 sample loop for 65..128 utterances (csrc/vocoder_batch_tc.cu, opt-in through bit 30 of
-    vqcpc_debug_set_ar_poll_gap): teacher-forced logits against the oracle, free-running samples inside the oracle's CDF
-    intervals, and agreement with the default (mma.sync, two-group) kernel."""
-    from vectorquantizedcpc_b200 import _lib
-    voc, sd = make_vocoder()
-    B, Tc, L = 100, 1, 200
-    codes, spk, u = fixtures.vocoder_inputs(B, Tc, seed=23, n_steps=L)
-    cd, sdv, ud = codes.to(dev()), spk.to(dev()), u.to(dev())
-    wav0, x0 = voc.generate(cd, sdv, uniforms=ud, n_steps=L, return_mulaw=True)
-    try:
-        _lib.check(_lib.lib().vqcpc_debug_set_ar_poll_gap(400 | (1 << 30)), "debug")
-        wav, x, logits = voc.generate(cd, sdv, uniforms=ud, n_steps=L, return_mulaw=True, return_logits=True)
-        x_in = torch.cat([torch.full((B, 1), 128, dtype=torch.int64, device=dev()), x[:, :-1]], dim=1)
-        tf = voc.forward(x_in, cd, sdv)
-    finally:
-        _lib.check(_lib.lib().vqcpc_debug_set_ar_poll_gap(400), "debug")
-    wav, x, logits, tf = wav.cpu(), x.cpu(), logits.cpu(), tf.cpu()
-    lut = torch.from_numpy(mulaw.mulaw_decode_lut(8))
-    assert torch.equal(wav, lut[x])
-    sel = [0, 31, 32, 63, 64, 99]
-    ref = ovoc.forward_teacher_forced(sd, x_in[sel].cpu(), codes[sel], spk[sel])
-    err = float((logits[sel] - ref).abs().max())
-    print(f"[tcgen05 batched generate B={B}] max |dlogit| vs oracle on replayed samples = {err:.3e}")
-    assert err < ATOL_LOGITS and float((tf[sel] - ref).abs().max()) < ATOL_LOGITS
-    cdf = ovoc.cdf_bounds(ref)
-    xs = x[sel]
-    hi = torch.gather(cdf, 2, xs[..., None])[..., 0]
-    lo = torch.where(xs > 0, torch.gather(cdf, 2, (xs - 1).clamp(min=0)[..., None])[..., 0], torch.zeros_like(hi))
-    ok = (u[sel].double() >= lo - 5e-5) & (u[sel].double() <= hi + 5e-5)
-    assert bool(ok.all())
-    assert float((x == x0.cpu()).float().mean()) > 0.97
-
-
 def test_vocoder_two_group_kernel_equals_single_group_kernel():
     """65..128 utterances per launch run as two interleaved groups (ar_batch2_kernel); per utterance the arithmetic is
     that of the single-group kernel, so samples and teacher-forced logits must agree bit for bit."""

@@ -5,7 +5,7 @@ from oracle import fixtures, vocoder as ovoc
 from vectorquantizedcpc_b200 import Vocoder, _lib
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 Tc = int(sys.argv[2]) if len(sys.argv) > 2 else 10
-flag = int(sys.argv[3]) if len(sys.argv) > 3 else 0        # e.g. 1073741824 (bit 30): tcgen05 kernel for 65..128 utterances
+flag = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 dev = torch.device("cuda:0")
 voc = Vocoder(); voc.load_state_dict(ovoc.init_state_dict(seed=13)); voc = voc.to(dev).eval()
 codes, spk, u = fixtures.vocoder_inputs(B, Tc, seed=0)

@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from oracle import fixtures, vocoder as ovoc
 from vectorquantizedcpc_b200 import Vocoder, _lib
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
-flag = int(sys.argv[2]) if len(sys.argv) > 2 else 0     # 1073741824 (bit 30): tcgen05 kernel for 65..128 utterances (stamps: G, barrier1, GEMM, epilogue, barrier2, fc2, codes wait)
+flag = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 dev = torch.device("cuda:0")
 voc = Vocoder(); voc.load_state_dict(ovoc.init_state_dict(seed=13)); voc = voc.to(dev).eval()
 codes, spk, u = fixtures.vocoder_inputs(B, 10, seed=0)

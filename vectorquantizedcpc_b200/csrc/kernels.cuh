@@ -53,9 +53,6 @@ int vq_lookup_auto(const float* x, const float* codebook, int64_t n, float* q, i
 
 // vocoder_batch.cu: batched sample loop (up to 64 utterances per launch, grid-barrier phases)
 size_t ar_batch_workspace_bytes();
-size_t ar_batch_tc_workspace_bytes();
-int ar_batch_tc_launch(const vqcpc_vocoder_weights* w, const float* G, const float* uniforms, const int64_t* x_in, int nb, int T2, int L,
-                       void* ws, int* status, float* out_wav, int32_t* out_codes, float* out_logits, cudaStream_t stream);
 int ensure_dyn_smem(const void* func, int bytes);   // per-(kernel, device) opt-in to large dynamic shared memory
 
 // persistent-kernel workspace header (first bytes of every workspace handed to a persistent kernel)

@@ -757,14 +757,13 @@ extern "C" int vqcpc_debug_exchange_floor(void* workspace, size_t workspace_byte
     *mean_cycles = sum / AR_CTAS / iters;
     return VQCPC_OK;
 }
-namespace vqcpc { extern int g_ab_two_group, g_ab_tc; }
+namespace vqcpc { extern int g_ab_two_group; }
 extern "C" int vqcpc_debug_set_ar_poll_gap(int32_t packed) {
     vqcpc::g_poll_gap = packed < 0 ? 0 : (packed & 0xffffff);
     const int cap = (packed >> 24) & 0xf;          // bits 24..27: cap on utterances per launch (0 = default)
     vqcpc::g_nb_cap = (cap >= 1 && cap <= vqcpc::AR_NB_MAX) ? cap : vqcpc::AR_NB_MAX;
     vqcpc::g_batch_min_b = ((packed >> 28) & 1) ? (1 << 30) : vqcpc::AR_BATCH_MIN_B;   // bit 28: disable the batched kernel
     vqcpc::g_ab_two_group = ((packed >> 29) & 1) ? 0 : 1;                                // bit 29: disable its two-group variant
-    vqcpc::g_ab_tc = (packed >> 30) & 1;                                                 // bit 30: 65..128 utterances on the tcgen05 kernel
     return VQCPC_OK;
 }
 extern "C" int vqcpc_debug_set_ar_cluster(int32_t enable, int32_t first_poll_delay, int32_t poll_mode) {

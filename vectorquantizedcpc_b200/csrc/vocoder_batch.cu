@@ -798,14 +798,12 @@ static size_t ab_ws_bytes() {
     return sizeof(float) * (2 * AB_H + AB_FC) * AB_B + sizeof(ll_word) * (AB_B * AB_Q + AB_B + AB_CTAS * 16);
 }
 size_t ar_batch_workspace_bytes() {
-    const size_t a = 2 * align_up(ab_ws_bytes(), 256), b = ar_batch_tc_workspace_bytes();
-    return a > b ? a : b;
+    return 2 * align_up(ab_ws_bytes(), 256);
 }
 
 long long* g_ab_trace = nullptr;
 int g_ab_trace_cta = 0, g_ab_trace_t0 = 0, g_ab_trace_n = 0;
 int g_ab_two_group = 1;      // debug switch (vqcpc_debug_set_ar_poll_gap bit 29 clears it)
-int g_ab_tc = 0;             // debug switch (bit 30 sets it): 65..128 utterances through the tcgen05 kernel (vocoder_batch_tc.cu)
 
 int ar_batch_run(const vqcpc_vocoder_weights* w, const float* G, const float* uniforms, const int64_t* x_in, int B, int T2,
                  int L, void* ws, int* status, float* out_wav, int32_t* out_codes, float* out_logits, cudaStream_t stream) {
@@ -832,12 +830,6 @@ int ar_batch_run(const vqcpc_vocoder_weights* w, const float* G, const float* un
         float* ow = out_wav ? out_wav + static_cast<int64_t>(b0) * L : nullptr;
         int32_t* oc = out_codes ? out_codes + static_cast<int64_t>(b0) * L : nullptr;
         float* ol = out_logits ? out_logits + static_cast<int64_t>(b0) * L * AB_Q : nullptr;
-        if (two && g_ab_tc) {
-            int rc = ar_batch_tc_launch(w, Gp, up, xp, nb, T2, L, ws, status, ow, oc, ol, stream);
-            if (rc) return rc;
-            b0 += nb;
-            continue;
-        }
         VQ_CUDA(cudaMemsetAsync(ws, 0, 2 * align_up(ab_ws_bytes(), 256), stream));
         if (!two) {
             AbParams p{};

@@ -324,13 +324,13 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vq_tc_kernel(const __grid_const
         int it = 0;
         const float emax = emax_s;
         int pend_code = 0;                                  // decided code of this lane's row of the PREVIOUS tile
-        long long pend_fr0 = -1;                            // first frame of this warp's 16 rows of that tile (-1: nothing pending)
+        int pend_tile = -1;                                 // tile whose output rows are still to be written (-1: none); 32-bit on purpose
+#define PEND_FR0() (static_cast<long long>(pend_tile) * VT_TF + quarter * 32 + ch * 16)
         uint32_t keymask;
         asm("mov.u32 %0, 0xfffffe00;" : "=r"(keymask));     // opaque to constant propagation on purpose (see the LOP3 below)
-        for (long long tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x, ++it) {
+        for (int tile = blockIdx.x; tile < static_cast<int>(n_tiles) && ok; tile += gridDim.x, ++it) {
             const int buf = it & 1;
             float b1 = INFINITY, b2 = INFINITY, xn = 0.f;
-            float hs1[2] = {INFINITY, INFINITY}, hs2[2] = {INFINITY, INFINITY};   // best two of each 128-code subset (half 0 / 1)
             if (e == 0) { VT_TRACE(7) }
             for (int half = 0; half < 2 && ok; ++half) {
                 ok = mbar_wait(&tfull_bar[half], tphase[half], p.err);
@@ -352,7 +352,7 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vq_tc_kernel(const __grid_const
                 // deferred output of the previous tile: its 8 gather loads are issued here and stored after this half's
                 // top-2 pass, so their latency hides behind ~2000 cycles of min/max work instead of ending every tile
                 float4 gq[8];
-                const bool flush_now = (half == 0) && (pend_fr0 >= 0) && !(p.debug & 2);
+                const bool flush_now = (half == 0) && (pend_tile >= 0) && !(p.debug & 2);
                 if (flush_now) {
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {
@@ -360,7 +360,7 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vq_tc_kernel(const __grid_const
                         const int code = __shfl_sync(0xffffffffu, pend_code, ch * 16 + r);
                         // volatile asm: the load must be ISSUED here (the compiler would otherwise sink it to its first use,
                         // the store after the pass, and expose the whole latency again)
-                        const float4* src = reinterpret_cast<const float4*>(p.codebook + code * VT_D) + (lane & 15);
+                        const float4* src = reinterpret_cast<const float4*>(p.codebook + (code < 0 ? 0 : code) * VT_D) + (lane & 15);
                         asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];"
                                      : "=f"(gq[k].x), "=f"(gq[k].y), "=f"(gq[k].z), "=f"(gq[k].w) : "l"(src));
                     }
@@ -399,14 +399,17 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vq_tc_kernel(const __grid_const
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {
                         const int r = 2 * k + (lane >> 4);
-                        if (pend_fr0 + r < p.n) reinterpret_cast<float4*>(p.out_q + (pend_fr0 + r) * VT_D)[lane & 15] = gq[k];
+                        const int code = __shfl_sync(0xffffffffu, pend_code, ch * 16 + r);      // < 0: flagged row, left to the rescan
+                        if (code >= 0 && PEND_FR0() + r < p.n) reinterpret_cast<float4*>(p.out_q + (PEND_FR0() + r) * VT_D)[lane & 15] = gq[k];
                     }
-                    pend_fr0 = -1;
+                    pend_tile = -1;
                 }
                 // fold this half's two chains into the tile's best two, with code indices (local index < 128, col0 a multiple of 128)
                 const float h1 = __uint_as_float(__float_as_uint(fminf(b1a, b1b)) + static_cast<uint32_t>(col0));
                 const float h2 = __uint_as_float(__float_as_uint(fminf(fmaxf(b1a, b1b), fminf(b2a, b2b))) + static_cast<uint32_t>(col0));
-                hs1[half] = h1; hs2[half] = h2;
+                // best two of this 128-code subset: straight to shared memory (the partner warp and the rare exact rescan read them
+                // there; keeping them in registers across the second half cost spills under the 128-register ceiling)
+                reinterpret_cast<float2*>(&part[buf][ch][row])[half] = make_float2(h1, h2);
                 b2 = fminf(fmaxf(b1, h1), fminf(b2, h2));
                 b1 = fminf(b1, h1);
                 if (e == 0) { if (half == 0) { VT_TRACE(9) } else { VT_TRACE(11) } }
@@ -415,18 +418,17 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vq_tc_kernel(const __grid_const
             // merge the two column halves: both warps of a row publish the best two of their two 128-code subsets, both read
             // the other's, so both know the row's best two candidates (and the best two of all four subsets) and each takes
             // half of the output work.
-            part[buf][ch][row] = make_float4(hs1[0], hs2[0], hs1[1], hs2[1]);
             bar_sync(1 + quarter, 64);            // only the two warps of this row quarter meet: a warp delayed by an exact
                                                   // re-decision does not hold up the other six
             if (e == 0) { VT_TRACE(12) }
-            const float4 o = part[buf][ch ^ 1][row];
             {
+                const float4 o = part[buf][ch ^ 1][row];
                 const float o1 = fminf(o.x, o.z), o2 = fminf(fmaxf(o.x, o.z), fminf(o.y, o.w));
                 const float n1 = fminf(b1, o1), n2 = fminf(fmaxf(b1, o1), fminf(b2, o2));
                 b1 = n1; b2 = n2;
             }
             int i1 = static_cast<int>(__float_as_uint(b1) & 511u);
-            const long long fr = tile * VT_TF + row;
+            const long long fr = static_cast<long long>(tile) * VT_TF + row;
             // warp (quarter, ch) finishes rows quarter*32 + ch*16 + [0, 16): lanes ch*16 .. ch*16+15 own them
             const bool owner = (lane >> 4) == ch && fr < p.n && !(p.debug & 2);
             // 2 x (coarse MMA error 2^-15 |x| max|e|  +  index-packing error 2^-14 |score|) = 2 eps
@@ -438,74 +440,35 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vq_tc_kernel(const __grid_const
             // the margin, and for negative scores the packed index even orders them backwards): the four 128-code subsets whose
             // best two are known are treated separately.  A subset whose SECOND best is outside the margin contributes at most
             // its best; a subset whose second best is inside may hide more and is rescanned completely.  All candidates get
-            // exact fp32 scores with the fp32 kernel's arithmetic; the first minimum wins (torch.argmin).  The warp works on one
-            // flagged frame at a time; ~0.1-0.3 % of the frames of an init-like codebook, none of a trained one.
-            unsigned fm = __ballot_sync(0xffffffffu, flagged);
-            while (fm) {
-                const int src = __ffs(fm) - 1;
-                fm &= fm - 1;
-                const float B1 = __shfl_sync(0xffffffffu, b1, src), mg = __shfl_sync(0xffffffffu, margin, src);
-                float f1[4], f2[4];
-                f1[0] = __shfl_sync(0xffffffffu, hs1[0], src); f2[0] = __shfl_sync(0xffffffffu, hs2[0], src);
-                f1[1] = __shfl_sync(0xffffffffu, hs1[1], src); f2[1] = __shfl_sync(0xffffffffu, hs2[1], src);
-                f1[2] = __shfl_sync(0xffffffffu, o.x, src); f2[2] = __shfl_sync(0xffffffffu, o.y, src);
-                f1[3] = __shfl_sync(0xffffffffu, o.z, src); f2[3] = __shfl_sync(0xffffffffu, o.w, src);
-                const float4* xr = reinterpret_cast<const float4*>(p.x + (tile * VT_TF + quarter * 32 + src) * VT_D);
-                float best = INFINITY;
-                int besti = VT_M;
-                auto consider = [&](int code) {
-                    const float4* er = reinterpret_cast<const float4*>(p.codebook + code * VT_D);
-                    float d = 0.f;
-#pragma unroll 1
-                    for (int k4 = 0; k4 < VT_D / 4; k4 += 8) {
-                        float4 xv[8], ev[8];
-#pragma unroll
-                        for (int u = 0; u < 8; ++u) { xv[u] = __ldg(xr + k4 + u); ev[u] = __ldg(er + k4 + u); }
-#pragma unroll
-                        for (int u = 0; u < 8; ++u) {
-                            d = fmaf(xv[u].x, ev[u].x, d); d = fmaf(xv[u].y, ev[u].y, d);
-                            d = fmaf(xv[u].z, ev[u].z, d); d = fmaf(xv[u].w, ev[u].w, d);
-                        }
-                    }
-                    const float sc = fmaf(-2.0f, d, e2s[code]);
-                    if (sc < best || (sc == best && code < besti)) { best = sc; besti = code; }
-                };
-                // subsets with one candidate inside the margin: lanes 0..3 score them in parallel
-                {
-                    const float mine1 = lane == 0 ? f1[0] : lane == 1 ? f1[1] : lane == 2 ? f1[2] : f1[3];
-                    const float mine2 = lane == 0 ? f2[0] : lane == 1 ? f2[1] : lane == 2 ? f2[2] : f2[3];
-                    if (lane < 4 && mine1 - B1 <= mg && !(mine2 - B1 <= mg)) consider(static_cast<int>(__float_as_uint(mine1) & 511u));
-                }
-                // subsets with two (hence possibly more) inside the margin: complete exact rescan, 4 codes per lane
-#pragma unroll 1
-                for (int sset = 0; sset < 4; ++sset) {
-                    if (!(f2[sset] - B1 <= mg)) continue;
-                    const int base = static_cast<int>(__float_as_uint(f1[sset]) & 0x180u);   // subset = 128 consecutive codes
-#pragma unroll 1
-                    for (int i = 0; i < 4; ++i) consider(base + 32 * i + lane);
-                }
-#pragma unroll
-                for (int off = 16; off > 0; off >>= 1) {
-                    const float ob = __shfl_xor_sync(0xffffffffu, best, off);
-                    const int oi = __shfl_xor_sync(0xffffffffu, besti, off);
-                    if (ob < best || (ob == best && oi < besti)) { best = ob; besti = oi; }
-                }
-                if (lane == src) i1 = besti;
+            // exact fp32 scores with the fp32 kernel's arithmetic; the first minimum wins (torch.argmin); ~0.1-0.3 % of the frames of
+            // an init-like codebook, none of a trained one.
+            // Flagged frames are NOT resolved here: the kernel stores the coarse winner as -1 - index, and vq_rescan_kernel
+            // (next launch in the stream) gives every such frame an exact fp32 argmin over all 512 codes.  (Resolved in place,
+            // a flagged frame held its warp for ~3 000 cycles and the bubble went through the whole tile pipeline: 2 600
+            // flagged frames per million cost an init-like run 12 %.)
+            if (owner) p.out_idx[fr] = flagged ? static_cast<long long>(-1 - i1) : static_cast<long long>(i1);
+            if (flagged) {
+                // what the rescan needs, parked in the frame's own (not yet written) output row: the best two of the four
+                // 128-code subsets, the coarse winner's key and the margin
+                const float4 own = part[buf][ch][row], oth = part[buf][ch ^ 1][row];
+                float4* st = reinterpret_cast<float4*>(p.out_q + fr * VT_D);
+                st[0] = make_float4(own.x, own.z, oth.x, oth.z);
+                st[1] = make_float4(own.y, own.w, oth.y, oth.w);
+                st[2] = make_float4(b1, margin, 0.f, 0.f);
             }
-            if (owner) p.out_idx[fr] = i1;
             __syncwarp();
-            pend_code = i1;
-            pend_fr0 = tile * VT_TF + quarter * 32 + ch * 16;
+            pend_code = flagged ? -1 : i1;                      // a flagged row is written by the rescan kernel, not by the deferred flush
+            pend_tile = tile;
             if (e == 0) { VT_TRACE(13) }
         }
-        if (pend_fr0 >= 0 && !(p.debug & 2)) {               // output of the last tile
+        if (pend_tile >= 0 && !(p.debug & 2)) {               // output of the last tile
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
                 const int r = 2 * k + (lane >> 4);
                 const int code = __shfl_sync(0xffffffffu, pend_code, ch * 16 + r);
-                if (pend_fr0 + r < p.n) {
+                if (code >= 0 && PEND_FR0() + r < p.n) {
                     const float4 v = __ldg(reinterpret_cast<const float4*>(p.codebook + code * VT_D) + (lane & 15));
-                    reinterpret_cast<float4*>(p.out_q + (pend_fr0 + r) * VT_D)[lane & 15] = v;
+                    reinterpret_cast<float4*>(p.out_q + (PEND_FR0() + r) * VT_D)[lane & 15] = v;
                 }
             }
         }
@@ -520,31 +483,105 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vq_tc_kernel(const __grid_const
     }
 }
 
-// One-time preparation of the codebook for vq_tc_kernel (one thread per code): bf16 hi/lo planes of -2 e_m, |e_m|^2 with
-// the fp32 kernel's arithmetic (sequential FMA over k), and the 32-byte row of the |e|^2 MMA block.
-__global__ void vq_prepare_kernel(const float* __restrict__ codebook, __nv_bfloat16* __restrict__ planes, float* __restrict__ e2,
-                                  __nv_bfloat16* __restrict__ aug_b) {
-    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+// Exact pass over the frames vq_tc_kernel flagged (out_idx < 0): one warp per flagged frame, exact fp32 scores of the candidate
+// codes with the fp32 kernel's arithmetic (sequential FMA over k, score = |e|^2 - 2 x.e), first minimum wins (torch.argmin
+// semantics); rewrites the index and the quantised row.  Unflagged frames cost this kernel one coalesced 8-byte read each.
+__global__ void __launch_bounds__(256) vq_rescan_kernel(const float* __restrict__ x, const float* __restrict__ codebook,
+                                                        const float* __restrict__ e2, float* __restrict__ out_q,
+                                                        long long* __restrict__ out_idx, long long n) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const long long n_warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+    for (long long base = warp * 32; base < n; base += n_warps * 32) {
+        const long long mine = base + lane < n ? out_idx[base + lane] : 0;
+        unsigned fm = __ballot_sync(0xffffffffu, mine < 0);
+        while (fm) {
+            const int src = __ffs(fm) - 1;
+            fm &= fm - 1;
+            const long long fr = base + src;
+            // Candidates (parked in the frame's output row by vq_tc_kernel): f1 / f2 = best two coarse keys of the four 128-code
+            // subsets, B1 = the coarse winner, mg = 2 eps.  Every coarse score is within eps of its exact fp32 score, so only codes
+            // with a coarse key <= B1 + mg can win.  A subset whose SECOND best is outside the margin contributes at most its
+            // best (lanes 0..3 score those in parallel); a subset whose second best is inside may hide more and is rescanned
+            // completely (4 codes per lane).  Typical flagged frame: two exact scores.
+            const float4* st = reinterpret_cast<const float4*>(out_q + fr * VT_D);
+            const float4 s1 = st[0], s2 = st[1], s3 = st[2];
+            const float f1[4] = {s1.x, s1.y, s1.z, s1.w}, f2[4] = {s2.x, s2.y, s2.z, s2.w};
+            const float B1 = s3.x, mg = s3.y;
+            const float4* xr = reinterpret_cast<const float4*>(x + fr * VT_D);
+            float best = INFINITY;
+            int besti = VT_M;
+            auto consider = [&](int code) {
+                const float4* er = reinterpret_cast<const float4*>(codebook + code * VT_D);
+                float d = 0.f;
+#pragma unroll
+                for (int k4 = 0; k4 < VT_D / 4; ++k4) {
+                    const float4 xv = __ldg(xr + k4), ev = __ldg(er + k4);
+                    d = fmaf(xv.x, ev.x, d); d = fmaf(xv.y, ev.y, d); d = fmaf(xv.z, ev.z, d); d = fmaf(xv.w, ev.w, d);
+                }
+                const float sc = fmaf(-2.0f, d, __ldg(e2 + code));
+                if (sc < best || (sc == best && code < besti)) { best = sc; besti = code; }
+            };
+            {
+                const float mine1 = lane == 0 ? f1[0] : lane == 1 ? f1[1] : lane == 2 ? f1[2] : f1[3];
+                const float mine2 = lane == 0 ? f2[0] : lane == 1 ? f2[1] : lane == 2 ? f2[2] : f2[3];
+                if (lane < 4 && mine1 - B1 <= mg && !(mine2 - B1 <= mg)) consider(static_cast<int>(__float_as_uint(mine1) & 511u));
+            }
+#pragma unroll 1
+            for (int sset = 0; sset < 4; ++sset) {
+                if (!(f2[sset] - B1 <= mg)) continue;
+                const int sb = static_cast<int>(__float_as_uint(f1[sset]) & 0x180u);   // subset = 128 consecutive codes
+#pragma unroll 1
+                for (int i = 0; i < 4; ++i) consider(sb + 32 * i + lane);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const float ob = __shfl_xor_sync(0xffffffffu, best, off);
+                const int oi = __shfl_xor_sync(0xffffffffu, besti, off);
+                if (ob < best || (ob == best && oi < besti)) { best = ob; besti = oi; }
+            }
+            if (lane == 0) out_idx[fr] = besti;
+            if (lane < 16) reinterpret_cast<float4*>(out_q + fr * VT_D)[lane] = __ldg(reinterpret_cast<const float4*>(codebook + besti * VT_D) + lane);
+        }
+    }
+}
+
+// Preparation of the codebook for vq_tc_kernel (one warp per code, 14 -> ~3 us per call): bf16 hi/lo planes of -2 e_m (lanes: two
+// dimensions each, coalesced), |e_m|^2 with the fp32 kernel's arithmetic (ONE lane, sequential FMA over k -- the order is part
+// of the exactness contract), and the 32-byte row of the |e|^2 MMA block.
+__global__ void __launch_bounds__(256) vq_prepare_kernel(const float* __restrict__ codebook, __nv_bfloat16* __restrict__ planes,
+                                                         float* __restrict__ e2, __nv_bfloat16* __restrict__ aug_b) {
+    const int m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (m >= VT_M) return;
     const float* e = codebook + m * VT_D;
-    float s = 0.f;
-    for (int k = 0; k < VT_D; ++k) {
-        const float ev = __ldg(e + k);
-        s = fmaf(ev, ev, s);
-        const float v = -2.0f * ev;
-        const __nv_bfloat16 h = __float2bfloat16_rn(v);
-        planes[m * 2 * VT_D + k] = h;
-        planes[m * 2 * VT_D + VT_D + k] = __float2bfloat16_rn(v - __bfloat162float(h));
+    const float2 ev = __ldg(reinterpret_cast<const float2*>(e) + lane);
+    {
+        const float v0 = -2.0f * ev.x, v1 = -2.0f * ev.y;
+        const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
+        reinterpret_cast<__nv_bfloat162*>(planes + m * 2 * VT_D)[lane] = __halves2bfloat162(h0, h1);
+        reinterpret_cast<__nv_bfloat162*>(planes + m * 2 * VT_D + VT_D)[lane] =
+            __halves2bfloat162(__float2bfloat16_rn(v0 - __bfloat162float(h0)), __float2bfloat16_rn(v1 - __bfloat162float(h1)));
     }
-    e2[m] = s;
-    const float hs = 0.5f * s;
-    const __nv_bfloat16 h0 = __float2bfloat16_rn(hs);
-    const float r1 = hs - __bfloat162float(h0);
-    const __nv_bfloat16 h1 = __float2bfloat16_rn(r1);
-    const __nv_bfloat16 h2 = __float2bfloat16_rn(r1 - __bfloat162float(h1));
-    __nv_bfloat16* brow = aug_b + m * 16;
-    for (int k = 0; k < 16; ++k) brow[k] = __float2bfloat16_rn(0.f);
-    brow[0] = h0; brow[1] = h1; brow[2] = h2; brow[8] = h0; brow[9] = h1; brow[10] = h2;
+    // sequential sum over k on lane 0, the values handed over by shuffles
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < VT_D / 2; ++k) {
+        const float a = __shfl_sync(0xffffffffu, ev.x, k), b = __shfl_sync(0xffffffffu, ev.y, k);
+        s = fmaf(a, a, s);
+        s = fmaf(b, b, s);
+    }
+    if (lane == 0) {
+        e2[m] = s;
+        const float hs = 0.5f * s;
+        const __nv_bfloat16 h0 = __float2bfloat16_rn(hs);
+        const float r1 = hs - __bfloat162float(h0);
+        const __nv_bfloat16 h1 = __float2bfloat16_rn(r1);
+        const __nv_bfloat16 h2 = __float2bfloat16_rn(r1 - __bfloat162float(h1));
+        __nv_bfloat16* brow = aug_b + m * 16;
+        for (int k = 0; k < 16; ++k) brow[k] = __float2bfloat16_rn(0.f);
+        brow[0] = h0; brow[1] = h1; brow[2] = h2; brow[8] = h0; brow[9] = h1; brow[10] = h2;
+    }
 }
 
 typedef CUresult (*PFN_encodeTiled2)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -569,7 +606,7 @@ int vq_lookup_tc(const float* x, const float* codebook, int64_t n, float* q, int
     }
     float* e2_ws = reinterpret_cast<float*>(static_cast<unsigned char*>(planes_ws) + VT_CB_BYTES);
     __nv_bfloat16* aug_ws = reinterpret_cast<__nv_bfloat16*>(static_cast<unsigned char*>(planes_ws) + VT_CB_BYTES + VT_M * 4);
-    vq_prepare_kernel<<<VT_M / 64, 64, 0, stream>>>(codebook, static_cast<__nv_bfloat16*>(planes_ws), e2_ws, aug_ws);
+    vq_prepare_kernel<<<VT_M * 32 / 256, 256, 0, stream>>>(codebook, static_cast<__nv_bfloat16*>(planes_ws), e2_ws, aug_ws);
     VQ_CUDA(cudaGetLastError());
     count_launch(1);
     CUtensorMap map;
@@ -582,6 +619,7 @@ int vq_lookup_tc(const float* x, const float* codebook, int64_t n, float* q, int
     if (r != CUDA_SUCCESS) { set_error("vq_lookup_tc: cuTensorMapEncodeTiled failed (%d)", static_cast<int>(r)); return VQCPC_ERR_CUDA; }
     if (int rc_attr = ensure_dyn_smem(reinterpret_cast<const void*>(vq_tc_kernel), static_cast<int>(VT_SMEM))) return rc_attr;
     const long long n_tiles = (n + VT_TF - 1) / VT_TF;
+    VQ_ARG(n_tiles < (1LL << 31) - 1024, "vq_lookup_tc: too many frames for one call (%lld)", static_cast<long long>(n));
     const int sms = device_sm_count();
     static int dbg = -1;
     if (dbg < 0) { const char* e = getenv("VQCPC_VQ_DEBUG"); dbg = e ? atoi(e) : 0; }
@@ -597,7 +635,14 @@ int vq_lookup_tc(const float* x, const float* codebook, int64_t n, float* q, int
     VqTcParams p{x, codebook, e2_ws, reinterpret_cast<const uint4*>(aug_ws), q, idx, err, static_cast<long long>(n), dbg, d_trace, trace_iters};
     vq_tc_kernel<<<static_cast<unsigned>(n_tiles < sms ? n_tiles : sms), VT_THREADS, VT_SMEM, stream>>>(map, p);
     VQ_CUDA(cudaGetLastError());
-    count_launch(1);
+    {
+        const long long warps = (n + 31) / 32;
+        const long long blocks = (warps + 7) / 8;
+        vq_rescan_kernel<<<static_cast<unsigned>(blocks < 8LL * sms ? blocks : 8LL * sms), 256, 0, stream>>>(x, codebook, e2_ws, q,
+                                                                                                             reinterpret_cast<long long*>(idx), n);
+        VQ_CUDA(cudaGetLastError());
+    }
+    count_launch(2);
     if (d_trace != nullptr) {
         std::vector<long long> h(16 * static_cast<size_t>(trace_iters));
         VQ_CUDA(cudaMemcpyAsync(h.data(), d_trace, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost, stream));
