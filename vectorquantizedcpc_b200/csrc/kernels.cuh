@@ -6,9 +6,15 @@
 namespace vqcpc {
 
 // gemm_f32.cu
+// split-K for the latency case M <= 256 (optional): splitk_ws = gemm_splitk_ws_bytes(M, N) bytes of scratch planes,
+// splitk_counters = SPLITK_COUNTERS zeroed words (self-resetting after each GEMM)
+constexpr int SPLITK_COUNTERS = 60;
 int gemm_dense(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias, float* C, int64_t ldc,
-               int64_t M, int N, int K, cudaStream_t stream);
-int gemm_conv(const float* mel, int B, int T, int Cin, const float* W, float* C, int Cout, cudaStream_t stream);
+               int64_t M, int N, int K, cudaStream_t stream, void* splitk_ws = nullptr, size_t splitk_ws_bytes = 0,
+               unsigned* splitk_counters = nullptr);
+int gemm_conv(const float* mel, int B, int T, int Cin, const float* W, float* C, int Cout, cudaStream_t stream,
+              void* splitk_ws = nullptr, size_t splitk_ws_bytes = 0, unsigned* splitk_counters = nullptr);
+size_t gemm_splitk_ws_bytes(int64_t M, int N);
 
 // gemm_tc.cu  (tcgen05 / TMEM / TMA)
 int gemm_tc(const void* a_planes, const void* w_planes, const float* bias, float* C, long long ldc, int M, int N, int K,

@@ -204,6 +204,9 @@ class Vocoder(nn.Module):
         return self._packed
 
     # -------------------------------------------------------------------------------- hot path
+    BATCHED_MIN_B = 8        # from this many utterances a launch runs the batched tensor-core kernels (csrc/vocoder.cu)
+    BATCHED_GROUP = 128      # utterances per launch of the two-group batched kernel
+
     def _check_inputs(self, z: Tensor, speaker: Tensor):
         _lib.require_cuda(z, "z")
         _lib.require_cuda(speaker, "speaker")
@@ -295,20 +298,59 @@ class Vocoder(nn.Module):
                 raise ValueError(f"uniforms must be ({B}, {L}), got {tuple(uniforms.shape)}")
             uniforms = uniforms.to(torch.float32).contiguous()
         lib = _lib.lib()
-        wav = torch.empty(B, L, device=dev)
-        codes = torch.empty(B, L, dtype=torch.int32, device=dev) if return_mulaw else None
-        logits = torch.empty(B, L, 256, device=dev) if return_logits else None
-        with torch.cuda.device(dev):
-            st = lib.vqcpc_vocoder_generate(C.byref(w), _lib.ptr(G), _lib.ptr(uniforms), B, 2 * Tc, L, _lib.ptr(ws),
-                                            ws.numel(), _lib.ptr(wav), _lib.ptr(codes), _lib.ptr(logits),
-                                            _lib.current_stream_ptr())
-            _lib.check(st, "Vocoder.generate")
-            if B > 0:
-                _lib.check(lib.vqcpc_check_status(_lib.ptr(ws), _lib.current_stream_ptr()), "Vocoder.generate")
-        if lengths is not None and B > 0 and L > 0:
-            valid = (torch.arange(L, device=dev)[None, :] <
-                     (torch.as_tensor(lengths, device=dev).to(torch.int64) * (2 * self.conf.rnnms.upsampling_t))[:, None])
-            wav = wav * valid
+        up2 = 2 * self.conf.rnnms.upsampling_t
+        if lengths is not None and B > 1 and L > 0:
+            # Ragged batch: length-sorted launch groups, each run only as far as ITS longest utterance (per-utterance stop for
+            # the single-utterance kernel, buckets of the batched kernels' natural group size otherwise) -- vocoder.py:69
+            # "cannot batch" / SURVEY 8f row 2.  The sample loop is causal, so an utterance's valid prefix does not depend on
+            # how far its launch runs; samples beyond 320*lengths[b] are 0.
+            len_host = torch.as_tensor(lengths).to("cpu", torch.int64)
+            steps = torch.clamp(len_host * up2, max=L)
+            order = torch.argsort(steps, descending=True, stable=True)
+            group = 1 if B < self.BATCHED_MIN_B else self.BATCHED_GROUP
+            wav = torch.zeros(B, L, device=dev)
+            codes = torch.zeros(B, L, dtype=torch.int32, device=dev) if return_mulaw else None
+            logits = torch.zeros(B, L, 256, device=dev) if return_logits else None
+            with torch.cuda.device(dev):
+                for g0 in range(0, B, group):
+                    sel = order[g0:g0 + group]
+                    Lg = int(steps[sel[0]])                      # the group's longest utterance
+                    if Lg == 0:
+                        continue
+                    seld = sel.to(dev)
+                    nb = int(sel.numel())
+                    whole = nb == B and Lg == L
+                    Gg = G if whole else G.index_select(0, seld)
+                    ug = uniforms if whole else uniforms.index_select(0, seld)[:, :Lg].contiguous()
+                    wg = torch.empty(nb, Lg, device=dev)
+                    cg = torch.empty(nb, Lg, dtype=torch.int32, device=dev) if return_mulaw else None
+                    lg = torch.empty(nb, Lg, 256, device=dev) if return_logits else None
+                    st = lib.vqcpc_vocoder_generate(C.byref(w), _lib.ptr(Gg), _lib.ptr(ug), nb, 2 * Tc, Lg, _lib.ptr(ws), ws.numel(),
+                                                    _lib.ptr(wg), _lib.ptr(cg), _lib.ptr(lg), _lib.current_stream_ptr())
+                    _lib.check(st, "Vocoder.generate")
+                    # every launch resets the workspace status word: read it before the next one (a launch is milliseconds)
+                    _lib.check(lib.vqcpc_check_status(_lib.ptr(ws), _lib.current_stream_ptr()), "Vocoder.generate")
+                    valid = torch.arange(Lg, device=dev)[None, :] < steps[sel].to(dev)[:, None]
+                    wav[seld, :Lg] = wg * valid
+                    if return_mulaw:
+                        codes[seld, :Lg] = cg * valid
+                    if return_logits:
+                        logits[seld, :Lg] = lg * valid[..., None]
+        else:
+            wav = torch.empty(B, L, device=dev)
+            codes = torch.empty(B, L, dtype=torch.int32, device=dev) if return_mulaw else None
+            logits = torch.empty(B, L, 256, device=dev) if return_logits else None
+            with torch.cuda.device(dev):
+                st = lib.vqcpc_vocoder_generate(C.byref(w), _lib.ptr(G), _lib.ptr(uniforms), B, 2 * Tc, L, _lib.ptr(ws),
+                                                ws.numel(), _lib.ptr(wav), _lib.ptr(codes), _lib.ptr(logits),
+                                                _lib.current_stream_ptr())
+                _lib.check(st, "Vocoder.generate")
+                if B > 0:
+                    _lib.check(lib.vqcpc_check_status(_lib.ptr(ws), _lib.current_stream_ptr()), "Vocoder.generate")
+            if lengths is not None and B > 0 and L > 0:
+                valid = (torch.arange(L, device=dev)[None, :] <
+                         (torch.as_tensor(lengths, device=dev).to(torch.int64) * up2)[:, None])
+                wav = wav * valid
         out = (wav,)
         if return_mulaw:
             out += (codes.to(torch.int64),)
