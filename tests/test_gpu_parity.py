@@ -832,6 +832,37 @@ def test_vq_duplicated_and_collapsed_codebook_rows():
     assert torch.equal(torch.cat(parts), idx)
 
 
+def test_vq_flag_list_overflow_and_degenerate_scales():
+    """The tensor-core search lists the frames whose coarse minimum is not alone inside the error margin and rescans them exactly.
+    Degenerate inputs must go the same way as ordinary ones: more flagged frames than the list holds (a fully collapsed codebook:
+    every frame is a 512-way tie -> the rescan falls back to sweeping the indices), all-zero frames (margin 0), and scores of
+    magnitude 1e-30 (where the saturating compare of the epilogue cannot be trusted and the frame is flagged by a guard).
+    Reference: the exact fp32 kernel on the same inputs (chunks below 8192 frames), itself pinned to the oracle elsewhere."""
+    g = torch.Generator().manual_seed(5)
+    n = 40000                                            # > VQ_TC_FLAG_CAP (32768)
+
+    def both(x, cb):
+        q, idx = run_vq(x[None], cb)
+        parts = [run_vq(x[None, lo:lo + 4000], cb) for lo in range(0, n, 4000)]
+        qs = torch.cat([p[0].reshape(-1, 64) for p in parts]); ix = torch.cat([p[1].reshape(-1) for p in parts])
+        assert torch.equal(idx.reshape(-1), ix) and torch.equal(q.reshape(-1, 64), qs)
+        return idx.reshape(-1)
+
+    # 1. collapsed codebook: all rows identical -> first index everywhere, every frame flagged
+    cb = torch.randn(1, 64, generator=g).repeat(512, 1)
+    x = torch.randn(n, 64, generator=g)
+    idx = both(x, cb)
+    assert bool((idx == 0).all())
+    # 2. ordinary codebook, frames of zeros mixed in (score = |e|^2 exactly, margin = 1e-6 max|e|^2 only)
+    cb = torch.randn(512, 64, generator=g)
+    x = torch.randn(n, 64, generator=g)
+    x[::7] = 0.0
+    idx = both(x, cb)
+    assert bool((idx[::7] == int((cb * cb).sum(1).argmin())).all())
+    # 3. everything scaled to 1e-15: scores ~1e-30
+    both(x * 1e-15, cb * 1e-15)
+
+
 def test_ragged_batches_against_the_oracle_directly():
     """SURVEY 8f row 2, compared with the ORACLE on the unpadded utterances (not with another CUDA run)."""
     voc, sd = make_vocoder()

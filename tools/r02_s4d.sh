@@ -1,0 +1,4 @@
+#!/bin/bash
+mkdir -p gpurun_out
+python tools/vq_flags.py 1000000 init > gpurun_out/vq_flags.log 2>&1
+python tools/vq_flags.py 1000000 trained >> gpurun_out/vq_flags.log 2>&1

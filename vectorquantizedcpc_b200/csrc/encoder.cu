@@ -324,7 +324,7 @@ __global__ void __launch_bounds__(256) vq_lookup_small_kernel(const float* __res
         }
     };
     float best = INFINITY;
-    int besti = VQ_M;
+    int besti = 0;                                    // all-NaN scores: index 0, as the large fp32 kernel (never out of range)
     stage(0, 0);
     __syncthreads();
     for (int chunk = 0; chunk < VQ_M / 32; ++chunk) {
@@ -569,6 +569,7 @@ static int lstm_launch(LstmParams prm, void* ll_mem, cudaStream_t stream) {
 // state, writes h_t into the output sequence and re-splits it into the planes the next step's GEMM reads.
 // ------------------------------------------------------------------------------------------------
 constexpr int LSTM_BATCHED_MIN_B = 64;
+constexpr int LSTM_CLUSTER_MAX_B = 9;              // one wave of 16-CTA clusters on 148 SMs
 constexpr int LSTM_FUSED_MAX_B = 2048;            // below: fused tcgen05 step kernel; from here on: GEMM + coalesced gate kernel
 
 __global__ void lstm_gate_kernel(const float* __restrict__ gates, const float* __restrict__ table,
@@ -704,6 +705,10 @@ int lstm_forward(const vqcpc_encoder_weights* w, const int64_t* idx, int B, int 
         }
         return VQCPC_OK;
     }
+    // a few utterances: one 16-CTA cluster each, h over DSMEM (lstm_cluster.cu); VQCPC_LSTM_CLUSTER16=0 keeps the L2 kernel
+    static const int use_cluster = [] { const char* e = getenv("VQCPC_LSTM_CLUSTER16"); return (e && e[0] == '0') ? 0 : 1; }();
+    if (use_cluster && B <= LSTM_CLUSTER_MAX_B && lstm_cluster_supported())
+        return lstm_cluster_launch(table, idx, w->lstm_w_hh, B, Tp, out_c, &hdr->status, stream);
     LstmParams prm{};
     prm.table = table;
     prm.idx = idx;

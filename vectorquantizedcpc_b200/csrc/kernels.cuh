@@ -43,6 +43,10 @@ int gemm_ln_pair(const void* a_planes, long long a_pitch, int a_lo_col, const vo
 // lstm_persist.cu: the whole batched LSTM recurrence in one persistent tcgen05 launch (W_hh slices resident in shared memory)
 int lstm_persist(const float* table, const int64_t* idx, const void* whh_planes, int B, int Tp, void* planes0, void* planes1,
                  unsigned* counters, float* out, int* err_flag, cudaStream_t stream);
+// lstm_cluster.cu: latency LSTM for a few utterances, one 16-CTA cluster each, h_t over DSMEM
+int lstm_cluster_supported();
+int lstm_cluster_launch(const float* table, const int64_t* idx, const float* w_hh, int B, int Tp, float* out, int* status,
+                        cudaStream_t stream);
 int split_planes(const float* x, long long ld, void* out, long long rows, int K, cudaStream_t stream);
 
 // encoder.cu
@@ -51,7 +55,9 @@ int vq_lookup(const float* x, const float* codebook, int64_t n, int n_codes, int
               cudaStream_t stream);
 // tensor-core search (vq_tc.cu); vq_lookup_auto picks it for n >= VQ_TC_MIN_FRAMES when scratch is provided
 constexpr int64_t VQ_TC_MIN_FRAMES = 8192;
-constexpr size_t VQ_TC_PLANES_BYTES = 512 * 128 * 2 + 512 * 4 + 512 * 32;   // bf16 hi/lo planes of -2e | |e|^2 fp32 | |e|^2 MMA block
+constexpr int VQ_TC_FLAG_CAP = 32768;           // frames the main kernel can list for the exact rescan before it falls back to a sweep
+// bf16 hi/lo planes of -2e | |e|^2 fp32 | |e|^2 MMA block | flagged-frame list (count + 3 pad words + VQ_TC_FLAG_CAP frame numbers)
+constexpr size_t VQ_TC_PLANES_BYTES = 512 * 128 * 2 + 512 * 4 + 512 * 32 + 16 + 4 * VQ_TC_FLAG_CAP;
 int vq_lookup_tc(const float* x, const float* codebook, int64_t n, float* q, int64_t* idx, void* planes_ws, int* err,
                  cudaStream_t stream);
 int vq_lookup_auto(const float* x, const float* codebook, int64_t n, float* q, int64_t* idx, void* planes_ws, int* err,

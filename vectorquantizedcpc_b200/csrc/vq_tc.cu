@@ -11,10 +11,15 @@
 //   * one thread issues tcgen05.mma (M=128, N=256, K=16): three K-segments (x_hi e_hi + x_hi e_lo + x_lo e_hi) per
 //     256-code half; the two halves of a tile are the two TMEM accumulators, so the MMAs of one half overlap the
 //     argmin epilogue of the other;
-//   * epilogue warps (thread = frame) read the accumulators with tcgen05.ld, add |e|^2 and keep the best two
-//     candidates.  The coarse scores carry an error <= 2^-15 |x| max|e|; a frame whose best two are closer than twice
-//     that is rescanned: exact fp32 scores of all 512 codes (same arithmetic as the fp32 kernel), first minimum wins.
-//     A frame outside the margin provably has its coarse winner as exact winner, so the result equals the fp32 path's.
+//   * epilogue warps (thread = frame) read the accumulators with tcgen05.ld (|e|^2 already folded in by one extra MMA
+//     step) and, per 32-column chunk, take the minimum (FMNMX3, half an ALU-pipe instruction per score) and then COUNT
+//     the scores within the margin of it on the FMA pipe: c = sat(BIG (min + margin - s)) is exactly 1 or 0 and
+//     acc += c (1024 + column) carries count and index in one fp32 (two full-rate FFMA per score; the earlier top-2
+//     tracking with the index packed into the mantissa cost 3.5 half-rate instructions per score and bounded the kernel).
+//     The coarse scores carry an error eps <= 2^-15 |x| max|e| + 2^-21 max|e|^2; the margin is 2 eps.  Exactly one score
+//     within the margin of the minimum: that code is provably the exact fp32 winner.  Anything else (near-ties, exact
+//     ties, duplicated codebook rows, NaN) puts the frame on a list and vq_rescan_kernel gives it exact fp32 scores of
+//     all 512 codes (the fp32 kernel's arithmetic), first minimum wins -- so the result equals the fp32 path's.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <stdlib.h>
@@ -43,8 +48,10 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
-    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    // suspend-time hint (ns): the warp may sleep in hardware until the phase completes instead of re-issuing the probe -- the
+    // kernel is issue-slot bound and a sixth of its executed instructions were spin probes
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(20000u) : "memory");
     return ok != 0;
 }
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, int* err) {
@@ -103,11 +110,20 @@ __device__ __forceinline__ float fmin3(float a, float b, float c) {
     asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));     // FMNMX3
     return d;
 }
+__device__ __forceinline__ float ffma_sat(float a, float b, float c) {
+    float d;
+    asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));       // FFMA.SAT: NaN -> +0
+    return d;
+}
 }  // namespace vqtc
 using namespace vqtc;
 
 constexpr int VT_D = 64, VT_M = 512, VT_TF = 128;
-constexpr int VT_MMA_WARP = 0, VT_CONV_WARP0 = 1, VT_EPI_WARP0 = 5, VT_EPI_WARPS = 8, VT_THREADS = (5 + VT_EPI_WARPS) * 32;
+// 12 warps = 384 threads: the register file then allows 168 registers per thread (13 warps round to 512 threads = 128), which the
+// epilogue needs to keep two 32-column TMEM reads in flight
+constexpr int VT_MMA_WARP = 0, VT_CONV_WARP0 = 1, VT_CONV_WARPS = 3, VT_EPI_WARP0 = 4, VT_EPI_WARPS = 8, VT_THREADS = (4 + VT_EPI_WARPS) * 32;
+constexpr int VT_CONV_ROWS = VT_CONV_WARPS * 4;              // rows covered per converter pass (8 threads per row)
+constexpr int VT_CONV_ITEMS = (VT_TF + VT_CONV_ROWS - 1) / VT_CONV_ROWS;
 constexpr uint32_t VT_CB_HALF = 256 * 128;                 // bytes of one (plane, half) block of the codebook: 256 rows x 128 B
 constexpr uint32_t VT_CB_BYTES = 4 * VT_CB_HALF;           // hi/lo x two halves = 128 KB
 constexpr uint32_t VT_PLANE = VT_TF * 128;                 // 16 KB: one bf16 plane of an x tile
@@ -125,6 +141,7 @@ struct VqTcParams {
     const uint4* aug_b;      // (512, 2) the |e|^2 MMA block, 32 bytes per code
     float* out_q;            // (n, 64)
     int64_t* out_idx;        // (n,)
+    unsigned* flags;         // [0] = number of flagged frames, [4 ..] their frame numbers (first VQ_TC_FLAG_CAP of them)
     int* err;
     long long n;
     int debug;               // bit 0: skip the argmin math, bit 1: skip the gather/output, bit 2: converters skip the x loads
@@ -139,7 +156,7 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vq_tc_kernel(const __grid_const
     __shared__ __align__(16) float e2s[VT_M];
     __shared__ float xnorm[2][VT_TF];
     __shared__ float emax_s;
-    __shared__ float4 part[2][2][VT_TF];              // [tile parity][column half][row]: top-2 keys of the two 128-code subsets
+    __shared__ float2 part[2][2][VT_TF];              // [tile parity][column half][row]: (minimum, count/index sum) of that warp's 256 codes
 
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(vt_smem) + 1023) & ~uintptr_t(1023));
     unsigned char* cb_s = smem;                       // [plane][half][256 rows][128 B]
@@ -148,11 +165,18 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vq_tc_kernel(const __grid_const
     unsigned char* aug_b = aug_a + VT_AUG_A;          // [512 rows][16 bf16]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (p.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) p.trace[14] = clock64();      // kernel entry
+    if (p.trace != nullptr && threadIdx.x == 0) {            // every CTA: entry stamps (clock, global timer), SM id
+        long long* c = p.trace + 16 * p.trace_iters + 8 * blockIdx.x;
+        unsigned smid; unsigned long long gt;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        c[0] = clock64(); c[2] = static_cast<long long>(gt); c[4] = smid;
+    }
 
     if (threadIdx.x == 0) {
         mbar_init(&cb_bar, 1);
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&xfull_bar[i], 4);              // one arrival per converter warp
+            mbar_init(&xfull_bar[i], VT_CONV_WARPS);  // one arrival per converter warp
             mbar_init(&xempty_bar[i], 1);             // tcgen05.commit
             mbar_init(&tfull_bar[i], 1);              // tcgen05.commit
             mbar_init(&tempty_bar[i], VT_EPI_WARPS);  // one arrival per epilogue warp
@@ -241,18 +265,19 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vq_tc_kernel(const __grid_const
         }
     } else if (warp < VT_EPI_WARP0) {
         // ------------------------------------------------------------------ converters: fp32 x -> bf16 hi/lo planes
-        // item (row r, 16-byte chunk c): thread t of the 128 handles c = t & 7, rows r = (t >> 3) + 16 j, j < 8.
+        // item (row r, 16-byte chunk c): thread t of the 96 handles c = t & 7, rows r = (t >> 3) + 12 j, j < 11 (r < 128).
         const int t = threadIdx.x - 32 * VT_CONV_WARP0;
         const int c = t & 7, r0 = t >> 3;
         uint32_t ephase[2] = {0, 0};
         bool ok = true;
         int it = 0;
-        float4 cur[8][2];
-        auto load_tile = [&](long long tile, float4 (&dst)[8][2]) {
+        float4 cur[VT_CONV_ITEMS][2];
+        auto load_tile = [&](long long tile, float4 (&dst)[VT_CONV_ITEMS][2]) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const long long fr = tile * VT_TF + r0 + 16 * j;
-                if (fr < p.n && !(p.debug & 4)) {
+            for (int j = 0; j < VT_CONV_ITEMS; ++j) {
+                const int r = r0 + VT_CONV_ROWS * j;
+                const long long fr = tile * VT_TF + r;
+                if (r < VT_TF && fr < p.n && !(p.debug & 4)) {
                     const float4* src = reinterpret_cast<const float4*>(p.x + fr * VT_D + 8 * c);
                     dst[j][0] = __ldg(src); dst[j][1] = __ldg(src + 1);
                 } else {
@@ -271,11 +296,13 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vq_tc_kernel(const __grid_const
             if (warp == VT_CONV_WARP0) { VT_TRACE(5) }
             unsigned char* hi = x_s + buf * VT_XBUF;
             unsigned char* lo = hi + VT_PLANE;
-            float ssq[8];
+            float ssq[VT_CONV_ITEMS];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
+            for (int j = 0; j < VT_CONV_ITEMS; ++j) {
+                ssq[j] = 0.f;
                 if (p.debug & 16) break;
-                const int r = r0 + 16 * j;
+                const int r = r0 + VT_CONV_ROWS * j;
+                if (r >= VT_TF) break;                     // last pass: only the first rows exist (uniform per 8-lane row group)
                 const float v[8] = {cur[j][0].x, cur[j][0].y, cur[j][0].z, cur[j][0].w, cur[j][1].x, cur[j][1].y, cur[j][1].z, cur[j][1].w};
                 __nv_bfloat162 h2[4], l2[4];
                 float ss = 0.f;
@@ -295,15 +322,16 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vq_tc_kernel(const __grid_const
                 *reinterpret_cast<uint4*>(hi + off) = *reinterpret_cast<const uint4*>(h2);
                 *reinterpret_cast<uint4*>(lo + off) = *reinterpret_cast<const uint4*>(l2);
             }
-            // row norms: the 8 lanes of a row reduce their partial sums (all 8 rows' butterflies interleaved)
+            // row norms: the 8 lanes of a row reduce their partial sums (all rows' butterflies interleaved)
 #pragma unroll
             for (int o = 1; o < 8; o <<= 1) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) ssq[j] += __shfl_xor_sync(0xffffffffu, ssq[j], o);
+                for (int j = 0; j < VT_CONV_ITEMS; ++j) ssq[j] += __shfl_xor_sync(0xffffffffu, ssq[j], o);
             }
             if (c == 0) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) xnorm[buf][r0 + 16 * j] = sqrtf(ssq[j]);
+                for (int j = 0; j < VT_CONV_ITEMS; ++j)
+                    if (r0 + VT_CONV_ROWS * j < VT_TF) xnorm[buf][r0 + VT_CONV_ROWS * j] = sqrtf(ssq[j]);
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic-proxy stores -> visible to tcgen05.mma
             __syncwarp();
@@ -312,25 +340,31 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vq_tc_kernel(const __grid_const
             if (tile + gridDim.x < n_tiles) load_tile(tile + gridDim.x, cur);   // prefetch the next tile's rows
         }
     } else {
-        // ------------------------------------------------------------------ epilogue: top-2 argmin, exact recheck, gather
+        // ------------------------------------------------------------------ epilogue: min + count-within-margin, gather
         // 8 warps: warp e handles TMEM lanes 32*(warp & 3) (its frame rows) and columns [128*ch, 128*ch + 128) of each
-        // 256-code accumulator, ch = e >> 2.  The code index is packed into the 9 low mantissa bits of the score, so
-        // tracking the best two (value, index) pairs is three FMNMX per element; two independent chains per thread.
-        // The packing perturbs a score by <= 2^-14 relative, which is added to the recheck margin.
+        // 256-code accumulator, ch = e >> 2.  State per subset of scores: (m, acc) = (minimum, sum over the scores within the
+        // margin of m of 1024 + code) -- acc in [1024, 1536) means "exactly one candidate, code acc - 1024".  Two subsets
+        // merge exactly: the one whose minimum is lower by more than the margin wins outright (the other holds no candidate);
+        // minima within the margin of each other mean at least two candidates (acc := 4096, invalid).
         const int e = warp - VT_EPI_WARP0, quarter = warp & 3, ch = e >> 2;
         const int row = quarter * 32 + lane;
         uint32_t tphase[2] = {0, 0};
         bool ok = true;
         int it = 0;
         const float emax = emax_s;
+        constexpr float BIG = 1.2676506e30f;               // 2^100: BIG * (thr - s) saturates to exactly 1 for any s < thr (|thr| >= 2^-76)
         int pend_code = 0;                                  // decided code of this lane's row of the PREVIOUS tile
         int pend_tile = -1;                                 // tile whose output rows are still to be written (-1: none); 32-bit on purpose
 #define PEND_FR0() (static_cast<long long>(pend_tile) * VT_TF + quarter * 32 + ch * 16)
-        uint32_t keymask;
-        asm("mov.u32 %0, 0xfffffe00;" : "=r"(keymask));     // opaque to constant propagation on purpose (see the LOP3 below)
+#define VT_MERGE(m_, acc_, mo_, acco_)                                                              \
+        {                                                                                           \
+            const float d_ = (mo_) - (m_);                                                          \
+            (acc_) = fabsf(d_) <= margin ? 4096.f : (d_ < -margin ? (acco_) : (acc_));              \
+            (m_) = fminf((m_), (mo_));                                                              \
+        }
         for (int tile = blockIdx.x; tile < static_cast<int>(n_tiles) && ok; tile += gridDim.x, ++it) {
             const int buf = it & 1;
-            float b1 = INFINITY, b2 = INFINITY, xn = 0.f;
+            float mt = INFINITY, acct = 0.f, margin = 0.f, mgB = 0.f;
             if (e == 0) { VT_TRACE(7) }
             for (int half = 0; half < 2 && ok; ++half) {
                 ok = mbar_wait(&tfull_bar[half], tphase[half], p.err);
@@ -339,24 +373,28 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vq_tc_kernel(const __grid_const
                 tphase[half] ^= 1;
                 tc_fence_after();
                 if (e == 0) { if (half == 0) { VT_TRACE(8) } else { VT_TRACE(10) } }
-                if (half == 0) xn = xnorm[buf][row];      // read now: the converters may refill this slot two tiles later
+                if (half == 0) {
+                    // read now: the converters may refill this slot two tiles later.  margin = 2 eps:
+                    // 2 x (bf16x3 product error 2^-15 |x| max|e|  +  accumulation of |e|^2 into the fp32 accumulator 2^-21 max|e|^2)
+                    const float xn = xnorm[buf][row];
+                    margin = 6.2e-5f * xn * emax + 1.0e-6f * emax * emax;
+                    mgB = margin * BIG;
+                }
                 // software-pipelined TMEM reads: the load of chunk c+1 is in flight while chunk c is reduced
                 const int col0 = half * 256 + ch * 128;
                 const uint32_t tbase = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + col0;
-                // the index packed into the score is LOCAL to these 128 columns -- an immediate of the LOP3; a global index
-                // costs one integer add per element on the same (half-rate) pipe as the min/max.  It is widened when the
-                // half is folded into (b1, b2).
-                float b1a = INFINITY, b2a = INFINITY, b1b = INFINITY, b2b = INFINITY;
+                float mh = INFINITY, acch = 0.f;
                 uint32_t va[32], vb[32];
                 tc_ld32(tbase, va);
-                // deferred output of the previous tile: its 8 gather loads are issued here and stored after this half's
-                // top-2 pass, so their latency hides behind ~2000 cycles of min/max work instead of ending every tile
-                float4 gq[8];
-                const bool flush_now = (half == 0) && (pend_tile >= 0) && !(p.debug & 2);
+                // deferred output of the previous tile, half of it per accumulator half: 4 gather loads (two rows each) are issued
+                // here and stored after this half's pass, so their latency hides behind the min/count work instead of ending
+                // every tile (all 8 at once held 32 registers through the pass and cost the TMEM double buffering)
+                float4 gq[4];
+                const bool flush_now = (pend_tile >= 0) && !(p.debug & 2);
                 if (flush_now) {
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        const int r = 2 * k + (lane >> 4);                   // row within this warp's 16
+                    for (int k = 0; k < 4; ++k) {
+                        const int r = 2 * (4 * half + k) + (lane >> 4);      // row within this warp's 16
                         const int code = __shfl_sync(0xffffffffu, pend_code, ch * 16 + r);
                         // volatile asm: the load must be ISSUED here (the compiler would otherwise sink it to its first use,
                         // the store after the pass, and expose the whole latency again)
@@ -372,24 +410,26 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vq_tc_kernel(const __grid_const
                     uint32_t (&vn)[32] = (cc & 1) ? va : vb;
                     tc_wait_ld();
                     if (cc + 1 < 4) tc_ld32(tbase + 32 * (cc + 1), vn);
+                    // pass 1 (ALU pipe): minimum of the 32 scores, two chains of FMNMX3
+                    float ma = fmin3(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]));
+                    float mb = fmin3(__uint_as_float(v[16]), __uint_as_float(v[17]), __uint_as_float(v[18]));
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        float k[4];
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const float sc = __uint_as_float(v[j + q]);                       // |e|^2 - 2 x.e, all from the tensor cores
-                            // one LOP3: (bits & mask) | local index -- the mask sits in a register so that the index can be
-                            // the instruction's single immediate operand
-                            uint32_t kb;
-                            asm("lop3.b32 %0, %1, %2, %3, 0xea;" : "=r"(kb) : "r"(__float_as_uint(sc)), "r"(keymask), "r"(32 * cc + j + q));
-                            k[q] = __uint_as_float(kb);
-                        }
-                        // merge the pair (lo <= hi) into the running (b1 <= b2): 5 ops per 2 elements
-                        const float lo0 = fminf(k[0], k[1]), hi0 = fmaxf(k[0], k[1]);
-                        b2a = fmin3(fmaxf(b1a, lo0), b2a, hi0); b1a = fminf(b1a, lo0);
-                        const float lo1 = fminf(k[2], k[3]), hi1 = fmaxf(k[2], k[3]);
-                        b2b = fmin3(fmaxf(b1b, lo1), b2b, hi1); b1b = fminf(b1b, lo1);
+                    for (int j = 3; j < 15; j += 2) {
+                        ma = fmin3(ma, __uint_as_float(v[j]), __uint_as_float(v[j + 1]));
+                        mb = fmin3(mb, __uint_as_float(v[16 + j]), __uint_as_float(v[16 + j + 1]));
                     }
+                    const float mc = fmin3(ma, mb, fminf(__uint_as_float(v[15]), __uint_as_float(v[31])));
+                    // pass 2 (FMA pipe): c = sat(BIG (mc + margin - s)) in {0, 1};  acc += c (1024 + local column)
+                    const float tb = fmaf(mc, BIG, mgB);
+                    float a4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        // in place: the score's register becomes its indicator (keeps both TMEM buffers within the register budget)
+                        asm("fma.rn.sat.f32 %0, %0, %1, %2;" : "+r"(v[j]) : "f"(-BIG), "f"(tb));
+                        a4[j & 3] = fmaf(__uint_as_float(v[j]), static_cast<float>(1024 + 32 * cc + j), a4[j & 3]);
+                    }
+                    const float accc = (a4[0] + a4[1]) + (a4[2] + a4[3]);
+                    VT_MERGE(mh, acch, mc, accc)
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -397,64 +437,44 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vq_tc_kernel(const __grid_const
                 if (flush_now) {
                     // one fully coalesced 256-byte row per 16 lanes
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        const int r = 2 * k + (lane >> 4);
+                    for (int k = 0; k < 4; ++k) {
+                        const int r = 2 * (4 * half + k) + (lane >> 4);
                         const int code = __shfl_sync(0xffffffffu, pend_code, ch * 16 + r);      // < 0: flagged row, left to the rescan
                         if (code >= 0 && PEND_FR0() + r < p.n) reinterpret_cast<float4*>(p.out_q + (PEND_FR0() + r) * VT_D)[lane & 15] = gq[k];
                     }
-                    pend_tile = -1;
+                    if (half == 1) pend_tile = -1;
                 }
-                // fold this half's two chains into the tile's best two, with code indices (local index < 128, col0 a multiple of 128)
-                const float h1 = __uint_as_float(__float_as_uint(fminf(b1a, b1b)) + static_cast<uint32_t>(col0));
-                const float h2 = __uint_as_float(__float_as_uint(fminf(fmaxf(b1a, b1b), fminf(b2a, b2b))) + static_cast<uint32_t>(col0));
-                // best two of this 128-code subset: straight to shared memory (the partner warp and the rare exact rescan read them
-                // there; keeping them in registers across the second half cost spills under the 128-register ceiling)
-                reinterpret_cast<float2*>(&part[buf][ch][row])[half] = make_float2(h1, h2);
-                b2 = fminf(fmaxf(b1, h1), fminf(b2, h2));
-                b1 = fminf(b1, h1);
+                // fold this half's 128 codes into the tile state; the column index becomes the code index (an invalid acc stays invalid:
+                // 0 + col0 < 1024, 4096 + col0 >= 2048)
+                const float accg = acch + static_cast<float>(col0);
+                VT_MERGE(mt, acct, mh, accg)
                 if (e == 0) { if (half == 0) { VT_TRACE(9) } else { VT_TRACE(11) } }
             }
             if (!ok) break;
-            // merge the two column halves: both warps of a row publish the best two of their two 128-code subsets, both read
-            // the other's, so both know the row's best two candidates (and the best two of all four subsets) and each takes
-            // half of the output work.
-            bar_sync(1 + quarter, 64);            // only the two warps of this row quarter meet: a warp delayed by an exact
-                                                  // re-decision does not hold up the other six
+            // merge the two column halves of the row: both warps publish their state and read the other's (the merge is
+            // symmetric, so both arrive at the same result) and each takes half of the output work.
+            part[buf][ch][row] = make_float2(mt, acct);
+            bar_sync(1 + quarter, 64);            // only the two warps of this row quarter meet
             if (e == 0) { VT_TRACE(12) }
             {
-                const float4 o = part[buf][ch ^ 1][row];
-                const float o1 = fminf(o.x, o.z), o2 = fminf(fmaxf(o.x, o.z), fminf(o.y, o.w));
-                const float n1 = fminf(b1, o1), n2 = fminf(fmaxf(b1, o1), fminf(b2, o2));
-                b1 = n1; b2 = n2;
+                const float2 o = part[buf][ch ^ 1][row];
+                VT_MERGE(mt, acct, o.x, o.y)
             }
-            int i1 = static_cast<int>(__float_as_uint(b1) & 511u);
             const long long fr = static_cast<long long>(tile) * VT_TF + row;
             // warp (quarter, ch) finishes rows quarter*32 + ch*16 + [0, 16): lanes ch*16 .. ch*16+15 own them
             const bool owner = (lane >> 4) == ch && fr < p.n && !(p.debug & 2);
-            // 2 x (coarse MMA error 2^-15 |x| max|e|  +  index-packing error 2^-14 |score|) = 2 eps
-            const float margin = 6.2e-5f * xn * emax + 1.3e-4f * fmaxf(fabsf(b1), fabsf(b2));
-            const bool flagged = owner && (b2 - b1 <= margin);
-            // Exactness.  Every coarse score is within eps of its exact fp32 score, so a code k can only beat (or tie) the coarse
-            // winner exactly if c_k <= c_1 + 2 eps.  Not flagged: no such code exists and the coarse winner is the strict exact
-            // winner.  Flagged (near-tie, exact tie, duplicated or collapsed codebook rows -- any NUMBER of codes may sit inside
-            // the margin, and for negative scores the packed index even orders them backwards): the four 128-code subsets whose
-            // best two are known are treated separately.  A subset whose SECOND best is outside the margin contributes at most
-            // its best; a subset whose second best is inside may hide more and is rescanned completely.  All candidates get
-            // exact fp32 scores with the fp32 kernel's arithmetic; the first minimum wins (torch.argmin); ~0.1-0.3 % of the frames of
-            // an init-like codebook, none of a trained one.
-            // Flagged frames are NOT resolved here: the kernel stores the coarse winner as -1 - index, and vq_rescan_kernel
-            // (next launch in the stream) gives every such frame an exact fp32 argmin over all 512 codes.  (Resolved in place,
-            // a flagged frame held its warp for ~3 000 cycles and the bubble went through the whole tile pipeline: 2 600
-            // flagged frames per million cost an init-like run 12 %.)
-            if (owner) p.out_idx[fr] = flagged ? static_cast<long long>(-1 - i1) : static_cast<long long>(i1);
+            // Exactness.  Every coarse score is within eps of its exact fp32 score and margin = 2 eps, so a code can only beat
+            // (or tie) the coarse winner exactly if its coarse score is <= min + margin.  acc in [1024, 1536): the minimum is the
+            // ONLY such score, hence the strict exact winner.  Otherwise the frame is listed for vq_rescan_kernel (next launch in
+            // the stream): exact fp32 argmin over all 512 codes.  |BIG thr| < 1e10 (scores of magnitude < 1e-20, where BIG (thr - s)
+            // might not saturate) goes the same way.  ~0.1-0.3 % of the frames of an init-like codebook, none of a trained one.
+            const bool valid = acct >= 1024.f && acct < 1536.f && fabsf(fmaf(mt, BIG, mgB)) >= 1e10f;
+            const int i1 = static_cast<int>(acct) - 1024;
+            const bool flagged = owner && !valid;
+            if (owner) p.out_idx[fr] = flagged ? -1LL : static_cast<long long>(i1);
             if (flagged) {
-                // what the rescan needs, parked in the frame's own (not yet written) output row: the best two of the four
-                // 128-code subsets, the coarse winner's key and the margin
-                const float4 own = part[buf][ch][row], oth = part[buf][ch ^ 1][row];
-                float4* st = reinterpret_cast<float4*>(p.out_q + fr * VT_D);
-                st[0] = make_float4(own.x, own.z, oth.x, oth.z);
-                st[1] = make_float4(own.y, own.w, oth.y, oth.w);
-                st[2] = make_float4(b1, margin, 0.f, 0.f);
+                const unsigned pos = atomicAdd(p.flags, 1u);
+                if (pos < static_cast<unsigned>(VQ_TC_FLAG_CAP)) p.flags[4 + pos] = static_cast<unsigned>(fr);
             }
             __syncwarp();
             pend_code = flagged ? -1 : i1;                      // a flagged row is written by the rescan kernel, not by the deferred flush
@@ -473,76 +493,104 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vq_tc_kernel(const __grid_const
             }
         }
     }
+#undef VT_MERGE
 #undef VT_TRACE
     tc_fence_before();
     __syncthreads();
     if (p.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) p.trace[15] = clock64();      // all roles done
+    if (p.trace != nullptr && threadIdx.x == 0) {
+        long long* c = p.trace + 16 * p.trace_iters + 8 * blockIdx.x;
+        unsigned long long gt;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        c[1] = clock64(); c[3] = static_cast<long long>(gt);
+    }
     if (warp == VT_MMA_WARP) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
     }
 }
 
-// Exact pass over the frames vq_tc_kernel flagged (out_idx < 0): one warp per flagged frame, exact fp32 scores of the candidate
-// codes with the fp32 kernel's arithmetic (sequential FMA over k, score = |e|^2 - 2 x.e), first minimum wins (torch.argmin
-// semantics); rewrites the index and the quantised row.  Unflagged frames cost this kernel one coalesced 8-byte read each.
-__global__ void __launch_bounds__(256) vq_rescan_kernel(const float* __restrict__ x, const float* __restrict__ codebook,
-                                                        const float* __restrict__ e2, float* __restrict__ out_q,
-                                                        long long* __restrict__ out_idx, long long n) {
+// Exact pass over the frames vq_tc_kernel flagged: one warp per flagged frame, exact fp32 scores of ALL 512 codes with the fp32
+// kernel's arithmetic (sequential FMA over k, score = |e|^2 - 2 x.e), first minimum wins (torch.argmin semantics); writes the
+// index and the quantised row.  The frames come from the list the main kernel appended to (under one per thousand); if the list
+// overflowed (or frame numbers do not fit 32 bits) every frame's index is inspected instead (out_idx < 0 = flagged).  A CTA
+// that has work stages the fp32 codebook in shared memory once (row pitch 65 words: lane = code reads are conflict-free), so a
+// frame costs ~2 000 warp instructions instead of 16 dependent L2 round trips.
+constexpr int VT_RS_PITCH = VT_D + 1;
+constexpr size_t VT_RS_SMEM = sizeof(float) * VT_M * VT_RS_PITCH;
+constexpr int VT_RS_WARPS = 8;
+
+__device__ __forceinline__ void vq_rescan_frame(const float* __restrict__ x, const float* __restrict__ codebook, const float* Es,
+                                                const float* __restrict__ e2, float* __restrict__ out_q,
+                                                long long* __restrict__ out_idx, long long fr, int lane) {
+    float xv[VT_D];
+    {
+        const float4* xr = reinterpret_cast<const float4*>(x + fr * VT_D);
+#pragma unroll
+        for (int k4 = 0; k4 < VT_D / 4; ++k4) {
+            const float4 v = __ldg(xr + k4);
+            xv[4 * k4] = v.x; xv[4 * k4 + 1] = v.y; xv[4 * k4 + 2] = v.z; xv[4 * k4 + 3] = v.w;
+        }
+    }
+    float best = INFINITY;
+    int besti = 0;                                             // all-NaN scores: index 0, as the fp32 kernel
+#pragma unroll 1
+    for (int i = 0; i < VT_M / 32; i += 4) {
+        // four codes per lane at a time (independent chains); codes ascend per lane: strict < keeps the first minimum
+        const float* er = Es + (32 * i + lane) * VT_RS_PITCH;
+        float d[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int k = 0; k < VT_D; ++k) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) d[c] = fmaf(xv[k], er[c * 32 * VT_RS_PITCH + k], d[c]);
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int code = 32 * (i + c) + lane;
+            const float sc = fmaf(-2.0f, d[c], __ldg(e2 + code));
+            if (sc < best) { best = sc; besti = code; }
+        }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, off);
+        const int oi = __shfl_xor_sync(0xffffffffu, besti, off);
+        if (ob < best || (ob == best && oi < besti)) { best = ob; besti = oi; }
+    }
+    if (lane == 0) out_idx[fr] = besti;
+    if (lane < 16) reinterpret_cast<float4*>(out_q + fr * VT_D)[lane] = __ldg(reinterpret_cast<const float4*>(codebook + besti * VT_D) + lane);
+}
+
+__global__ void __launch_bounds__(VT_RS_WARPS * 32) vq_rescan_kernel(const float* __restrict__ x, const float* __restrict__ codebook,
+                                                                     const float* __restrict__ e2, float* __restrict__ out_q,
+                                                                     long long* __restrict__ out_idx, long long n,
+                                                                     const unsigned* __restrict__ flags) {
+    extern __shared__ float rs_Es[];                           // [512][65]
     const int lane = threadIdx.x & 31;
-    const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-    const long long n_warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+    const long long warp = static_cast<long long>(blockIdx.x) * VT_RS_WARPS + (threadIdx.x >> 5);
+    const long long n_warps = static_cast<long long>(gridDim.x) * VT_RS_WARPS;
+    const unsigned count = flags[0];
+    if (count == 0) return;
+    const bool listed = count <= static_cast<unsigned>(VQ_TC_FLAG_CAP) && n <= 0xffffffffLL;
+    if (listed && static_cast<long long>(blockIdx.x) * VT_RS_WARPS >= count) return;      // no entry for any warp of this CTA
+    for (int f = threadIdx.x; f < VT_M * (VT_D / 4); f += VT_RS_WARPS * 32) {
+        const int m = f >> 4, q = f & 15;
+        const float4 v = __ldg(reinterpret_cast<const float4*>(codebook) + f);
+        float* dst = rs_Es + m * VT_RS_PITCH + 4 * q;
+        dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+    }
+    __syncthreads();
+    if (listed) {
+        for (long long i = warp; i < count; i += n_warps) vq_rescan_frame(x, codebook, rs_Es, e2, out_q, out_idx, flags[4 + i], lane);
+        return;
+    }
     for (long long base = warp * 32; base < n; base += n_warps * 32) {
         const long long mine = base + lane < n ? out_idx[base + lane] : 0;
         unsigned fm = __ballot_sync(0xffffffffu, mine < 0);
         while (fm) {
             const int src = __ffs(fm) - 1;
             fm &= fm - 1;
-            const long long fr = base + src;
-            // Candidates (parked in the frame's output row by vq_tc_kernel): f1 / f2 = best two coarse keys of the four 128-code
-            // subsets, B1 = the coarse winner, mg = 2 eps.  Every coarse score is within eps of its exact fp32 score, so only codes
-            // with a coarse key <= B1 + mg can win.  A subset whose SECOND best is outside the margin contributes at most its
-            // best (lanes 0..3 score those in parallel); a subset whose second best is inside may hide more and is rescanned
-            // completely (4 codes per lane).  Typical flagged frame: two exact scores.
-            const float4* st = reinterpret_cast<const float4*>(out_q + fr * VT_D);
-            const float4 s1 = st[0], s2 = st[1], s3 = st[2];
-            const float f1[4] = {s1.x, s1.y, s1.z, s1.w}, f2[4] = {s2.x, s2.y, s2.z, s2.w};
-            const float B1 = s3.x, mg = s3.y;
-            const float4* xr = reinterpret_cast<const float4*>(x + fr * VT_D);
-            float best = INFINITY;
-            int besti = VT_M;
-            auto consider = [&](int code) {
-                const float4* er = reinterpret_cast<const float4*>(codebook + code * VT_D);
-                float d = 0.f;
-#pragma unroll
-                for (int k4 = 0; k4 < VT_D / 4; ++k4) {
-                    const float4 xv = __ldg(xr + k4), ev = __ldg(er + k4);
-                    d = fmaf(xv.x, ev.x, d); d = fmaf(xv.y, ev.y, d); d = fmaf(xv.z, ev.z, d); d = fmaf(xv.w, ev.w, d);
-                }
-                const float sc = fmaf(-2.0f, d, __ldg(e2 + code));
-                if (sc < best || (sc == best && code < besti)) { best = sc; besti = code; }
-            };
-            {
-                const float mine1 = lane == 0 ? f1[0] : lane == 1 ? f1[1] : lane == 2 ? f1[2] : f1[3];
-                const float mine2 = lane == 0 ? f2[0] : lane == 1 ? f2[1] : lane == 2 ? f2[2] : f2[3];
-                if (lane < 4 && mine1 - B1 <= mg && !(mine2 - B1 <= mg)) consider(static_cast<int>(__float_as_uint(mine1) & 511u));
-            }
-#pragma unroll 1
-            for (int sset = 0; sset < 4; ++sset) {
-                if (!(f2[sset] - B1 <= mg)) continue;
-                const int sb = static_cast<int>(__float_as_uint(f1[sset]) & 0x180u);   // subset = 128 consecutive codes
-#pragma unroll 1
-                for (int i = 0; i < 4; ++i) consider(sb + 32 * i + lane);
-            }
-            __syncwarp();
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) {
-                const float ob = __shfl_xor_sync(0xffffffffu, best, off);
-                const int oi = __shfl_xor_sync(0xffffffffu, besti, off);
-                if (ob < best || (ob == best && oi < besti)) { best = ob; besti = oi; }
-            }
-            if (lane == 0) out_idx[fr] = besti;
-            if (lane < 16) reinterpret_cast<float4*>(out_q + fr * VT_D)[lane] = __ldg(reinterpret_cast<const float4*>(codebook + besti * VT_D) + lane);
+            vq_rescan_frame(x, codebook, rs_Es, e2, out_q, out_idx, base + src, lane);
         }
     }
 }
@@ -551,8 +599,10 @@ __global__ void __launch_bounds__(256) vq_rescan_kernel(const float* __restrict_
 // dimensions each, coalesced), |e_m|^2 with the fp32 kernel's arithmetic (ONE lane, sequential FMA over k -- the order is part
 // of the exactness contract), and the 32-byte row of the |e|^2 MMA block.
 __global__ void __launch_bounds__(256) vq_prepare_kernel(const float* __restrict__ codebook, __nv_bfloat16* __restrict__ planes,
-                                                         float* __restrict__ e2, __nv_bfloat16* __restrict__ aug_b) {
+                                                         float* __restrict__ e2, __nv_bfloat16* __restrict__ aug_b,
+                                                         unsigned* __restrict__ flags) {
     const int m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (blockIdx.x == 0 && threadIdx.x == 0) flags[0] = 0;       // the main kernel's list of flagged frames starts empty
     if (m >= VT_M) return;
     const float* e = codebook + m * VT_D;
     const float2 ev = __ldg(reinterpret_cast<const float2*>(e) + lane);
@@ -606,7 +656,8 @@ int vq_lookup_tc(const float* x, const float* codebook, int64_t n, float* q, int
     }
     float* e2_ws = reinterpret_cast<float*>(static_cast<unsigned char*>(planes_ws) + VT_CB_BYTES);
     __nv_bfloat16* aug_ws = reinterpret_cast<__nv_bfloat16*>(static_cast<unsigned char*>(planes_ws) + VT_CB_BYTES + VT_M * 4);
-    vq_prepare_kernel<<<VT_M * 32 / 256, 256, 0, stream>>>(codebook, static_cast<__nv_bfloat16*>(planes_ws), e2_ws, aug_ws);
+    unsigned* flags_ws = reinterpret_cast<unsigned*>(static_cast<unsigned char*>(planes_ws) + VT_CB_BYTES + VT_M * 4 + VT_M * 32);
+    vq_prepare_kernel<<<VT_M * 32 / 256, 256, 0, stream>>>(codebook, static_cast<__nv_bfloat16*>(planes_ws), e2_ws, aug_ws, flags_ws);
     VQ_CUDA(cudaGetLastError());
     count_launch(1);
     CUtensorMap map;
@@ -629,27 +680,41 @@ int vq_lookup_tc(const float* x, const float* codebook, int64_t n, float* q, int
     if (trace_iters < 0) { const char* e = getenv("VQCPC_VQ_TRACE"); trace_iters = e ? atoi(e) : 0; }
     long long* d_trace = nullptr;
     if (trace_iters > 0) {
-        VQ_CUDA(cudaMalloc(&d_trace, sizeof(long long) * 16 * trace_iters));
-        VQ_CUDA(cudaMemsetAsync(d_trace, 0, sizeof(long long) * 16 * trace_iters, stream));
+        VQ_CUDA(cudaMalloc(&d_trace, sizeof(long long) * (16 * trace_iters + 8 * sms)));
+        VQ_CUDA(cudaMemsetAsync(d_trace, 0, sizeof(long long) * (16 * trace_iters + 8 * sms), stream));
     }
-    VqTcParams p{x, codebook, e2_ws, reinterpret_cast<const uint4*>(aug_ws), q, idx, err, static_cast<long long>(n), dbg, d_trace, trace_iters};
+    VqTcParams p{x, codebook, e2_ws, reinterpret_cast<const uint4*>(aug_ws), q, idx, flags_ws, err, static_cast<long long>(n), dbg, d_trace, trace_iters};
     vq_tc_kernel<<<static_cast<unsigned>(n_tiles < sms ? n_tiles : sms), VT_THREADS, VT_SMEM, stream>>>(map, p);
     VQ_CUDA(cudaGetLastError());
     {
-        const long long warps = (n + 31) / 32;
-        const long long blocks = (warps + 7) / 8;
-        vq_rescan_kernel<<<static_cast<unsigned>(blocks < 8LL * sms ? blocks : 8LL * sms), 256, 0, stream>>>(x, codebook, e2_ws, q,
-                                                                                                             reinterpret_cast<long long*>(idx), n);
+        if (int rc_attr = ensure_dyn_smem(reinterpret_cast<const void*>(vq_rescan_kernel), static_cast<int>(VT_RS_SMEM))) return rc_attr;
+        vq_rescan_kernel<<<sms, VT_RS_WARPS * 32, VT_RS_SMEM, stream>>>(x, codebook, e2_ws, q, reinterpret_cast<long long*>(idx), n, flags_ws);
         VQ_CUDA(cudaGetLastError());
     }
     count_launch(2);
     if (d_trace != nullptr) {
-        std::vector<long long> h(16 * static_cast<size_t>(trace_iters));
+        std::vector<long long> h(16 * static_cast<size_t>(trace_iters) + 8 * static_cast<size_t>(sms));
         VQ_CUDA(cudaMemcpyAsync(h.data(), d_trace, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost, stream));
         VQ_CUDA(cudaStreamSynchronize(stream));
         VQ_CUDA(cudaFree(d_trace));
         const long long per_cta = (n_tiles + (n_tiles < sms ? n_tiles : sms) - 1) / (n_tiles < sms ? n_tiles : sms);
         const int iters = static_cast<int>(per_cta - 1 < trace_iters ? per_cta - 1 : trace_iters);
+        {
+            // per-CTA spans: cycles entry -> done, and the global-timer window of the whole grid
+            const int ncta = static_cast<int>(n_tiles < sms ? n_tiles : sms);
+            std::vector<long long> cyc;
+            long long g0 = -1, g1 = -1, gfirst_end = -1;
+            for (int b = 0; b < ncta; ++b) {
+                const long long* c = h.data() + 16 * trace_iters + 8 * b;
+                cyc.push_back(c[1] - c[0]);
+                if (g0 < 0 || c[2] < g0) g0 = c[2];
+                if (c[3] > g1) g1 = c[3];
+                if (gfirst_end < 0 || c[3] < gfirst_end) gfirst_end = c[3];
+            }
+            std::sort(cyc.begin(), cyc.end());
+            fprintf(stderr, "[vq_tc trace] %d CTAs: cycles entry->done min %lld median %lld max %lld; global timer: grid span %lld ns, first CTA done after %lld ns\n",
+                    ncta, cyc.front(), cyc[cyc.size() / 2], cyc.back(), g1 - g0, gfirst_end - g0);
+        }
         if (iters > 4) {
             // differences between stamps, median over iterations 2 .. iters-1 (steady state)
             auto med = [&](int a_slot, int a_it_off, int b_slot) {
