@@ -196,7 +196,8 @@ def run_other_workload(args, world, rank, local, dev, timed, peaks, lib, workloa
 
         def step_e2e():
             with torch.no_grad():
-                _, _, idx = enc.encode(mel_h.to(dev, non_blocking=True))
+                # chunks of ~512 utterances (whole GEMM waves): each chunk's GEMM stack runs under the next chunk's host->device copy
+                _, _, idx = enc.encode_from_host(mel_h)
                 gather_idx(idx)
                 idx_h.copy_(idx, non_blocking=True)
             torch.cuda.current_stream().synchronize()

@@ -125,15 +125,16 @@ int vqcpc_vq_lookup(const float* x, const float* codebook, int64_t n_frames, int
                     float* out_q, int64_t* out_idx, void* workspace, size_t workspace_bytes, void* stream);
 /* workspace == NULL: the exact fp32 SIMT search.  With a workspace of vqcpc_vq_workspace_bytes() bytes (caller-owned, one per
  * stream in flight -- the library keeps no hidden state) and n_frames >= 8192 the search runs on the tensor cores: tcgen05
- * coarse pass over bf16 hi/lo planes, and an exact fp32 rescan of all 512 codes for every frame whose best two coarse
- * scores are within the coarse error bound (any other frame provably has its coarse winner as exact winner), so results are
- * identical.  vqcpc_check_status(workspace, stream) returns VQCPC_ERR_TIMEOUT if that pipeline timed out. */
+ * coarse pass over bf16 hi/lo planes, and an exact fp32 rescan of all 512 codes for every frame whose coarse minimum is
+ * not the only score within twice the coarse error bound of it (any other frame provably has its coarse winner as exact
+ * winner), so results are identical.  vqcpc_check_status(workspace, stream) returns VQCPC_ERR_TIMEOUT if that pipeline timed out. */
 size_t vqcpc_vq_workspace_bytes(void);
 
 /* ------------------------------------------------------------------ Encoder.encode -- model.py:59-70
  * mel (B, 80, T) fp32 -> out_z (B, T', 64) quantised, out_c (B, T', 256), out_idx (B, T') int64,
  * T' = (T-2)/2+1.  Optional (nullable): out_prevq (B, T', 64) = output of encoder.encoder[-1] (what the
- * forward hook of encode.py:34-40 observes); out_hidden (B, T', C) = its input. */
+ * forward hook of encode.py:34-40 observes); out_hidden (B, T', C) = its input; out_c (NULL: the recurrence is skipped,
+ * see vqcpc_lstm_forward_ex). */
 size_t vqcpc_encoder_workspace_bytes(int32_t B, int32_t T, int32_t channels);
 int vqcpc_encoder_forward(const vqcpc_encoder_weights* w, const float* mel, int32_t B, int32_t T,
                           void* workspace, size_t workspace_bytes,
@@ -148,6 +149,13 @@ int vqcpc_encoder_forward_ex(const vqcpc_encoder_weights* w, const float* mel, i
 size_t vqcpc_lstm_workspace_bytes(int32_t B, int32_t Tp);
 int vqcpc_lstm_forward(const vqcpc_encoder_weights* w, const int64_t* idx, int32_t B, int32_t Tp,
                        void* workspace, size_t workspace_bytes, float* out_c, void* stream);
+/* Same with an explicit arithmetic (VQCPC_GEMM_*): the tensor-core modes run batches of >= 64 utterances as one persistent
+ * tcgen05 launch (lstm_whh_p planes present), otherwise as the fp32 entry above.  Together with out_c == NULL in
+ * vqcpc_encoder_forward_ex (front part only: conv .. VQ, no recurrence) this lets a caller encode a large batch in chunks
+ * -- overlapping each chunk's host->device copy with the previous chunk's GEMMs -- and run the recurrence, whose latency chain
+ * does not shrink with the batch, once over all utterances (Encoder.encode_from_host). */
+int vqcpc_lstm_forward_ex(const vqcpc_encoder_weights* w, const int64_t* idx, int32_t B, int32_t Tp,
+                          void* workspace, size_t workspace_bytes, float* out_c, int32_t gemm_mode, void* stream);
 
 /* ------------------------------------------------------------------ Vocoder -- network_vocoder.py:41-78
  * vqcpc_vocoder_pack: weight-only precompute, eprime_out (256, 2688). */

@@ -381,6 +381,28 @@ def test_persistent_batched_lstm_matches_oracle(B, T):
     assert torch.allclose(c[sel].cpu(), ref, rtol=RTOL, atol=ATOL_C), err
 
 
+@pytest.mark.parametrize("mode", ["fp32", "bf16x3"])
+def test_encode_from_host_equals_encode(mode):
+    """Encoder.encode_from_host streams a host-resident batch to the GPU in chunks (front part per chunk, overlapped with the
+    next chunk's copy; one LSTM launch over all utterances at the end, vqcpc_lstm_forward_ex): same results as encode() of the
+    resident batch, and the indices / context match the oracle."""
+    enc, sd = make_encoder(512, True)
+    enc.gemm_mode = mode
+    B, T = 70, 60
+    mel = fixtures.synthetic_mel(B, T, seed=9)
+    with torch.no_grad():
+        z0, c0, i0 = enc.encode(mel.to(dev()))
+        z1, c1, i1 = enc.encode_from_host(mel.pin_memory(), chunk_utterances=32)      # chunks of 32, 32, 6
+        z2, c2, i2 = enc.encode_from_host(mel, chunk_utterances=1000)                  # one chunk, pageable memory
+    for z, c, i in ((z1, c1, i1), (z2, c2, i2)):
+        assert torch.equal(i.cpu(), i0.cpu()) and torch.equal(z.cpu(), z0.cpu())
+        assert torch.allclose(c.cpu(), c0.cpu(), rtol=RTOL, atol=ATOL_C), float((c.cpu() - c0.cpu()).abs().max())
+    sel = torch.tensor([0, 31, 32, 63, 64, 69])
+    ref = oenc.lstm(sd["codebook.embedding"][i1[sel].cpu()], sd["rnn.weight_ih_l0"], sd["rnn.weight_hh_l0"],
+                    sd["rnn.bias_ih_l0"], sd["rnn.bias_hh_l0"])
+    assert torch.allclose(c1[sel].cpu(), ref, rtol=RTOL, atol=ATOL_C)
+
+
 # ------------------------------------------------------------------------------------------ vocoder
 def test_vocoder_conditioning_matches_oracle():
     voc, sd = make_vocoder()

@@ -68,6 +68,7 @@ SIGNATURES = {
     "vqcpc_encoder_forward_ex": (C.c_int, [C.POINTER(EncoderWeights), _vp, _i32, _i32, _vp, _sz, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
     "vqcpc_lstm_workspace_bytes": (_sz, [_i32, _i32]),
     "vqcpc_lstm_forward": (C.c_int, [C.POINTER(EncoderWeights), _vp, _i32, _i32, _vp, _sz, _vp, _vp]),
+    "vqcpc_lstm_forward_ex": (C.c_int, [C.POINTER(EncoderWeights), _vp, _i32, _i32, _vp, _sz, _vp, _i32, _vp]),
     "vqcpc_vocoder_pack": (C.c_int, [C.POINTER(VocoderWeights), _vp, _vp]),
     "vqcpc_vocoder_workspace_bytes": (_sz, [_i32, _i32]),
     "vqcpc_vocoder_condition": (C.c_int, [C.POINTER(VocoderWeights), _vp, _vp, _i32, _i32, _vp, _sz, _vp, _vp, _vp]),

@@ -743,7 +743,7 @@ int encoder_forward(const vqcpc_encoder_weights* w, const float* mel, int B, int
                     float* out_z, float* out_c, int64_t* out_idx, float* out_prevq, float* out_hidden, int mode,
                     cudaStream_t stream) {
     if (B == 0) return VQCPC_OK;
-    VQ_ARG(w && mel && ws && out_z && out_c && out_idx, "encoder: null pointer");
+    VQ_ARG(w && mel && ws && out_z && out_idx, "encoder: null pointer");
     VQ_ARG(B >= 0 && T >= 2, "encoder: bad shape B=%d T=%d (T must be >= 2)", B, T);
     VQ_ARG(mode == VQCPC_GEMM_FP32 || mode == VQCPC_GEMM_BF16X3 || mode == VQCPC_GEMM_BF16, "encoder: unknown gemm_mode %d", mode);
     const int C = w->channels;
@@ -831,6 +831,7 @@ int encoder_forward(const vqcpc_encoder_weights* w, const float* mel, int B, int
     }
     // the nearest-code search is exact in both modes (tensor-core coarse pass + exact recheck, or the fp32 kernel)
     if ((rc = vq_lookup_auto(zpre, w->codebook, M, out_z, out_idx, vq_planes, &hdr->status, stream))) return rc;
+    if (out_c == nullptr) return VQCPC_OK;      // front part only (the caller runs the recurrence later: vqcpc_lstm_forward_ex)
     return lstm_forward(w, out_idx, B, Tp, lstm_ws, lstm_ws_bytes(B), out_c, stream, false, mode);
 }
 
@@ -880,9 +881,12 @@ extern "C" size_t vqcpc_lstm_workspace_bytes(int32_t B, int32_t Tp) {
     (void)Tp;
     return vqcpc::lstm_ws_bytes(B);
 }
-extern "C" int vqcpc_lstm_forward(const vqcpc_encoder_weights* w, const int64_t* idx, int32_t B, int32_t Tp,
-                                  void* workspace, size_t workspace_bytes, float* out_c, void* stream) {
-    const int rc = vqcpc::lstm_forward(w, idx, B, Tp, workspace, workspace_bytes, out_c, static_cast<cudaStream_t>(stream));
+extern "C" int vqcpc_lstm_forward_ex(const vqcpc_encoder_weights* w, const int64_t* idx, int32_t B, int32_t Tp,
+                                     void* workspace, size_t workspace_bytes, float* out_c, int32_t gemm_mode, void* stream) {
+    VQ_ARG(gemm_mode == VQCPC_GEMM_FP32 || gemm_mode == VQCPC_GEMM_BF16X3 || gemm_mode == VQCPC_GEMM_BF16,
+           "lstm: unknown gemm_mode %d", gemm_mode);
+    const int rc = vqcpc::lstm_forward(w, idx, B, Tp, workspace, workspace_bytes, out_c, static_cast<cudaStream_t>(stream), true,
+                                       gemm_mode);
     if (rc == VQCPC_OK && idx != nullptr && workspace != nullptr && B > 0 && Tp > 0) {
         // caller-supplied indices: an index outside [0, 512) is clamped by the gathers and reported here (after the run, so that
         // the workspace header the run resets carries it): vqcpc_check_status(workspace) returns VQCPC_ERR_ARG
@@ -893,4 +897,8 @@ extern "C" int vqcpc_lstm_forward(const vqcpc_encoder_weights* w, const int64_t*
         vqcpc::count_launch(1);
     }
     return rc;
+}
+extern "C" int vqcpc_lstm_forward(const vqcpc_encoder_weights* w, const int64_t* idx, int32_t B, int32_t Tp,
+                                  void* workspace, size_t workspace_bytes, float* out_c, void* stream) {
+    return vqcpc_lstm_forward_ex(w, idx, B, Tp, workspace, workspace_bytes, out_c, VQCPC_GEMM_FP32, stream);
 }

@@ -26,6 +26,7 @@ struct LcParams {
     float* out;             // (B, Tp, 256)
     int* status;
     int B, Tp;
+    int debug;              // VQCPC_LC_DEBUG (timing ablations, wrong results): 1 no dot product, 2 no gate math, 4 no exchange
 };
 
 __device__ __forceinline__ float2 lc_ffma2(float2 a, float2 b, float2 c) {
@@ -114,13 +115,14 @@ __global__ void __cluster_dims__(LC_S, 1, 1) __launch_bounds__(LC_THREADS, 1) ls
 
         for (int t = t0; t < t_end; ++t) {
             const int cur = t & 1, prev = cur ^ 1;             // step t reads h_s[prev] (h_{t-1}) and fills h_s[cur] everywhere
-            if (tid == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar_a + 8 * cur), "r"(LC_H * 4) : "memory");
+            if (tid == 0 && !(p.debug & 4)) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar_a + 8 * cur), "r"(LC_H * 4) : "memory");
             fetch(t + LC_RING - 1, t0);
             // ---- this row's dot product over its 64 columns
             const float4* hp = reinterpret_cast<const float4*>(&h_s[prev][4 * chunk]);
             float2 acc[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
 #pragma unroll
             for (int k = 0; k < 16; ++k) {
+                if (p.debug & 1) break;
                 const float4 hv = hp[4 * k];
                 acc[k & 3] = lc_ffma2(w[2 * k + 1], make_float2(hv.z, hv.w), lc_ffma2(w[2 * k], make_float2(hv.x, hv.y), acc[k & 3]));
             }
@@ -133,21 +135,26 @@ __global__ void __cluster_dims__(LC_S, 1, 1) __launch_bounds__(LC_THREADS, 1) ls
             const float sf = __shfl_down_sync(0xffffffffu, s, 4), sg = __shfl_down_sync(0xffffffffu, s, 8), so = __shfl_down_sync(0xffffffffu, s, 12);
             if (owner) {
                 // PyTorch gate order i, f, g, o
-                const float ig = sigmoid_fast(s);
-                const float fg = sigmoid_fast(sf);
-                const float gg = tanh_fast(sg);
-                const float og = sigmoid_fast(so);
-                cst = fg * cst + ig * gg;
-                const float hn = og * tanh_fast(cst);
+                float hn;
+                if (p.debug & 2) {
+                    hn = 0.25f * (s + sf + sg + so);
+                } else {
+                    const float ig = sigmoid_fast(s);
+                    const float fg = sigmoid_fast(sf);
+                    const float gg = tanh_fast(sg);
+                    const float og = sigmoid_fast(so);
+                    cst = fg * cst + ig * gg;
+                    hn = og * tanh_fast(cst);
+                }
                 p.out[(static_cast<int64_t>(b) * p.Tp + t) * LC_H + unit] = hn;
-                if (t + 1 < p.Tp) {
+                if (t + 1 < p.Tp && !(p.debug & 4)) {
 #pragma unroll
                     for (int d = 0; d < LC_S; ++d)
                         asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.f32 [%0], %1, [%2];"
                                      ::"r"(dst[d] + cur * LC_H * 4), "f"(hn), "r"(dmb[d] + 8 * cur) : "memory");
                 }
             }
-            if (t + 1 < p.Tp) {
+            if (t + 1 < p.Tp && !(p.debug & 4)) {
                 // ---- wait for all 256 values of h_t (16 ranks x 16 units x 4 bytes on this CTA's mbarrier)
                 const unsigned parity = (static_cast<unsigned>(t) >> 1) & 1u;
                 const long long tw = clock64();
@@ -196,7 +203,8 @@ int lstm_cluster_supported() {
 
 int lstm_cluster_launch(const float* table, const int64_t* idx, const float* w_hh, int B, int Tp, float* out, int* status,
                         cudaStream_t stream) {
-    LcParams p{table, idx, w_hh, out, status, B, Tp};
+    static const int dbg = [] { const char* e = getenv("VQCPC_LC_DEBUG"); return e ? atoi(e) : 0; }();
+    LcParams p{table, idx, w_hh, out, status, B, Tp, dbg};
     lstm_cluster_kernel<<<B * LC_S, LC_THREADS, 0, stream>>>(p);
     VQ_CUDA(cudaGetLastError());
     count_launch(1);

@@ -209,6 +209,75 @@ class Encoder(nn.Module):
             out.append((z[b, :n], c[b, :n], idx[b, :n]))
         return out
 
+    def encode_from_host(self, mel: Tensor, chunk_utterances: int | None = None) -> Tuple[Tensor, Tensor, Tensor]:
+        """``encode`` of a batch that still sits in HOST memory (pin it for a truly asynchronous copy): the utterances go to
+        the GPU in chunks on a copy stream, double buffered, and each chunk's front part (conv .. VQ, per frame) runs while
+        the next chunk is in flight; the LSTM -- a T'-step latency chain whose cost hardly depends on the batch -- runs once
+        over all utterances at the end.  Results equal ``encode(mel.cuda())`` (frames and utterances are independent).
+        Default chunk: about 512 utterances, rounded so that a chunk's rows fill whole waves of the persistent GEMM
+        (SM pairs x 256 rows) -- 512 x 3 s is 4.05 waves on 148 SMs and would pay for 5."""
+        if mel.is_cuda:
+            return self.encode(mel)
+        _check_no_grad(mel)
+        if mel.dim() != 3 or mel.shape[1] != self.conf.in_channels:
+            raise ValueError(f"mel must be (B, {self.conf.in_channels}, T), got {tuple(mel.shape)}")
+        if mel.shape[2] < 2:
+            raise ValueError("mel needs at least 2 frames (Conv1d kernel 4, stride 2, padding 1)")
+        if chunk_utterances is not None and chunk_utterances < 1:
+            raise ValueError("chunk_utterances must be >= 1")
+        dev = self.rnn.weight_hh_l0.device
+        if dev.type != "cuda":
+            raise RuntimeError("Encoder.encode_from_host: the module must live on a CUDA device (no CPU fallback)")
+        w, _keep = self.pack_weights()
+        mel = mel.detach().to(torch.float32).contiguous()
+        B, _, T = mel.shape
+        Tp = (T - 2) // 2 + 1
+        lib = _lib.lib()
+        z = torch.empty(B, Tp, self.conf.z_dim, device=dev)
+        c = torch.empty(B, Tp, self.conf.c_dim, device=dev)
+        idx = torch.empty(B, Tp, dtype=torch.int64, device=dev)
+        if B == 0:
+            return z, c, idx
+        mode = self._resolve_mode(B * Tp)
+        if chunk_utterances is None:
+            rows_per_wave = max(1, torch.cuda.get_device_properties(dev).multi_processor_count // 2) * 256
+            waves = max(1, round(512 * Tp / rows_per_wave))
+            chunk_utterances = max(1, (waves * rows_per_wave) // Tp)
+        n = min(chunk_utterances, B)
+        with torch.cuda.device(dev):
+            cur = torch.cuda.current_stream()
+            copy = torch.cuda.Stream()
+            bufs = [torch.empty(n, self.conf.in_channels, T, device=dev) for _ in range(2)]
+            ready = [torch.cuda.Event() for _ in range(2)]
+            free = [torch.cuda.Event() for _ in range(2)]
+            copy.wait_stream(cur)
+            ws_bytes = lib.vqcpc_encoder_workspace_bytes_ex(n, T, self.conf.channels, mode)
+            wss = []
+            for k, lo in enumerate(range(0, B, n)):
+                hi, b = min(lo + n, B), k & 1
+                with torch.cuda.stream(copy):
+                    if k >= 2:
+                        copy.wait_event(free[b])
+                    bufs[b][:hi - lo].copy_(mel[lo:hi], non_blocking=True)
+                    ready[b].record(copy)
+                cur.wait_event(ready[b])
+                ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)      # one per chunk: each keeps its own status word
+                wss.append(ws)
+                st = lib.vqcpc_encoder_forward_ex(C.byref(w), _lib.ptr(bufs[b]), hi - lo, T, _lib.ptr(ws), ws_bytes,
+                                                  _lib.ptr(z[lo:hi]), None, _lib.ptr(idx[lo:hi]), None, None, mode,
+                                                  _lib.current_stream_ptr())
+                _lib.check(st, "Encoder.encode_from_host")
+                free[b].record(cur)
+            lws_bytes = lib.vqcpc_lstm_workspace_bytes(B, Tp)
+            lws = torch.empty(lws_bytes, dtype=torch.uint8, device=dev)
+            _lib.check(lib.vqcpc_lstm_forward_ex(C.byref(w), _lib.ptr(idx), B, Tp, _lib.ptr(lws), lws_bytes, _lib.ptr(c), mode,
+                                                 _lib.current_stream_ptr()), "Encoder.encode_from_host (LSTM)")
+            for ws in wss + [lws]:
+                _lib.check(lib.vqcpc_check_status(_lib.ptr(ws), _lib.current_stream_ptr()), "Encoder.encode_from_host (persistent kernels)")
+            for t in bufs:
+                t.record_stream(copy)
+        return z, c, idx
+
     def encode_with_aux(self, mel: Tensor):
         """``encode`` plus the pre-VQ projection (B,T',64) -- what encode.py:34-40 captures with a forward hook."""
         z, c, idx, prevq, _ = self._encode(mel, want_aux=True)
