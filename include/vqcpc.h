@@ -222,6 +222,15 @@ size_t vqcpc_logmel_workspace_bytes(const vqcpc_logmel_config* cfg, int32_t B, i
 int vqcpc_logmel_forward(const vqcpc_logmel_config* cfg, const float* wave, const int32_t* lengths, int32_t B, int32_t N,
                          const float* window, const float* dft, const float* melw, void* workspace, size_t workspace_bytes,
                          float* out, void* stream);
+/* ---- text dump of encode.py: np.savetxt(file, z, fmt="%.16f") of encode.py:48-52,57-67 on the GPU.
+ * x (rows, cols) fp32 -> the exact bytes numpy writes: every value as "%.16f" % float(v) (the finite decimal expansion of the
+ * fp32 value rounded to 16 fractional digits, ties to even; "nan", "inf", "-inf"), values of a row separated by ' ', every
+ * row ended by '\n'.  out_text == NULL: only *out_len (bytes) is computed; otherwise out_capacity >= *out_len is required
+ * (VQCPC_ERR_ARG with *out_len set if not).  One host synchronisation per call (the length). */
+size_t vqcpc_textdump_workspace_bytes(int64_t rows, int32_t cols);
+int vqcpc_textdump_f16(const float* x, int64_t rows, int32_t cols, unsigned char* out_text, size_t out_capacity,
+                       int64_t* out_len, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- output stage of convert.py: pyloudnorm's integrated loudness and gain.
  * Replaces pyloudnorm.Meter(sr).integrated_loudness (convert.py:50,57,79) and pyloudnorm.normalize.loudness
  * (convert.py:80): K-weighting biquads for `rate`, 400 ms blocks / 75 % overlap, -70 LUFS absolute and -10 LU relative

@@ -403,6 +403,37 @@ def test_encode_from_host_equals_encode(mode):
     assert torch.allclose(c1[sel].cpu(), ref, rtol=RTOL, atol=ATOL_C)
 
 
+def test_text_dump_equals_numpy_savetxt(tmp_path):
+    """encode.py:48-67 writes z, c and the pre-VQ embedding with np.savetxt(fmt="%.16f"); the GPU formatter (csrc/textdump.cu)
+    must produce the same bytes -- checked against numpy itself, the function the reference calls."""
+    from oracle import textio as otext
+    from vectorquantizedcpc_b200 import format_txt, save_txt
+    g = torch.Generator().manual_seed(3)
+    # (a) the shapes encode.py writes: z (T', 64), c (T', 256) of a real encode
+    enc, _ = make_encoder(512, True)
+    with torch.no_grad():
+        z, c, _ = enc.encode(fixtures.synthetic_mel(1, 300, seed=4).to(dev()))
+    for t in (z[0], c[0]):
+        assert format_txt(t).cpu().numpy().tobytes() == otext.savetxt_bytes(t.cpu().numpy())
+    # (b) every kind of value: signs, zeros, denormals, huge magnitudes, ties at the 17th digit, nan / inf, random bit patterns
+    edge = torch.tensor([0.0, -0.0, 1.0, -1.0, 0.5, 0.99999994, 9.9999999, 2.0 ** -149, 1e-45, 2.0 ** 24, 3.4e38, -3.4e38,
+                         float("inf"), float("-inf"), float("nan"), 2.0 ** -16, 2.0 ** -17, 3 * 2.0 ** -18, 123456.789, -1e-20])
+    ties = torch.arange(1, 200, 2, dtype=torch.float32) * 2.0 ** -17
+    bits = torch.randint(-2 ** 31, 2 ** 31 - 1, (4000,), generator=g, dtype=torch.int64).to(torch.int32).view(torch.float32)
+    allv = torch.cat([edge, ties, bits])
+    allv = allv[: (allv.numel() // 7) * 7].reshape(-1, 7)
+    assert format_txt(allv.to(dev())).cpu().numpy().tobytes() == otext.savetxt_bytes(allv.numpy())
+    # (c) 1-D input (one value per line), a ragged last block, and the file writer
+    v = torch.randn(1000, generator=g)
+    assert format_txt(v.to(dev())).cpu().numpy().tobytes() == otext.savetxt_bytes(v.numpy())
+    big = torch.randn(3001, 64, generator=g) * 3
+    p = tmp_path / "z.txt"
+    nbytes = save_txt(p, big.to(dev()))
+    data = open(p, "rb").read()
+    assert len(data) == nbytes and data == otext.savetxt_bytes(big.numpy())
+    assert torch.equal(torch.from_numpy(np.loadtxt(p, dtype=np.float32)), big)      # %.16f round-trips fp32 of this range
+
+
 # ------------------------------------------------------------------------------------------ vocoder
 def test_vocoder_conditioning_matches_oracle():
     voc, sd = make_vocoder()

@@ -72,6 +72,8 @@ SIGNATURES = {
     "vqcpc_vocoder_pack": (C.c_int, [C.POINTER(VocoderWeights), _vp, _vp]),
     "vqcpc_vocoder_workspace_bytes": (_sz, [_i32, _i32]),
     "vqcpc_vocoder_condition": (C.c_int, [C.POINTER(VocoderWeights), _vp, _vp, _i32, _i32, _vp, _sz, _vp, _vp, _vp]),
+    "vqcpc_textdump_workspace_bytes": (_sz, [C.c_int64, _i32]),
+    "vqcpc_textdump_f16": (C.c_int, [_vp, C.c_int64, _i32, _vp, _sz, C.POINTER(C.c_int64), _vp, _sz, _vp]),
     "vqcpc_loudness_workspace_bytes": (_sz, [_i32, _i32, _i32]),
     "vqcpc_integrated_loudness": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp, _sz, _vp, _vp]),
     "vqcpc_loudness_normalize": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _sz, _vp, _vp, _vp]),

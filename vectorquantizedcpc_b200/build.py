@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libvqcpc_b200.so")
-SOURCES = ["capi.cu", "gemm_f32.cu", "gemm_tc.cu", "gemm_pair.cu", "vq_tc.cu", "encoder.cu", "lstm_persist.cu", "lstm_cluster.cu", "vocoder.cu", "vocoder_cluster.cu", "vocoder_batch.cu", "frontend.cu", "loudness.cu"]
+SOURCES = ["capi.cu", "gemm_f32.cu", "gemm_tc.cu", "gemm_pair.cu", "vq_tc.cu", "encoder.cu", "lstm_persist.cu", "lstm_cluster.cu", "vocoder.cu", "vocoder_cluster.cu", "vocoder_batch.cu", "frontend.cu", "loudness.cu", "textdump.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]
 
