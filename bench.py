@@ -462,7 +462,7 @@ def main():
     t_exch_us = mean_cyc.value / sm_mhz
     floor_us = t_smem_us + t_exch_us
     ar_bytes = 4 * (2688 * 896 + 256 * 896 + 256 * 256 + 2688 + 512 + 256 * 2688 + 2 * Tc * 2688 + 2 * L + 256)
-    roofline = {"kernel": "ar_cluster_kernel", "bound": "latency", "unit": "us/step", "achieved": us_per_step, "peak": floor_us,
+    roofline = {"kernel": "ar_cluster_kernel" if lib.vqcpc_ar_cluster_active() else "ar_kernel", "bound": "latency", "unit": "us/step", "achieved": us_per_step, "peak": floor_us,
                 "frac": floor_us / us_per_step,
                 "floor": {"t_smem_us": t_smem_us, "one_empty_grid_exchange_us": t_exch_us, "exchange_cycles": mean_cyc.value,
                           "sm_mhz_used": sm_mhz},

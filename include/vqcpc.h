@@ -199,6 +199,11 @@ int vqcpc_debug_set_ar_poll_gap(int32_t packed);
  * first_poll_delay = cycles between a CTA's own publish of h_t and its first L2 poll; poll_mode is reserved (0): probes in flight beyond one were measured slower.
  * The cluster kernel's trace (vqcpc_debug_set_ar_trace) has 32 slots per step instead of 8. */
 int vqcpc_debug_set_ar_cluster(int32_t enable, int32_t first_poll_delay, int32_t poll_mode);
+/* Which kernel single-utterance generate uses on the current device: 1 = cluster kernel, 0 = round-1 128-CTA kernel.  The
+ * latter is chosen when the device cannot co-schedule 7 clusters of 16 CTAs, when VQCPC_AR_CLUSTER=0 is set in the environment,
+ * and when Nsight Compute is attached to the process (ncu cannot launch the cluster grid -- a cooperative launch that takes
+ * every 16-CTA cluster slot of the device -- in any replay mode; a profiled run therefore shows ar_kernel).  Same samples. */
+int vqcpc_ar_cluster_active(void);
 /* Measures the bare grid-scope exchange of the sample loop that generate runs on this device, with no compute in between:
  * mean SM cycles per exchange over `iters` exchanges.  Cluster kernel (default): 112 CTAs publish 8 LL words each and poll
  * all 896 with the kernel's own first-probe delay -- ONE of these per step (floor = t_smem + one exchange).

@@ -86,6 +86,7 @@ SIGNATURES = {
     "vqcpc_debug_set_ar_trace": (C.c_int, [_vp, _i32, _i32, _i32]),
     "vqcpc_debug_set_ar_poll_gap": (C.c_int, [_i32]),
     "vqcpc_debug_set_ar_cluster": (C.c_int, [_i32, _i32, _i32]),
+    "vqcpc_ar_cluster_active": (C.c_int, []),
     "vqcpc_debug_exchange_floor": (C.c_int, [_vp, _sz, _i32, C.POINTER(C.c_double), _vp]),
 }
 

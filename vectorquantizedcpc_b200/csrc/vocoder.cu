@@ -771,6 +771,9 @@ extern "C" int vqcpc_debug_set_ar_cluster(int32_t enable, int32_t first_poll_del
     vqcpc::ar_cluster_set_poll(first_poll_delay < 0 ? 0 : first_poll_delay, poll_mode);
     return VQCPC_OK;
 }
+// 1 = single-utterance generate runs on the cluster kernel on the current device, 0 = on the round-1 128-CTA kernel (forced by
+// vqcpc_debug_set_ar_cluster(0, ..) / VQCPC_AR_CLUSTER=0, a device that cannot co-schedule 7 x 16 CTAs, or Nsight Compute attached)
+extern "C" int vqcpc_ar_cluster_active(void) { return (vqcpc::g_cl_enable && vqcpc::ar_cluster_supported()) ? 1 : 0; }
 namespace vqcpc { extern long long* g_ab_trace; extern int g_ab_trace_cta, g_ab_trace_t0, g_ab_trace_n; }
 extern "C" int vqcpc_debug_set_ar_trace(long long* device_buf, int32_t cta, int32_t first_step, int32_t n_steps) {
     vqcpc::g_trace = vqcpc::ArTrace{device_buf, cta, first_step, n_steps};

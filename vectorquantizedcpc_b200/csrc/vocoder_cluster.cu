@@ -21,6 +21,8 @@
 // fma.rn.f32x2), 16 fc2 weights per thread.  h_t never goes through shared memory.
 #include <cooperative_groups.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -571,6 +573,17 @@ int g_cl_enable = 1;
 
 // 1 = the device can hold the 7 x 16 cluster grid at one CTA per SM, 0 = it cannot (fall back to ar_kernel), cached per device
 int ar_cluster_supported() {
+    // VQCPC_AR_CLUSTER=0 / 1: explicit choice.  Otherwise the cluster kernel is used unless Nsight Compute is attached to this
+    // process: ncu cannot launch this grid in any replay mode (a cooperative launch that takes every 16-CTA cluster slot of the
+    // device; profiles/r02_launches_summary.md) and takes the process down with it, so a profiled run uses the 128-CTA ar_kernel,
+    // which it can replay.  The two kernels produce the same samples (tests/test_gpu_parity.py).
+    static const int policy = [] {
+        const char* e = getenv("VQCPC_AR_CLUSTER");
+        if (e != nullptr && e[0] != '\0') return e[0] == '0' ? 0 : 1;
+        if (getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") != nullptr || getenv("NV_NSIGHT_INJECTION_PORT_BASE") != nullptr) return 0;
+        return 1;
+    }();
+    if (!policy) return 0;
     static int cache[64] = {0};     // 0 unknown, 1 yes, 2 no
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;
