@@ -202,7 +202,8 @@ int vqcpc_debug_set_ar_cluster(int32_t enable, int32_t first_poll_delay, int32_t
 /* Which kernel single-utterance generate uses on the current device: 1 = cluster kernel, 0 = round-1 128-CTA kernel.  The
  * latter is chosen when the device cannot co-schedule 7 clusters of 16 CTAs, when VQCPC_AR_CLUSTER=0 is set in the environment,
  * and when Nsight Compute is attached to the process (ncu cannot launch the cluster grid -- a cooperative launch that takes
- * every 16-CTA cluster slot of the device -- in any replay mode; a profiled run therefore shows ar_kernel).  Same samples. */
+ * every 16-CTA cluster slot of the device -- in any replay mode; a profiled run therefore shows ar_kernel).  The two kernels agree to
+ * summation-order noise (logits within 1e-5, tests/test_gpu_parity.py); both are held to the oracle. */
 int vqcpc_ar_cluster_active(void);
 /* Measures the bare grid-scope exchange of the sample loop that generate runs on this device, with no compute in between:
  * mean SM cycles per exchange over `iters` exchanges.  Cluster kernel (default): 112 CTAs publish 8 LL words each and poll

@@ -576,7 +576,7 @@ int ar_cluster_supported() {
     // VQCPC_AR_CLUSTER=0 / 1: explicit choice.  Otherwise the cluster kernel is used unless Nsight Compute is attached to this
     // process: ncu cannot launch this grid in any replay mode (a cooperative launch that takes every 16-CTA cluster slot of the
     // device; profiles/r02_launches_summary.md) and takes the process down with it, so a profiled run uses the 128-CTA ar_kernel,
-    // which it can replay.  The two kernels produce the same samples (tests/test_gpu_parity.py).
+    // which it can replay.  The two kernels agree to summation-order noise (logits within 1e-5, tests/test_gpu_parity.py).
     static const int policy = [] {
         const char* e = getenv("VQCPC_AR_CLUSTER");
         if (e != nullptr && e[0] != '\0') return e[0] == '0' ? 0 : 1;
