@@ -26,22 +26,25 @@ def shard(t: torch.Tensor, rank: Optional[int] = None, world: Optional[int] = No
 
 
 def gather_utterances(local: torch.Tensor, n_total: int, dst: int = 0) -> Optional[torch.Tensor]:
-    """Gather per-rank blocks (dim 0, possibly ragged / empty) back into utterance order on ``dst``.
-    Blocks are padded to the common block size so one fixed-size ``gather`` suffices.  Returns the full
-    tensor on ``dst`` and None elsewhere."""
+    """Gather per-rank blocks (dim 0, possibly ragged / empty) back into utterance order on ``dst``: ONE fixed-size
+    ``gather`` straight into the slices of the result -- with ceil(n/world) utterances per rank only trailing ranks are
+    short or empty, so the valid rows form a prefix of the (world * per) buffer and nothing is copied afterwards; a full
+    block is sent as it is, a short one padded to the common size.  Returns the full tensor on ``dst`` and None elsewhere."""
     world, rank = dist.get_world_size(), dist.get_rank()
     per = (n_total + world - 1) // world
-    pad = torch.zeros((per,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
-    pad[: local.shape[0]] = local
-    bufs: Optional[List[torch.Tensor]] = [torch.empty_like(pad) for _ in range(world)] if rank == dst else None
-    dist.gather(pad, bufs, dst=dst)
-    if rank != dst:
-        return None
-    parts = []
-    for r in range(world):
-        lo, hi = shard_range(n_total, r, world)
-        parts.append(bufs[r][: hi - lo])
-    return torch.cat(parts, dim=0)
+    local = local.contiguous()
+    if local.shape[0] == per:
+        send = local
+    else:
+        send = torch.zeros((per,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        send[: local.shape[0]] = local
+    out = None
+    bufs: Optional[List[torch.Tensor]] = None
+    if rank == dst:
+        out = torch.empty((world * per,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        bufs = [out[r * per:(r + 1) * per] for r in range(world)]
+    dist.gather(send, bufs, dst=dst)
+    return out[:n_total] if rank == dst else None
 
 
 def convert_sharded(encoder, vocoder, mel: torch.Tensor, speaker: torch.Tensor, dst: int = 0, **generate_kw):
