@@ -148,23 +148,32 @@ static int layernorm_relu_split(const float* x, const float* w, const float* b, 
     return VQCPC_OK;
 }
 
-// one thread per (row m = b*Tp + t, input channel i): the 4 taps mel[b, i, 2t-1 .. 2t+2] (zero padded)
-__global__ void im2col_split_kernel(const float* __restrict__ mel, __nv_bfloat16* __restrict__ planes, int B, int T, int Tp,
-                                    int Cin) {
-    const int K = Cin * 4;
-    const int64_t total = static_cast<int64_t>(B) * Tp * Cin;
-    for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
-         idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-        const int i = static_cast<int>(idx % Cin);
-        const int64_t m = idx / Cin;
-        const int b = static_cast<int>(m / Tp), t = static_cast<int>(m - static_cast<int64_t>(b) * Tp);
-        const float* p = mel + (static_cast<int64_t>(b) * Cin + i) * T + 2 * t - 1;
-        float4 v;
-        v.x = (t > 0) ? __ldg(p) : 0.0f;
-        v.y = __ldg(p + 1);
-        v.z = (2 * t + 1 < T) ? __ldg(p + 2) : 0.0f;
-        v.w = (2 * t + 2 < T) ? __ldg(p + 3) : 0.0f;
-        __nv_bfloat16* row = planes + m * 2 * K;
+// One CTA per (utterance, 64 output frames): the 80 x 130 window of mel it needs is read coalesced along time into shared memory
+// (the channel-major input has its channels T floats apart: one thread per (row, channel) reading its 4 taps straight from global
+// memory touched a different 1.2 KB row per lane), then every thread writes the 4 taps mel[b, i, 2t-1 .. 2t+2] (zero padded) of a
+// (row, channel) as 8 bytes of the hi and 8 bytes of the lo plane -- consecutive channels, consecutive addresses.
+constexpr int IM_TT = 64;                 // output frames per CTA
+constexpr int IM_W = 2 * IM_TT + 2;       // input frames they touch
+constexpr int IM_PITCH = IM_W + 3;        // 133: odd pitch, channel-strided reads of the write phase are conflict-free
+constexpr int IM_CIN = 80;
+__global__ void __launch_bounds__(256) im2col_split_kernel(const float* __restrict__ mel, __nv_bfloat16* __restrict__ planes, int T,
+                                                           int Tp, int tiles_per_utt) {
+    __shared__ float win[IM_CIN * IM_PITCH];
+    const int b = blockIdx.x / tiles_per_utt, t0 = (blockIdx.x % tiles_per_utt) * IM_TT;
+    const float* src = mel + static_cast<int64_t>(b) * IM_CIN * T;
+    for (int idx = threadIdx.x; idx < IM_CIN * IM_W; idx += 256) {
+        const int i = idx / IM_W, j = idx - i * IM_W;
+        const int tin = 2 * t0 - 1 + j;
+        win[i * IM_PITCH + j] = (tin >= 0 && tin < T) ? __ldg(src + static_cast<int64_t>(i) * T + tin) : 0.0f;
+    }
+    __syncthreads();
+    const int K = IM_CIN * 4;
+    const int nt = min(IM_TT, Tp - t0);
+    for (int idx = threadIdx.x; idx < nt * IM_CIN; idx += 256) {
+        const int tt = idx / IM_CIN, i = idx - tt * IM_CIN;
+        const float* w = win + i * IM_PITCH + 2 * tt;
+        const float4 v = make_float4(w[0], w[1], w[2], w[3]);
+        __nv_bfloat16* row = planes + (static_cast<int64_t>(b) * Tp + t0 + tt) * 2 * K;
         split_store4(v, row + 4 * i, row + K + 4 * i);
     }
 }
@@ -797,9 +806,8 @@ int encoder_forward(const vqcpc_encoder_weights* w, const float* mel, int B, int
         const int out_pitch = nseg == 3 ? 2 * C : C;
         VQ_CUDA(cudaMemsetAsync(hdr, 0, sizeof(WorkspaceHeader), stream));
         {
-            const int64_t total = M * 80;
-            const unsigned grid = static_cast<unsigned>((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
-            im2col_split_kernel<<<grid, 256, 0, stream>>>(mel, static_cast<__nv_bfloat16*>(planes), B, T, Tp, 80);
+            const int tiles_per_utt = (Tp + IM_TT - 1) / IM_TT;
+            im2col_split_kernel<<<static_cast<unsigned>(B) * tiles_per_utt, 256, 0, stream>>>(mel, static_cast<__nv_bfloat16*>(planes), T, Tp, tiles_per_utt);
             VQ_CUDA(cudaGetLastError());
             count_launch(1);
         }
