@@ -32,6 +32,28 @@ void set_error(const char* fmt, ...);
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// Programmatic dependent launch (latency paths: chains of small kernels on one stream).  A kernel launched with launch_pdl() may
+// start while its predecessor is still running; pdl_sync() at its top -- before the first access to anything the predecessor
+// touches -- waits for the predecessor's completion and memory flush, then lets ITS successor be scheduled, so every kernel's
+// launch latency and prologue run under the kernel before it.  In a kernel launched normally both instructions are no-ops.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_sync() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                     Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
 // ---------------------------------------------------------------------------------------------
 // Warp helpers
 // ---------------------------------------------------------------------------------------------

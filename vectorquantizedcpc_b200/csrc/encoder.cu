@@ -30,6 +30,7 @@ __global__ void __launch_bounds__(256) ln_relu_kernel(float* __restrict__ x, con
     constexpr int C = N4 * 128;
     const int lane = threadIdx.x & 31;
     const int64_t row = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    pdl_sync();
     if (row >= rows) return;
     float4* p = reinterpret_cast<float4*>(x + row * C);
     float4 v[N4];
@@ -60,14 +61,14 @@ __global__ void __launch_bounds__(256) ln_relu_kernel(float* __restrict__ x, con
     }
 }
 
-int layernorm_relu(float* x, const float* w, const float* b, int64_t rows, int C, cudaStream_t stream) {
+int layernorm_relu(float* x, const float* w, const float* b, int64_t rows, int C, cudaStream_t stream, bool pdl) {
     if (rows == 0) return VQCPC_OK;
     VQ_ARG(x && w && b, "layernorm: null pointer");
     VQ_ARG(C % 128 == 0 && C >= 128 && C <= 1024, "layernorm: C=%d must be a multiple of 128 in [128,1024]", C);
     if (rows == 0) return VQCPC_OK;
     const unsigned grid = static_cast<unsigned>((rows + 7) / 8);
     switch (C / 128) {
-#define LN_CASE(n) case n: ln_relu_kernel<n><<<grid, 256, 0, stream>>>(x, w, b, rows); break;
+#define LN_CASE(n) case n: VQ_CUDA(launch_pdl(pdl, ln_relu_kernel<n>, dim3(grid), dim3(256), 0, stream, x, w, b, rows)); break;
         LN_CASE(1) LN_CASE(2) LN_CASE(3) LN_CASE(4) LN_CASE(5) LN_CASE(6) LN_CASE(7) LN_CASE(8)
 #undef LN_CASE
     }
@@ -318,6 +319,7 @@ __global__ void __launch_bounds__(256) vq_lookup_small_kernel(const float* __res
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t fr = static_cast<int64_t>(blockIdx.x) * 8 + warp;
     const bool valid = fr < n_frames;
+    pdl_sync();
     float xr[VQ_D];
 #pragma unroll
     for (int k4 = 0; k4 < VQ_D / 4; ++k4) {
@@ -365,15 +367,14 @@ __global__ void __launch_bounds__(256) vq_lookup_small_kernel(const float* __res
 constexpr int64_t VQ_SMALL_MAX_FRAMES = 1024;
 
 int vq_lookup(const float* x, const float* codebook, int64_t n, int n_codes, int dim, float* q, int64_t* idx,
-              cudaStream_t stream) {
+              cudaStream_t stream, bool pdl) {
     if (n == 0) return VQCPC_OK;
     VQ_ARG(x && codebook && q && idx, "vq_lookup: null pointer");
     VQ_ARG(n_codes == VQ_M && dim == VQ_D, "vq_lookup: only a 512x64 codebook is supported (got %dx%d)", n_codes, dim);
     VQ_ARG(n >= 0, "vq_lookup: negative frame count");
     if (n == 0) return VQCPC_OK;
     if (n <= VQ_SMALL_MAX_FRAMES) {
-        vq_lookup_small_kernel<<<static_cast<unsigned>((n + 7) / 8), 256, 0, stream>>>(x, codebook, n, q, idx);
-        VQ_CUDA(cudaGetLastError());
+        VQ_CUDA(launch_pdl(pdl, vq_lookup_small_kernel, dim3(static_cast<unsigned>((n + 7) / 8)), dim3(256), 0, stream, x, codebook, n, q, idx));
         count_launch(1);
         return VQCPC_OK;
     }
@@ -388,10 +389,10 @@ int vq_lookup(const float* x, const float* codebook, int64_t n, int n_codes, int
 }
 
 int vq_lookup_auto(const float* x, const float* codebook, int64_t n, float* q, int64_t* idx, void* planes_ws, int* err,
-                   cudaStream_t stream) {
+                   cudaStream_t stream, bool pdl) {
     if (planes_ws != nullptr && err != nullptr && n >= VQ_TC_MIN_FRAMES)
         return vq_lookup_tc(x, codebook, n, q, idx, planes_ws, err, stream);
-    return vq_lookup(x, codebook, n, VQ_M, VQ_D, q, idx, stream);
+    return vq_lookup(x, codebook, n, VQ_M, VQ_D, q, idx, stream, pdl);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -774,6 +775,7 @@ int encoder_forward(const vqcpc_encoder_weights* w, const float* mel, int B, int
     float* zpre = out_prevq ? out_prevq : zpre_ws;
 
     int rc;
+    bool vq_pdl = false;
     if (mode == VQCPC_GEMM_FP32) {
         VQ_CUDA(cudaMemsetAsync(hdr, 0, sizeof(WorkspaceHeader), stream));
         // latency case (M <= 256 frames): split-K planes behind the other buffers, tile counters in the header's reserved words
@@ -781,17 +783,21 @@ int encoder_forward(const vqcpc_encoder_weights* w, const float* mel, int B, int
         const size_t sk_bytes = gemm_splitk_ws_bytes(M, C);
         unsigned* sk_ctr = reinterpret_cast<unsigned*>(hdr->reserved);
         static_assert(sizeof(hdr->reserved) >= SPLITK_COUNTERS * sizeof(unsigned), "header too small for the split-K counters");
+        // one utterance (M <= 256): eleven small kernels in a row -- each is launched as a programmatic dependent of the one before
+        // it (launch latency and prologue under the predecessor).  The first one follows the memset and is launched normally.
+        const bool pdl = M <= 256;
         if ((rc = gemm_conv(mel, B, T, 80, w->conv_w, act[0], C, stream, sk, sk_bytes, sk_ctr))) return rc;
-        if ((rc = layernorm_relu(act[0], w->ln_w[0], w->ln_b[0], M, C, stream))) return rc;
+        if ((rc = layernorm_relu(act[0], w->ln_w[0], w->ln_b[0], M, C, stream, pdl))) return rc;
         int cur = 0;
         for (int j = 0; j < 4; ++j) {
-            if ((rc = gemm_dense(act[cur], C, w->fc_w[j], C, nullptr, act[cur ^ 1], C, M, C, C, stream, sk, sk_bytes, sk_ctr))) return rc;
+            if ((rc = gemm_dense(act[cur], C, w->fc_w[j], C, nullptr, act[cur ^ 1], C, M, C, C, stream, sk, sk_bytes, sk_ctr, pdl))) return rc;
             cur ^= 1;
-            if ((rc = layernorm_relu(act[cur], w->ln_w[j + 1], w->ln_b[j + 1], M, C, stream))) return rc;
+            if ((rc = layernorm_relu(act[cur], w->ln_w[j + 1], w->ln_b[j + 1], M, C, stream, pdl))) return rc;
         }
         if (out_hidden)
             VQ_CUDA(cudaMemcpyAsync(out_hidden, act[cur], M * C * sizeof(float), cudaMemcpyDeviceToDevice, stream));
-        if ((rc = gemm_dense(act[cur], C, w->proj_w, C, w->proj_b, zpre, VQ_D, M, VQ_D, C, stream, sk, sk_bytes, sk_ctr))) return rc;
+        if ((rc = gemm_dense(act[cur], C, w->proj_w, C, w->proj_b, zpre, VQ_D, M, VQ_D, C, stream, sk, sk_bytes, sk_ctr, pdl && !out_hidden))) return rc;
+        vq_pdl = pdl;
     } else {
         // tensor-core mode: every GEMM is tcgen05 over bf16 hi/lo planes; LN+ReLU re-splits its output for the next one
         VQ_ARG(w->conv_wp && w->fc_wp[0] && w->fc_wp[1] && w->fc_wp[2] && w->fc_wp[3] && w->proj_wp,
@@ -838,7 +844,7 @@ int encoder_forward(const vqcpc_encoder_weights* w, const float* mel, int B, int
         }
     }
     // the nearest-code search is exact in both modes (tensor-core coarse pass + exact recheck, or the fp32 kernel)
-    if ((rc = vq_lookup_auto(zpre, w->codebook, M, out_z, out_idx, vq_planes, &hdr->status, stream))) return rc;
+    if ((rc = vq_lookup_auto(zpre, w->codebook, M, out_z, out_idx, vq_planes, &hdr->status, stream, vq_pdl))) return rc;
     if (out_c == nullptr) return VQCPC_OK;      // front part only (the caller runs the recurrence later: vqcpc_lstm_forward_ex)
     return lstm_forward(w, out_idx, B, Tp, lstm_ws, lstm_ws_bytes(B), out_c, stream, false, mode);
 }

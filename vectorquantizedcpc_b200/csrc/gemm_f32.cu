@@ -57,6 +57,7 @@ sgemm_tn_kernel(ALoader a, const float* __restrict__ W, int64_t ldw, const float
     const int tx = tid & 15, ty = tid >> 4;
     const int64_t m0 = static_cast<int64_t>(blockIdx.x) * BM;
     const int n0 = blockIdx.y * BN;
+    pdl_sync();
 
     float4 ra[RM], rb[RN];
     float acc[RM][4][RN][4];
@@ -216,7 +217,7 @@ size_t gemm_splitk_ws_bytes(int64_t M, int N) {
 template <class ALoader>
 static int launch_gemm(ALoader a, const float* W, int64_t ldw, const float* bias, float* C, int64_t ldc,
                        int64_t M, int N, int K, cudaStream_t stream, void* splitk_ws = nullptr, size_t splitk_ws_bytes = 0,
-                       unsigned* splitk_counters = nullptr) {
+                       unsigned* splitk_counters = nullptr, bool pdl = false) {
     VQ_ARG(M >= 0 && N > 0 && K > 0, "gemm: bad shape M=%lld N=%d K=%d", (long long)M, N, K);
     VQ_ARG(K % GEMM_BK == 0, "gemm: K=%d must be a multiple of %d", K, GEMM_BK);
     VQ_ARG(N % 4 == 0 && ldc % 4 == 0 && ldw % 4 == 0, "gemm: N, ldc, ldw must be multiples of 4");
@@ -236,11 +237,14 @@ static int launch_gemm(ALoader a, const float* W, int64_t ldw, const float* bias
             for (int cand = SPLITK_MAX_S; cand >= 2; --cand)
                 if (K % (GEMM_BK * cand) == 0 && K / cand >= 64 && tiles * cand <= 2 * device_sm_count()) { S = cand; break; }
         }
+        // pdl: the caller's latency path is a chain of small kernels (programmatic dependent launches, common.cuh)
         if (S > 1) {
             grid.z = S;
-            sgemm_tn_kernel<1, 1, ALoader><<<grid, 256, 0, stream>>>(a, W, ldw, bias, C, ldc, M, N, K, static_cast<float*>(splitk_ws), splitk_counters);
+            VQ_CUDA(launch_pdl(pdl, sgemm_tn_kernel<1, 1, ALoader>, grid, dim3(256), 0, stream, a, W, ldw, bias, C, ldc, M, N, K,
+                               static_cast<float*>(splitk_ws), splitk_counters));
         } else {
-            sgemm_tn_kernel<1, 1, ALoader><<<grid, 256, 0, stream>>>(a, W, ldw, bias, C, ldc, M, N, K, nullptr, nullptr);
+            VQ_CUDA(launch_pdl(pdl, sgemm_tn_kernel<1, 1, ALoader>, grid, dim3(256), 0, stream, a, W, ldw, bias, C, ldc, M, N, K,
+                               static_cast<float*>(nullptr), static_cast<unsigned*>(nullptr)));
         }
     }
     VQ_CUDA(cudaGetLastError());
@@ -249,12 +253,12 @@ static int launch_gemm(ALoader a, const float* W, int64_t ldw, const float* bias
 }
 
 int gemm_dense(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias, float* C, int64_t ldc,
-               int64_t M, int N, int K, cudaStream_t stream, void* splitk_ws, size_t splitk_ws_bytes, unsigned* splitk_counters) {
+               int64_t M, int N, int K, cudaStream_t stream, void* splitk_ws, size_t splitk_ws_bytes, unsigned* splitk_counters, bool pdl) {
     if (M == 0) return VQCPC_OK;
     VQ_ARG(A && W && C, "gemm: null pointer");
     VQ_ARG(lda % 4 == 0, "gemm: lda must be a multiple of 4");
     DenseA a{A, lda};
-    return launch_gemm(a, W, ldw, bias, C, ldc, M, N, K, stream, splitk_ws, splitk_ws_bytes, splitk_counters);
+    return launch_gemm(a, W, ldw, bias, C, ldc, M, N, K, stream, splitk_ws, splitk_ws_bytes, splitk_counters, pdl);
 }
 
 int gemm_conv(const float* mel, int B, int T, int Cin, const float* W, float* C, int Cout, cudaStream_t stream, void* splitk_ws,

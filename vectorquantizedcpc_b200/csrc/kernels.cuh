@@ -11,7 +11,7 @@ namespace vqcpc {
 constexpr int SPLITK_COUNTERS = 60;
 int gemm_dense(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias, float* C, int64_t ldc,
                int64_t M, int N, int K, cudaStream_t stream, void* splitk_ws = nullptr, size_t splitk_ws_bytes = 0,
-               unsigned* splitk_counters = nullptr);
+               unsigned* splitk_counters = nullptr, bool pdl = false);      // pdl: programmatic dependent launch (common.cuh)
 int gemm_conv(const float* mel, int B, int T, int Cin, const float* W, float* C, int Cout, cudaStream_t stream,
               void* splitk_ws = nullptr, size_t splitk_ws_bytes = 0, unsigned* splitk_counters = nullptr);
 size_t gemm_splitk_ws_bytes(int64_t M, int N);
@@ -46,13 +46,13 @@ int lstm_persist(const float* table, const int64_t* idx, const void* whh_planes,
 // lstm_cluster.cu: latency LSTM for a few utterances, one 16-CTA cluster each, h_t over DSMEM
 int lstm_cluster_supported();
 int lstm_cluster_launch(const float* table, const int64_t* idx, const float* w_hh, int B, int Tp, float* out, int* status,
-                        cudaStream_t stream);
+                        cudaStream_t stream);      // launched as a programmatic dependent of the kernel before it
 int split_planes(const float* x, long long ld, void* out, long long rows, int K, cudaStream_t stream);
 
 // encoder.cu
-int layernorm_relu(float* x, const float* w, const float* b, int64_t rows, int C, cudaStream_t stream);
+int layernorm_relu(float* x, const float* w, const float* b, int64_t rows, int C, cudaStream_t stream, bool pdl = false);
 int vq_lookup(const float* x, const float* codebook, int64_t n, int n_codes, int dim, float* q, int64_t* idx,
-              cudaStream_t stream);
+              cudaStream_t stream, bool pdl = false);
 // tensor-core search (vq_tc.cu); vq_lookup_auto picks it for n >= VQ_TC_MIN_FRAMES when scratch is provided
 constexpr int64_t VQ_TC_MIN_FRAMES = 8192;
 constexpr int VQ_TC_FLAG_CAP = 32768;           // frames the main kernel can list for the exact rescan before it falls back to a sweep
@@ -61,7 +61,7 @@ constexpr size_t VQ_TC_PLANES_BYTES = 512 * 128 * 2 + 512 * 4 + 512 * 32 + 16 + 
 int vq_lookup_tc(const float* x, const float* codebook, int64_t n, float* q, int64_t* idx, void* planes_ws, int* err,
                  cudaStream_t stream);
 int vq_lookup_auto(const float* x, const float* codebook, int64_t n, float* q, int64_t* idx, void* planes_ws, int* err,
-                   cudaStream_t stream);
+                   cudaStream_t stream, bool pdl = false);
 
 // vocoder_batch.cu: batched sample loop (up to 64 utterances per launch, grid-barrier phases)
 size_t ar_batch_workspace_bytes();

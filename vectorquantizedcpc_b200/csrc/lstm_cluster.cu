@@ -65,6 +65,7 @@ __global__ void __cluster_dims__(LC_S, 1, 1) __launch_bounds__(LC_THREADS, 1) ls
             w[2 * k] = make_float2(v.x, v.y); w[2 * k + 1] = make_float2(v.z, v.w);
         }
     }
+    pdl_sync();        // W_hh is not written by any kernel of the call: its load above runs under the predecessor (table GEMM)
     const unsigned mbar_a = static_cast<unsigned>(__cvta_generic_to_shared(&mbar[0]));
     const unsigned hs_a = static_cast<unsigned>(__cvta_generic_to_shared(&h_s[0][0]));
     const unsigned ring_a = static_cast<unsigned>(__cvta_generic_to_shared(&x_ring[0][row]));
@@ -205,8 +206,7 @@ int lstm_cluster_launch(const float* table, const int64_t* idx, const float* w_h
                         cudaStream_t stream) {
     static const int dbg = [] { const char* e = getenv("VQCPC_LC_DEBUG"); return e ? atoi(e) : 0; }();
     LcParams p{table, idx, w_hh, out, status, B, Tp, dbg};
-    lstm_cluster_kernel<<<B * LC_S, LC_THREADS, 0, stream>>>(p);
-    VQ_CUDA(cudaGetLastError());
+    VQ_CUDA(launch_pdl(true, lstm_cluster_kernel, dim3(B * LC_S), dim3(LC_THREADS), 0, stream, p));
     count_launch(1);
     return VQCPC_OK;
 }
