@@ -62,6 +62,9 @@ typedef struct {
     const void* fc_wp[4];     /* (C, 2*C) */
     const void* proj_wp;      /* (64, 2*C) */
     const void* lstm_whh_p;   /* (1024, 2*256): planes of rnn.weight_hh_l0 for the batched (B >= 64) LSTM */
+    /* optional, weight-only: the LSTM input projection of every CODE, table[m] = lstm_w_ih codebook[m] + lstm_b (512, 1024),
+     * exactly vqcpc_linear_f32(codebook, lstm_w_ih, lstm_b).  NULL: recomputed inside every call (one 512 x 1024 x 64 GEMM). */
+    const float* lstm_table;
 } vqcpc_encoder_weights;
 
 /* GEMM arithmetic of Encoder.encode */

@@ -31,11 +31,25 @@ def test_library_exports_every_declared_symbol():
     assert lib.vqcpc_abi_version() == 1
 
 
-def test_struct_layout_matches_header():
+def test_struct_layout_matches_header(tmp_path):
+    """The ctypes mirrors against the header itself: gcc compiles include/vqcpc.h and prints sizeof / offsetof."""
     import ctypes as C
-    # 6 int32 + 21 pointers each
-    assert C.sizeof(_lib.EncoderWeights) == 24 + 8 * 28
-    assert C.sizeof(_lib.VocoderWeights) == 24 + 8 * 21
+    import subprocess
+    src = tmp_path / "layout.c"
+    src.write_text(
+        '#include <stdio.h>\n#include <stddef.h>\n#include "vqcpc.h"\n'
+        'int main(void) { printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(vqcpc_encoder_weights), sizeof(vqcpc_vocoder_weights),\n'
+        '  offsetof(vqcpc_encoder_weights, lstm_whh_p), offsetof(vqcpc_encoder_weights, lstm_table),\n'
+        '  offsetof(vqcpc_vocoder_weights, mulaw_lut), sizeof(vqcpc_logmel_config)); return 0; }\n')
+    exe = tmp_path / "layout"
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.check_call(["gcc", "-I", os.path.join(root, "include"), str(src), "-o", str(exe)])
+    enc_sz, voc_sz, off_whh, off_tab, off_lut, mel_sz = map(int, subprocess.check_output([str(exe)]).split())
+    assert C.sizeof(_lib.EncoderWeights) == enc_sz == 24 + 8 * 29      # 6 int32 + 29 pointers
+    assert C.sizeof(_lib.VocoderWeights) == voc_sz == 24 + 8 * 21
+    assert _lib.EncoderWeights.lstm_whh_p.offset == off_whh and _lib.EncoderWeights.lstm_table.offset == off_tab
+    assert _lib.VocoderWeights.mulaw_lut.offset == off_lut
+    assert C.sizeof(_lib.LogMelConfig) == mel_sz
 
 
 def test_state_dict_layout_matches_reference_appendix_c():

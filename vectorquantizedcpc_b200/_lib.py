@@ -26,6 +26,7 @@ class EncoderWeights(C.Structure):
         ("proj_w", C.c_void_p), ("proj_b", C.c_void_p), ("codebook", C.c_void_p),
         ("lstm_w_ih", C.c_void_p), ("lstm_w_hh", C.c_void_p), ("lstm_b", C.c_void_p),
         ("conv_wp", C.c_void_p), ("fc_wp", C.c_void_p * 4), ("proj_wp", C.c_void_p), ("lstm_whh_p", C.c_void_p),
+        ("lstm_table", C.c_void_p),
     ]
 
 

@@ -644,10 +644,14 @@ int lstm_forward(const vqcpc_encoder_weights* w, const int64_t* idx, int B, int 
     if (B == 0 || Tp == 0) return VQCPC_OK;
     unsigned char* base = static_cast<unsigned char*>(ws);
     WorkspaceHeader* hdr = reinterpret_cast<WorkspaceHeader*>(base);
-    float* table = reinterpret_cast<float*>(base + sizeof(WorkspaceHeader));
+    float* table_ws = reinterpret_cast<float*>(base + sizeof(WorkspaceHeader));
     void* ll = base + sizeof(WorkspaceHeader) + align_up(sizeof(float) * VQ_M * LSTM_G, 256);
     if (reset_status) VQ_CUDA(cudaMemsetAsync(hdr, 0, sizeof(WorkspaceHeader), stream));
-    int rc = gemm_dense(w->codebook, VQ_D, w->lstm_w_ih, VQ_D, w->lstm_b, table, LSTM_G, VQ_M, LSTM_G, VQ_D, stream);
+    // the 512-row input-projection table: precomputed with the weights (vqcpc_encoder_weights::lstm_table) or built here
+    int rc = VQCPC_OK;
+    if (w->lstm_table == nullptr)
+        rc = gemm_dense(w->codebook, VQ_D, w->lstm_w_ih, VQ_D, w->lstm_b, table_ws, LSTM_G, VQ_M, LSTM_G, VQ_D, stream);
+    const float* table = w->lstm_table != nullptr ? w->lstm_table : table_ws;
     if (rc) return rc;
     if (B >= LSTM_BATCHED_MIN_B) {
         unsigned char* bb = static_cast<unsigned char*>(ll) + lstm_ll_bytes(LSTM_MAX_GROUPS, LSTM_MAX_NB);

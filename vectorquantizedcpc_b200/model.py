@@ -176,6 +176,14 @@ class Encoder(nn.Module):
             w.fc_wp[i] = planes(t)
         w.proj_wp = planes(pw)
         w.lstm_whh_p = planes(whh)
+        # weight-only precompute: the LSTM sees quantised vectors only, so its input projection is a 512-row table
+        table = torch.empty(cb.shape[0], wih.shape[0], device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.vqcpc_linear_f32(cb.data_ptr(), cb.shape[1], wih.data_ptr(), wih.shape[1], lstm_b.data_ptr(),
+                                            table.data_ptr(), table.shape[1], cb.shape[0], table.shape[1], cb.shape[1],
+                                            _lib.current_stream_ptr()), "Encoder.pack_weights (LSTM table)")
+        keep.append(table)
+        w.lstm_table = table.data_ptr()
         self._packed, self._packed_key = (w, keep), key
         return self._packed
 
