@@ -628,7 +628,8 @@ static bool lstm_persist_enabled() {          // VQCPC_LSTM_PERSIST=0 selects th
 static size_t lstm_batched_bytes(int B) {
     if (B < LSTM_BATCHED_MIN_B) return 0;
     return align_up(sizeof(float) * B * LSTM_G, 256) + align_up(sizeof(float) * B * LSTM_H, 256) +
-           2 * align_up(2 * static_cast<size_t>(B) * 2 * LSTM_H, 256);      // two h-plane buffers (ping-pong across steps)
+           2 * align_up(2 * static_cast<size_t>(B) * 2 * LSTM_H, 256) +      // two h-plane buffers (ping-pong across steps)
+           align_up(lstm_persist_table_bytes(), 256);                         // permuted input-projection table of lstm_persist
 }
 static size_t lstm_ws_bytes(int B) {
     return sizeof(WorkspaceHeader) + align_up(sizeof(float) * VQ_M * LSTM_G, 256) +
@@ -658,13 +659,14 @@ int lstm_forward(const vqcpc_encoder_weights* w, const int64_t* idx, int B, int 
         float* gates = reinterpret_cast<float*>(bb); bb += align_up(sizeof(float) * B * LSTM_G, 256);
         float* cstate = reinterpret_cast<float*>(bb); bb += align_up(sizeof(float) * B * LSTM_H, 256);
         __nv_bfloat16* hplanes = reinterpret_cast<__nv_bfloat16*>(bb); bb += align_up(2 * static_cast<size_t>(B) * 2 * LSTM_H, 256);
-        __nv_bfloat16* hplanes2 = reinterpret_cast<__nv_bfloat16*>(bb);
+        __nv_bfloat16* hplanes2 = reinterpret_cast<__nv_bfloat16*>(bb); bb += align_up(2 * static_cast<size_t>(B) * 2 * LSTM_H, 256);
+        float* table_perm = reinterpret_cast<float*>(bb);
         const bool tc = (mode != VQCPC_GEMM_FP32) && (w->lstm_whh_p != nullptr);   // bf16 mode too: the recurrence stays bf16x3
         const int64_t total = static_cast<int64_t>(B) * (LSTM_H / 4);
         const unsigned grid = static_cast<unsigned>((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
         if (tc && lstm_persist_enabled()) {
             // one persistent launch for all T' steps (lstm_persist.cu); the gates buffer doubles as its counter scratch
-            return lstm_persist(table, idx, w->lstm_whh_p, B, Tp, hplanes, hplanes2, reinterpret_cast<unsigned*>(gates), out_c,
+            return lstm_persist(table, idx, w->lstm_whh_p, B, Tp, hplanes, hplanes2, reinterpret_cast<unsigned*>(gates), table_perm, out_c,
                                 &hdr->status, stream);
         }
         if (tc && B >= LSTM_FUSED_MAX_B) {

@@ -42,7 +42,8 @@ int gemm_ln_pair(const void* a_planes, long long a_pitch, int a_lo_col, const vo
                  cudaStream_t stream);
 // lstm_persist.cu: the whole batched LSTM recurrence in one persistent tcgen05 launch (W_hh slices resident in shared memory)
 int lstm_persist(const float* table, const int64_t* idx, const void* whh_planes, int B, int Tp, void* planes0, void* planes1,
-                 unsigned* counters, float* out, int* err_flag, cudaStream_t stream);
+                 unsigned* counters, float* table_perm, float* out, int* err_flag, cudaStream_t stream);
+size_t lstm_persist_table_bytes();
 // lstm_cluster.cu: latency LSTM for a few utterances, one 16-CTA cluster each, h_t over DSMEM
 int lstm_cluster_supported();
 int lstm_cluster_launch(const float* table, const int64_t* idx, const float* w_hh, int B, int Tp, float* out, int* status,

@@ -33,13 +33,14 @@ constexpr int LP_H = 256, LP_G = 4 * LP_H;
 constexpr int LP_KB = LP_H / TC_BK;   // 4 k-blocks of 64
 
 struct LpParams {
-    const float* table;          // (512, 1024) = W_ih e + b_ih + b_hh per code
+    const float* table;          // (512, 1024) = W_ih e + b_ih + b_hh per code, PERMUTED: [code][unit / 8][gate][unit % 8]
     const int64_t* idx;          // (B, Tp)
     float* out;                  // (B, Tp, 256)
     __nv_bfloat16* planes[2];    // (B, 512) [hi | lo] of h_t, ping-pong across steps
     unsigned* counters;          // one per row tile, zeroed before launch
     int* err;
     int B, Tp, n_ns;
+    int dbg;                     // VQCPC_LP_DEBUG ablation bits (timing only; results are wrong with any bit set)
 };
 
 __device__ __forceinline__ int lp_clamp_code(int64_t id) { return id < 0 ? 0 : (id > 511 ? 511 : static_cast<int>(id)); }
@@ -133,7 +134,7 @@ lstm_persist_kernel(const __grid_constant__ CUtensorMap map_h0, const __grid_con
                 // h_{t-1} of this row tile is complete once all n_ns CTAs of the tile have finished step t-1
                 const unsigned want = 4u * static_cast<unsigned>(p.n_ns) * static_cast<unsigned>(t);   // four epilogue warps per CTA
                 const long long t0 = clock64();
-                while (ld_acquire_u32(ctr) < want) {
+                while (!(p.dbg & 8) && ld_acquire_u32(ctr) < want) {
                     if (clock64() - t0 > TC_TIMEOUT) { atomicExch(p.err, VQCPC_ERR_TIMEOUT); ok = false; break; }
                 }
                 if (!ok) break;
@@ -209,11 +210,12 @@ lstm_persist_kernel(const __grid_constant__ CUtensorMap map_h0, const __grid_con
         // table values of the first 8-unit chunk of step 0 (every later chunk is prefetched one chunk / one step ahead)
         float4 xa[4], xb[4];
         auto fetch = [&](int cd, int ug) {
-            const float* tr = p.table + static_cast<int64_t>(cd) * LP_G + u0 + ug;
+            // permuted table (lp_permute_table_kernel): the 4 gates x 8 units of a chunk are ONE 128-byte line
+            const float4* tr = reinterpret_cast<const float4*>(p.table + static_cast<int64_t>((p.dbg & 1) ? 0 : cd) * LP_G + (u0 + ug) * 4);
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
-                xa[g] = __ldg(reinterpret_cast<const float4*>(tr + g * LP_H));
-                xb[g] = __ldg(reinterpret_cast<const float4*>(tr + g * LP_H) + 1);
+                xa[g] = __ldg(tr + 2 * g);
+                xb[g] = __ldg(tr + 2 * g + 1);
             }
         };
         fetch(code, 0);
@@ -256,15 +258,29 @@ lstm_persist_kernel(const __grid_constant__ CUtensorMap map_h0, const __grid_con
                     // same expression order as lstm_gate_kernel: table + gates, then the cell
                     const float gi = x[0][k] + __uint_as_float(v[0][k]), gf = x[1][k] + __uint_as_float(v[1][k]);
                     const float gg = x[2][k] + __uint_as_float(v[2][k]), go = x[3][k] + __uint_as_float(v[3][k]);
+                    if (p.dbg & 4) { c[ug + k] = 0.5f * c[ug + k] + gf * gi + gg; h[k] = go * 0.001f + c[ug + k] * 0.001f; continue; }
                     c[ug + k] = sigmoid_fast(gf) * c[ug + k] + sigmoid_fast(gi) * tanh_fast(gg);
                     h[k] = sigmoid_fast(go) * tanh_fast(c[ug + k]);
                 }
                 if (valid) {
+                    if (!(p.dbg & 2)) {
                     *reinterpret_cast<float4*>(op + ug) = make_float4(h[0], h[1], h[2], h[3]);
                     *reinterpret_cast<float4*>(op + ug + 4) = make_float4(h[4], h[5], h[6], h[7]);
-                    if (t + 1 < Tp) {
-                        tc_split_store4(make_float4(h[0], h[1], h[2], h[3]), pr + ug, pr + LP_H + ug);
-                        tc_split_store4(make_float4(h[4], h[5], h[6], h[7]), pr + ug + 4, pr + LP_H + ug + 4);
+                    }
+                    if (t + 1 < Tp && !(p.dbg & 16)) {
+                        // hi / lo planes of the 8 units: one 16-byte store each (same rounding as tc_split_store4)
+                        uint32_t ph[4], pl[4];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const __nv_bfloat16 a = __float2bfloat16_rn(h[2 * k]), b = __float2bfloat16_rn(h[2 * k + 1]);
+                            const __nv_bfloat162 hh = __halves2bfloat162(a, b);
+                            const __nv_bfloat162 ll = __halves2bfloat162(__float2bfloat16_rn(h[2 * k] - __bfloat162float(a)),
+                                                                         __float2bfloat16_rn(h[2 * k + 1] - __bfloat162float(b)));
+                            ph[k] = *reinterpret_cast<const uint32_t*>(&hh);
+                            pl[k] = *reinterpret_cast<const uint32_t*>(&ll);
+                        }
+                        *reinterpret_cast<uint4*>(pr + ug) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+                        *reinterpret_cast<uint4*>(pr + LP_H + ug) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
                     }
                 }
             }
@@ -288,6 +304,15 @@ lstm_persist_kernel(const __grid_constant__ CUtensorMap map_h0, const __grid_con
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
     }
+}
+
+// table[code][gate * 256 + unit]  ->  perm[code][unit / 8][gate][unit % 8]: what a thread of the epilogue needs for one
+// 8-unit chunk (4 gates x 8 units) is one aligned 128-byte line instead of four 32-byte pieces 1 KB apart
+__global__ void lp_permute_table_kernel(const float* __restrict__ table, float* __restrict__ perm, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int code = i / LP_G, r = i % LP_G, g = r / LP_H, u = r % LP_H;
+    perm[static_cast<int64_t>(code) * LP_G + (u >> 3) * 32 + g * 8 + (u & 7)] = table[i];
 }
 
 // ------------------------------------------------------------------------------------------------ host
@@ -350,11 +375,17 @@ int lstm_persist_max_rows() {
     return 2 * (sms / 8) * TC_BM;
 }
 size_t lstm_persist_counter_bytes() { return 64 * sizeof(unsigned); }
+size_t lstm_persist_table_bytes() { return sizeof(float) * 512 * LP_G; }
 
-// planes: two (B, 512) bf16 buffers; counters: >= lstm_persist_counter_bytes(), any content (zeroed here)
-int lstm_persist(const float* table, const int64_t* idx, const void* whh_planes, int B, int Tp, void* planes0, void* planes1,
-                 unsigned* counters, float* out, int* err_flag, cudaStream_t stream) {
-    VQ_ARG(table && idx && whh_planes && planes0 && planes1 && counters && out && err_flag, "lstm_persist: null pointer");
+// planes: two (B, 512) bf16 buffers; counters: >= lstm_persist_counter_bytes(), any content (zeroed here); table_perm:
+// lstm_persist_table_bytes() of scratch for the permuted copy of the input-projection table
+int lstm_persist(const float* table_in, const int64_t* idx, const void* whh_planes, int B, int Tp, void* planes0, void* planes1,
+                 unsigned* counters, float* table_perm, float* out, int* err_flag, cudaStream_t stream) {
+    VQ_ARG(table_in && idx && whh_planes && planes0 && planes1 && counters && table_perm && out && err_flag, "lstm_persist: null pointer");
+    lp_permute_table_kernel<<<(512 * LP_G + 255) / 256, 256, 0, stream>>>(table_in, table_perm, 512 * LP_G);
+    VQ_CUDA(cudaGetLastError());
+    count_launch(1);
+    const float* table = table_perm;
     const int max_rows = lstm_persist_max_rows();
     VQ_ARG(max_rows >= TC_BM, "lstm_persist: device too small");
     const int n_chunks = (B + max_rows - 1) / max_rows;
@@ -369,6 +400,7 @@ int lstm_persist(const float* table, const int64_t* idx, const void* whh_planes,
         // 12.1 vs 11.9) -- the step is a latency chain (counter hop, TMA first byte, 128 KB of shared-memory ingest per CTA either
         // way, MMA operand reads, epilogue, store visibility), not L2-bandwidth bound.
         static const int lp_cs = [] { const char* e = getenv("VQCPC_LSTM_CLUSTER"); return (e && e[0] == '4') ? 4 : 1; }();
+        static const int lp_dbg = [] { const char* e = getenv("VQCPC_LP_DEBUG"); return e ? atoi(e) : 0; }();
         int rc = VQCPC_ERR_ARG;
         bool done = false;
         auto try_cfg = [&](auto utc, auto ntc, auto csc) {
@@ -386,7 +418,7 @@ int lstm_persist(const float* table, const int64_t* idx, const void* whh_planes,
             if (cudaMemsetAsync(counters, 0, lstm_persist_counter_bytes(), stream) != cudaSuccess) { rc = VQCPC_ERR_CUDA; done = true; return; }
             LpParams p{};
             p.table = table; p.idx = idx + static_cast<int64_t>(b0) * Tp; p.out = out + static_cast<int64_t>(b0) * Tp * LP_H;
-            p.planes[0] = p0; p.planes[1] = p1; p.counters = counters; p.err = err_flag; p.B = nb; p.Tp = Tp; p.n_ns = n_ns;
+            p.planes[0] = p0; p.planes[1] = p1; p.counters = counters; p.err = err_flag; p.B = nb; p.Tp = Tp; p.n_ns = n_ns; p.dbg = lp_dbg;
             rc = lp_launch<UT_, NT_, CS_>(h0, h1, mw, p, n_mt, stream);
             done = true;
         };
