@@ -1,0 +1,5 @@
+#!/bin/bash
+mkdir -p gpurun_out
+python tools/lstm_time.py 64 512 1024 2048 4096 > gpurun_out/lp_final.log 2>&1
+python -m pytest tests -m gpu -x -q >> gpurun_out/lp_final.log 2>&1
+python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err

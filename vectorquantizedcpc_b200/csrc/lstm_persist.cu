@@ -19,6 +19,7 @@
 //     each and TMA-multicast it to all four (the L2 -> SM traffic, 16 MB per step at 512 utterances, was what bound the step).
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <type_traits>
 
@@ -43,6 +44,8 @@ struct LpParams {
     int dbg;                     // VQCPC_LP_DEBUG ablation bits (timing only; results are wrong with any bit set)
 };
 
+__device__ long long lp_trace[8 * 8];     // VQCPC_LP_DEBUG & 32: clock64 stamps of CTA 0, row tile 0, steps 60..67 (printed by the host)
+#define LP_STAMP(slot) do { if ((p.dbg & 32) && blockIdx.x == 0 && t >= 60 && t < 68) lp_trace[(t - 60) * 8 + (slot)] = clock64(); } while (0)
 __device__ __forceinline__ int lp_clamp_code(int64_t id) { return id < 0 ? 0 : (id > 511 ? 511 : static_cast<int>(id)); }
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
     unsigned v;
@@ -67,11 +70,15 @@ __device__ __forceinline__ void tc_commit_mc(uint64_t* bar, uint16_t mask) {
 }
 
 // CS = cluster size (1: every CTA loads its own copy of h_{t-1}; 4: each loads a quarter and multicasts it)
-template <int UT, int NT, int CS>
-__global__ void __launch_bounds__(64 + 128 * NT, 1)
+// EW = epilogue warps per row tile (4, 8 or 16)
+template <int UT, int NT, int CS, int EW>
+__global__ void __launch_bounds__(64 + 32 * EW * NT, 1)
 lstm_persist_kernel(const __grid_constant__ CUtensorMap map_h0, const __grid_constant__ CUtensorMap map_h1,
                     const __grid_constant__ CUtensorMap map_w, LpParams p) {
     constexpr int N = 4 * UT;                                   // gate columns of this CTA: [i | f | g | o] x UT units
+    constexpr int UW = UT / (EW / 4);                           // hidden units per epilogue warp
+    constexpr int CH = (UW >= 8 && 64 + 32 * EW * NT <= 384) ? 8 : 4;   // units per chunk (register budget)
+    static_assert(EW % 4 == 0 && UW >= 4 && UW % CH == 0, "epilogue split");
     constexpr uint32_t A_TILE = TC_BM * TC_BK * 2;              // 16 KB
     constexpr uint32_t STAGE_BYTES = 2 * A_TILE;                // hi + lo tile of one k-block
     constexpr int STAGES = UT == 32 ? 3 : 4;
@@ -95,7 +102,7 @@ lstm_persist_kernel(const __grid_constant__ CUtensorMap map_h0, const __grid_con
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], CS); }
-        for (int j = 0; j < NT; ++j) { mbar_init(&tfull_bar[j], 1); mbar_init(&tempty_bar[j], 4); }
+        for (int j = 0; j < NT; ++j) { mbar_init(&tfull_bar[j], 1); mbar_init(&tempty_bar[j], EW); }
         mbar_init(&w_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -132,12 +139,13 @@ lstm_persist_kernel(const __grid_constant__ CUtensorMap map_h0, const __grid_con
                 if (mt * TC_BM >= p.B) continue;                      // an odd number of row tiles: the last CTA row has one
                 const unsigned* ctr = p.counters + mt;
                 // h_{t-1} of this row tile is complete once all n_ns CTAs of the tile have finished step t-1
-                const unsigned want = 4u * static_cast<unsigned>(p.n_ns) * static_cast<unsigned>(t);   // four epilogue warps per CTA
+                const unsigned want = static_cast<unsigned>(EW) * static_cast<unsigned>(p.n_ns) * static_cast<unsigned>(t);   // EW epilogue warps per CTA
                 const long long t0 = clock64();
                 while (!(p.dbg & 8) && ld_acquire_u32(ctr) < want) {
                     if (clock64() - t0 > TC_TIMEOUT) { atomicExch(p.err, VQCPC_ERR_TIMEOUT); ok = false; break; }
                 }
                 if (!ok) break;
+                if (j == 0) LP_STAMP(0);
                 asm volatile("fence.proxy.async;" ::: "memory");          // other CTAs' generic-proxy stores -> TMA reads
                 const CUtensorMap* mh = ((t - 1) & 1) ? &map_h1 : &map_h0;
                 for (int kb = 0; kb < LP_KB && ok; ++kb) {
@@ -155,6 +163,7 @@ lstm_persist_kernel(const __grid_constant__ CUtensorMap map_h0, const __grid_con
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
+                if (j == 0) LP_STAMP(1);
             }
         }
     } else if (warp == 1) {
@@ -174,6 +183,8 @@ lstm_persist_kernel(const __grid_constant__ CUtensorMap map_h0, const __grid_con
                 for (int kb = 0; kb < LP_KB && ok; ++kb) {
                     ok = mbar_wait(&full_bar[stage], phase, p.err);
                     if (!ok) break;
+                    if (j == 0 && kb == 0) LP_STAMP(2);
+                    if (j == 0 && kb == LP_KB - 1) LP_STAMP(3);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(a_s + stage * STAGE_BYTES);
                     const uint64_t a_hi = umma_desc_sw128(sa), a_lo = umma_desc_sw128(sa + A_TILE);
@@ -193,30 +204,36 @@ lstm_persist_kernel(const __grid_constant__ CUtensorMap map_h0, const __grid_con
         }
     } else {
         // ------------------------------------------------------------------ epilogue: thread = utterance (TMEM lane)
+        // EW warps per row tile: warp = (TMEM lane quarter, column group); a column group is UW = UT / (EW / 4) hidden units,
+        // worked through in chunks of CH units.  With ONE warp per scheduler the epilogue was a serial latency chain (TMEM read ->
+        // table lines -> ten MUFU-deep gate math -> stores: 3 500 cycles per 8 units, 14 300 per step at UT = 32); several
+        // warps per scheduler overlap those chains.
         const int quarter = warp & 3;                           // TMEM lanes 32 quarter .. +31 (a warp may only touch its own quarter)
-        const int j = (warp - 2) >> 2;                          // row tile of this warp group
+        const int e = warp - 2;
+        const int j = e / EW;                                   // row tile of this warp
+        const int ub = ((e % EW) >> 2) * UW;                    // first unit (within the CTA's UT) of this warp's column group
         const int mt = mt0 + j;
         const int row = mt * TC_BM + quarter * 32 + lane;
         const bool valid = row < p.B;
         const bool tile_live = mt * TC_BM < p.B;
         const uint32_t tb = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + j * N;
         const int64_t* irow = p.idx + static_cast<int64_t>(valid ? row : 0) * Tp;
-        float c[UT];
+        float c[UW];
 #pragma unroll
-        for (int k = 0; k < UT; ++k) c[k] = 0.f;
+        for (int k = 0; k < UW; ++k) c[k] = 0.f;
         uint32_t tphase = 0;
         bool ok = true;
         int code = valid ? lp_clamp_code(__ldg(irow)) : 0;
-        // table values of the first 8-unit chunk of step 0 (every later chunk is prefetched one chunk / one step ahead)
-        float4 xa[4], xb[4];
+        // table values of the first chunk of step 0 (every later chunk is prefetched one chunk / one step ahead)
+        float4 xq[4][CH / 4];
         auto fetch = [&](int cd, int ug) {
-            // permuted table (lp_permute_table_kernel): the 4 gates x 8 units of a chunk are ONE 128-byte line
-            const float4* tr = reinterpret_cast<const float4*>(p.table + static_cast<int64_t>((p.dbg & 1) ? 0 : cd) * LP_G + (u0 + ug) * 4);
+            // permuted table (lp_permute_table_kernel): the 4 gates x 8 units of an aligned 8-unit group are ONE 128-byte line
+            const int u = u0 + ub + ug;
+            const float4* tr = reinterpret_cast<const float4*>(p.table + static_cast<int64_t>((p.dbg & 1) ? 0 : cd) * LP_G + (u >> 3) * 32 + (u & 7));
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-                xa[g] = __ldg(tr + 2 * g);
-                xb[g] = __ldg(tr + 2 * g + 1);
-            }
+            for (int g = 0; g < 4; ++g)
+#pragma unroll
+                for (int q = 0; q < CH / 4; ++q) xq[g][q] = __ldg(tr + 2 * g + q);
         };
         fetch(code, 0);
         for (int t = 0; t < Tp && ok && tile_live; ++t) {
@@ -227,34 +244,38 @@ lstm_persist_kernel(const __grid_constant__ CUtensorMap map_h0, const __grid_con
                 if (!ok) break;
                 tphase ^= 1;
                 tc_fence_after();
+                if (warp == 2 && lane == 0) LP_STAMP(4);
             }
-            float* op = p.out + (static_cast<int64_t>(valid ? row : 0) * Tp + t) * LP_H + u0;
-            __nv_bfloat16* pr = p.planes[t & 1] + static_cast<int64_t>(valid ? row : 0) * 2 * LP_H + u0;
+            float* op = p.out + (static_cast<int64_t>(valid ? row : 0) * Tp + t) * LP_H + u0 + ub;
+            __nv_bfloat16* pr = p.planes[t & 1] + static_cast<int64_t>(valid ? row : 0) * 2 * LP_H + u0 + ub;
 #pragma unroll
-            for (int ug = 0; ug < UT; ug += 8) {
-                uint32_t v[4][8];
+            for (int ug = 0; ug < UW; ug += CH) {
+                uint32_t v[4][CH];
                 if (t > 0) {
 #pragma unroll
-                    for (int g = 0; g < 4; ++g) tc_ld8(tb + g * UT + ug, v[g]);
+                    for (int g = 0; g < 4; ++g) {
+                        if constexpr (CH == 8) tc_ld8(tb + g * UT + ub + ug, v[g]); else tc_ld4(tb + g * UT + ub + ug, v[g]);
+                    }
                     tc_wait_ld();
                 } else {
 #pragma unroll
                     for (int g = 0; g < 4; ++g)
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) v[g][k] = 0u;
+                        for (int k = 0; k < CH; ++k) v[g][k] = 0u;
                 }
-                float x[4][8];
+                float x[4][CH];
 #pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    x[g][0] = xa[g].x; x[g][1] = xa[g].y; x[g][2] = xa[g].z; x[g][3] = xa[g].w;
-                    x[g][4] = xb[g].x; x[g][5] = xb[g].y; x[g][6] = xb[g].z; x[g][7] = xb[g].w;
-                }
+                for (int g = 0; g < 4; ++g)
+#pragma unroll
+                    for (int q = 0; q < CH / 4; ++q) {
+                        x[g][4 * q + 0] = xq[g][q].x; x[g][4 * q + 1] = xq[g][q].y; x[g][4 * q + 2] = xq[g][q].z; x[g][4 * q + 3] = xq[g][q].w;
+                    }
                 // prefetch the next chunk (of this step, or chunk 0 of the next step) while this one is computed
-                if (ug + 8 < UT) fetch(code, ug + 8);
+                if (ug + CH < UW) fetch(code, ug + CH);
                 else if (t + 1 < Tp) fetch(code_next, 0);
-                float h[8];
+                float h[CH];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
+                for (int k = 0; k < CH; ++k) {
                     // same expression order as lstm_gate_kernel: table + gates, then the cell
                     const float gi = x[0][k] + __uint_as_float(v[0][k]), gf = x[1][k] + __uint_as_float(v[1][k]);
                     const float gg = x[2][k] + __uint_as_float(v[2][k]), go = x[3][k] + __uint_as_float(v[3][k]);
@@ -264,14 +285,15 @@ lstm_persist_kernel(const __grid_constant__ CUtensorMap map_h0, const __grid_con
                 }
                 if (valid) {
                     if (!(p.dbg & 2)) {
-                    *reinterpret_cast<float4*>(op + ug) = make_float4(h[0], h[1], h[2], h[3]);
-                    *reinterpret_cast<float4*>(op + ug + 4) = make_float4(h[4], h[5], h[6], h[7]);
+#pragma unroll
+                        for (int q = 0; q < CH / 4; ++q)
+                            *reinterpret_cast<float4*>(op + ug + 4 * q) = make_float4(h[4 * q], h[4 * q + 1], h[4 * q + 2], h[4 * q + 3]);
                     }
                     if (t + 1 < Tp && !(p.dbg & 16)) {
-                        // hi / lo planes of the 8 units: one 16-byte store each (same rounding as tc_split_store4)
-                        uint32_t ph[4], pl[4];
+                        // hi / lo planes of the chunk: one 16-byte (8 units) or 8-byte (4 units) store each; same rounding as tc_split_store4
+                        uint32_t ph[CH / 2], pl[CH / 2];
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
+                        for (int k = 0; k < CH / 2; ++k) {
                             const __nv_bfloat16 a = __float2bfloat16_rn(h[2 * k]), b = __float2bfloat16_rn(h[2 * k + 1]);
                             const __nv_bfloat162 hh = __halves2bfloat162(a, b);
                             const __nv_bfloat162 ll = __halves2bfloat162(__float2bfloat16_rn(h[2 * k] - __bfloat162float(a)),
@@ -279,21 +301,30 @@ lstm_persist_kernel(const __grid_constant__ CUtensorMap map_h0, const __grid_con
                             ph[k] = *reinterpret_cast<const uint32_t*>(&hh);
                             pl[k] = *reinterpret_cast<const uint32_t*>(&ll);
                         }
-                        *reinterpret_cast<uint4*>(pr + ug) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-                        *reinterpret_cast<uint4*>(pr + LP_H + ug) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+                        if constexpr (CH == 8) {
+                            *reinterpret_cast<uint4*>(pr + ug) = make_uint4(ph[0], ph[1], ph[CH / 2 - 2], ph[CH / 2 - 1]);
+                            *reinterpret_cast<uint4*>(pr + LP_H + ug) = make_uint4(pl[0], pl[1], pl[CH / 2 - 2], pl[CH / 2 - 1]);
+                        } else {
+                            *reinterpret_cast<uint2*>(pr + ug) = make_uint2(ph[0], ph[1]);
+                            *reinterpret_cast<uint2*>(pr + LP_H + ug) = make_uint2(pl[0], pl[1]);
+                        }
                     }
                 }
             }
             code = code_next;
             if (t + 1 < Tp) {
-                // this warp's h_t is written: publish (release) and hand the accumulator back
+                // this warp's h_t is written: publish and hand the accumulator back.  The lanes' stores are ordered before lane
+                // 0's gpu-scope release by the warp barrier (the pattern of a grid barrier: block barrier, then ONE thread fences);
+                // a fence in every lane (VQCPC_LP_DEBUG & 64) cost ~1 000 cycles more per step
+                if (warp == 2 && lane == 0) LP_STAMP(5);
                 tc_fence_before();
-                __threadfence();
+                if (p.dbg & 64) __threadfence();
                 __syncwarp();
                 if (lane == 0) {
                     mbar_arrive(&tempty_bar[j]);
-                    red_release_add_u32(p.counters + mt, 1u);              // four arrivals per CTA and step
+                    red_release_add_u32(p.counters + mt, 1u);              // EW arrivals per CTA and step
                 }
+                if (warp == 2 && lane == 0) LP_STAMP(6);
             }
         }
     }
@@ -318,16 +349,16 @@ __global__ void lp_permute_table_kernel(const float* __restrict__ table, float* 
 // ------------------------------------------------------------------------------------------------ host
 int make_map_bf16(void* map, const void* base, long long rows, long long cols, long long ld_elems, int box_rows);
 
-template <int UT, int NT, int CS>
+template <int UT, int NT, int CS, int EW>
 static size_t lp_smem() {
     constexpr int N = 4 * UT;
     constexpr int STAGES = UT == 32 ? 3 : 4;
     return 2 * LP_KB * N * TC_BK * 2 + STAGES * 2 * TC_BM * TC_BK * 2 + 1024;
 }
-template <int UT, int NT, int CS>
+template <int UT, int NT, int CS, int EW>
 static void lp_config(cudaLaunchConfig_t* cfg, cudaLaunchAttribute* attr, int n_ctas, cudaStream_t stream) {
     *cfg = cudaLaunchConfig_t{};
-    cfg->gridDim = dim3(n_ctas); cfg->blockDim = dim3(64 + 128 * NT); cfg->dynamicSmemBytes = lp_smem<UT, NT, CS>(); cfg->stream = stream;
+    cfg->gridDim = dim3(n_ctas); cfg->blockDim = dim3(64 + 32 * EW * NT); cfg->dynamicSmemBytes = lp_smem<UT, NT, CS, EW>(); cfg->stream = stream;
     attr[0].id = cudaLaunchAttributeCooperative;          // all CTAs co-resident, or the launch fails (never a silent hang)
     attr[0].val.cooperative = 1;
     attr[1].id = cudaLaunchAttributeClusterDimension;
@@ -335,36 +366,36 @@ static void lp_config(cudaLaunchConfig_t* cfg, cudaLaunchAttribute* attr, int n_
     cfg->attrs = attr; cfg->numAttrs = CS > 1 ? 2 : 1;
 }
 // how many CTAs of this instantiation the device holds at once (0 on error), cached per device
-template <int UT, int NT, int CS>
+template <int UT, int NT, int CS, int EW>
 static int lp_capacity() {
     static int cache[64] = {0};
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;
     if (cache[dev]) return cache[dev] > 0 ? cache[dev] : 0;
     int cap = 0;
-    if (ensure_dyn_smem(reinterpret_cast<const void*>(lstm_persist_kernel<UT, NT, CS>), static_cast<int>(lp_smem<UT, NT, CS>())) == VQCPC_OK) {
+    if (ensure_dyn_smem(reinterpret_cast<const void*>(lstm_persist_kernel<UT, NT, CS, EW>), static_cast<int>(lp_smem<UT, NT, CS, EW>())) == VQCPC_OK) {
         if (CS == 1) {
             int per_sm = 0;
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lstm_persist_kernel<UT, NT, CS>, 64 + 128 * NT, lp_smem<UT, NT, CS>()) == cudaSuccess)
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lstm_persist_kernel<UT, NT, CS, EW>, 64 + 32 * EW * NT, lp_smem<UT, NT, CS, EW>()) == cudaSuccess)
                 cap = per_sm * device_sm_count();
         } else {
             cudaLaunchConfig_t cfg; cudaLaunchAttribute attr[2];
-            lp_config<UT, NT, CS>(&cfg, attr, CS, nullptr);
+            lp_config<UT, NT, CS, EW>(&cfg, attr, CS, nullptr);
             cfg.numAttrs = 2; attr[0] = attr[1]; cfg.numAttrs = 1;      // occupancy query: cluster dimension only
             int ncl = 0;
-            if (cudaOccupancyMaxActiveClusters(&ncl, lstm_persist_kernel<UT, NT, CS>, &cfg) == cudaSuccess) cap = ncl * CS;
+            if (cudaOccupancyMaxActiveClusters(&ncl, lstm_persist_kernel<UT, NT, CS, EW>, &cfg) == cudaSuccess) cap = ncl * CS;
         }
     }
     cudaGetLastError();
     cache[dev] = cap > 0 ? cap : -1;
     return cap;
 }
-template <int UT, int NT, int CS>
+template <int UT, int NT, int CS, int EW>
 static int lp_launch(const CUtensorMap& h0, const CUtensorMap& h1, const CUtensorMap& mw, LpParams p, int n_mt, cudaStream_t stream) {
-    if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(lstm_persist_kernel<UT, NT, CS>), static_cast<int>(lp_smem<UT, NT, CS>()))) return rc;
+    if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(lstm_persist_kernel<UT, NT, CS, EW>), static_cast<int>(lp_smem<UT, NT, CS, EW>()))) return rc;
     cudaLaunchConfig_t cfg; cudaLaunchAttribute attr[2];
-    lp_config<UT, NT, CS>(&cfg, attr, ((n_mt + NT - 1) / NT) * p.n_ns, stream);
-    VQ_CUDA(cudaLaunchKernelEx(&cfg, lstm_persist_kernel<UT, NT, CS>, h0, h1, mw, p));
+    lp_config<UT, NT, CS, EW>(&cfg, attr, ((n_mt + NT - 1) / NT) * p.n_ns, stream);
+    VQ_CUDA(cudaLaunchKernelEx(&cfg, lstm_persist_kernel<UT, NT, CS, EW>, h0, h1, mw, p));
     count_launch(1);
     return VQCPC_OK;
 }
@@ -403,12 +434,17 @@ int lstm_persist(const float* table_in, const int64_t* idx, const void* whh_plan
         static const int lp_dbg = [] { const char* e = getenv("VQCPC_LP_DEBUG"); return e ? atoi(e) : 0; }();
         int rc = VQCPC_ERR_ARG;
         bool done = false;
-        auto try_cfg = [&](auto utc, auto ntc, auto csc) {
-            constexpr int UT_ = decltype(utc)::value, NT_ = decltype(ntc)::value, CS_ = decltype(csc)::value;
-            if (done || (CS_ > 1 && lp_cs == 1)) return;
+        // epilogue warps per row tile: eight (two per scheduler) with one row tile per CTA, four with two (the two tiles' epilogues
+        // already overlap).  Measured on random codes, us/step at 512 / 1024 / 2048 / 4096 utterances: four warps 6.25 / 8.27 / 12.9 /
+        // 16.6, eight 6.11 / 7.32 / 11.0 / 17.5, sixteen - / 7.91 / 11.4 / -.  VQCPC_LP_EW=1 forces four everywhere (A/B).
+        static const int lp_ew = [] { const char* e = getenv("VQCPC_LP_EW"); return (e && e[0] == '1') ? 1 : 2; }();
+        auto try_cfg = [&](auto utc, auto ntc, auto csc, auto ewc) {
+            constexpr int UT_ = decltype(utc)::value, NT_ = decltype(ntc)::value, CS_ = decltype(csc)::value, EW_ = decltype(ewc)::value;
+            if (done || (CS_ > 1) != (lp_cs > 1)) return;
+            if (EW_ != ((NT_ == 2 || lp_ew == 1) ? 4 : 8)) return;
             const int n_ns = LP_H / UT_;
             const int ctas = ((n_mt + NT_ - 1) / NT_) * n_ns;
-            if (ctas > lp_capacity<UT_, NT_, CS_>()) return;
+            if (ctas > lp_capacity<UT_, NT_, CS_, EW_>()) return;
             alignas(64) CUtensorMap h0, h1;
             __nv_bfloat16* p0 = static_cast<__nv_bfloat16*>(planes0) + static_cast<int64_t>(b0) * 2 * LP_H;
             __nv_bfloat16* p1 = static_cast<__nv_bfloat16*>(planes1) + static_cast<int64_t>(b0) * 2 * LP_H;
@@ -419,15 +455,31 @@ int lstm_persist(const float* table_in, const int64_t* idx, const void* whh_plan
             LpParams p{};
             p.table = table; p.idx = idx + static_cast<int64_t>(b0) * Tp; p.out = out + static_cast<int64_t>(b0) * Tp * LP_H;
             p.planes[0] = p0; p.planes[1] = p1; p.counters = counters; p.err = err_flag; p.B = nb; p.Tp = Tp; p.n_ns = n_ns; p.dbg = lp_dbg;
-            rc = lp_launch<UT_, NT_, CS_>(h0, h1, mw, p, n_mt, stream);
+            rc = lp_launch<UT_, NT_, CS_, EW_>(h0, h1, mw, p, n_mt, stream);
             done = true;
         };
         using I1 = std::integral_constant<int, 1>; using I2 = std::integral_constant<int, 2>; using I4 = std::integral_constant<int, 4>;
         using U8 = std::integral_constant<int, 8>; using U16 = std::integral_constant<int, 16>; using U32 = std::integral_constant<int, 32>;
-        try_cfg(U8{}, I1{}, I4{});  try_cfg(U16{}, I1{}, I4{}); try_cfg(U32{}, I1{}, I4{}); try_cfg(U32{}, I2{}, I4{});
-        try_cfg(U8{}, I1{}, I1{});  try_cfg(U16{}, I1{}, I1{}); try_cfg(U32{}, I1{}, I1{}); try_cfg(U32{}, I2{}, I1{});
+        using E4 = std::integral_constant<int, 4>; using E8 = std::integral_constant<int, 8>;
+        auto try_ut = [&](auto utc, auto ntc, auto csc) {
+            constexpr int NT_ = decltype(ntc)::value;
+            try_cfg(utc, ntc, csc, E4{});
+            if constexpr (NT_ == 1) try_cfg(utc, ntc, csc, E8{});
+        };
+        try_ut(U8{}, I1{}, I4{});  try_ut(U16{}, I1{}, I4{}); try_ut(U32{}, I1{}, I4{}); try_ut(U32{}, I2{}, I4{});
+        try_ut(U8{}, I1{}, I1{});  try_ut(U16{}, I1{}, I1{}); try_ut(U32{}, I1{}, I1{}); try_ut(U32{}, I2{}, I1{});
         if (!done) { set_error("lstm_persist: no configuration fits the device (%d row tiles)", n_mt); return VQCPC_ERR_CUDA; }
         if (rc) return rc;
+        if (lp_dbg & 32) {
+            long long tr[64];
+            cudaStreamSynchronize(stream);
+            if (cudaMemcpyFromSymbol(tr, lp_trace, sizeof(tr)) == cudaSuccess)
+                for (int s = 0; s + 1 < 8; ++s)
+                    fprintf(stderr, "lp step %d: counter ok 0 | TMA issued %lld | first stage full %lld | last stage full %lld | accumulator full %lld | "
+                            "epilogue done %lld | published %lld | next counter ok %lld\n", 60 + s, tr[s * 8 + 1] - tr[s * 8], tr[s * 8 + 2] - tr[s * 8],
+                            tr[s * 8 + 3] - tr[s * 8], tr[s * 8 + 4] - tr[s * 8], tr[s * 8 + 5] - tr[s * 8], tr[s * 8 + 6] - tr[s * 8],
+                            tr[(s + 1) * 8] - tr[s * 8]);
+        }
     }
     return VQCPC_OK;
 }

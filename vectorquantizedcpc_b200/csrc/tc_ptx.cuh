@@ -66,6 +66,10 @@ __device__ __forceinline__ void tc_ld8(uint32_t taddr, uint32_t (&v)[8]) {
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
                  : "r"(taddr) : "memory");
 }
+__device__ __forceinline__ void tc_ld4(uint32_t taddr, uint32_t (&v)[4]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(taddr) : "memory");
+}
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tc_split_store4(float4 o, __nv_bfloat16* hi, __nv_bfloat16* lo) {
     const __nv_bfloat16 h0 = __float2bfloat16_rn(o.x), h1 = __float2bfloat16_rn(o.y), h2 = __float2bfloat16_rn(o.z),
