@@ -218,7 +218,7 @@ lstm_persist_kernel(const __grid_constant__ CUtensorMap map_h0, const __grid_con
         const bool tile_live = mt * TC_BM < p.B;
         const uint32_t tb = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + j * N;
         const int64_t* irow = p.idx + static_cast<int64_t>(valid ? row : 0) * Tp;
-        float c[UW];
+        float c[UW], hout[UW];
 #pragma unroll
         for (int k = 0; k < UW; ++k) c[k] = 0.f;
         uint32_t tphase = 0;
@@ -283,12 +283,9 @@ lstm_persist_kernel(const __grid_constant__ CUtensorMap map_h0, const __grid_con
                     c[ug + k] = sigmoid_fast(gf) * c[ug + k] + sigmoid_fast(gi) * tanh_fast(gg);
                     h[k] = sigmoid_fast(go) * tanh_fast(c[ug + k]);
                 }
-                if (valid) {
-                    if (!(p.dbg & 2)) {
 #pragma unroll
-                        for (int q = 0; q < CH / 4; ++q)
-                            *reinterpret_cast<float4*>(op + ug + 4 * q) = make_float4(h[4 * q], h[4 * q + 1], h[4 * q + 2], h[4 * q + 3]);
-                    }
+                for (int k = 0; k < CH; ++k) hout[ug + k] = h[k];
+                if (valid) {
                     if (t + 1 < Tp && !(p.dbg & 16)) {
                         // hi / lo planes of the chunk: one 16-byte (8 units) or 8-byte (4 units) store each; same rounding as tc_split_store4
                         uint32_t ph[CH / 2], pl[CH / 2];
@@ -325,6 +322,12 @@ lstm_persist_kernel(const __grid_constant__ CUtensorMap map_h0, const __grid_con
                     red_release_add_u32(p.counters + mt, 1u);              // EW arrivals per CTA and step
                 }
                 if (warp == 2 && lane == 0) LP_STAMP(6);
+            }
+            // the fp32 output sequence is nobody's input: stored AFTER the release, so that the release waits only for the planes
+            if (valid && !(p.dbg & 2)) {
+#pragma unroll
+                for (int q = 0; q < UW / 4; ++q)
+                    *reinterpret_cast<float4*>(op + 4 * q) = make_float4(hout[4 * q], hout[4 * q + 1], hout[4 * q + 2], hout[4 * q + 3]);
             }
         }
     }
