@@ -46,6 +46,20 @@ struct LpParams {
 
 __device__ long long lp_trace[8 * 8];     // VQCPC_LP_DEBUG & 32: clock64 stamps of CTA 0, row tile 0, steps 60..67 (printed by the host)
 #define LP_STAMP(slot) do { if ((p.dbg & 32) && blockIdx.x == 0 && t >= 60 && t < 68) lp_trace[(t - 60) * 8 + (slot)] = clock64(); } while (0)
+// LSTM cell with 7 MUFU instead of 10: the three sigmoids / two tanhs of  c' = s(f) c + s(i) tanh(g),  h = s(o) tanh(c')  put on
+// common denominators -- c' = [c (1+Ei)(1+Eg) + (1-Eg)(1+Ef)] / [(1+Ef)(1+Ei)(1+Eg)],  h = (1-Ec) / [(1+Eo)(1+Ec)]  with
+// Ex = e^-x (sigmoid) or e^-2x (tanh) from ex2.approx, one rcp.approx each.  Arguments are clamped from below (-28 / -14) so that
+// a product of three (1 + E) terms stays finite (<= e^84); there sigmoid / 1 + tanh are < 7e-13, below fp32 resolution of the sums.
+__device__ __forceinline__ float lp_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float lp_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float lp_cell(float gi, float gf, float gg, float go, float& c) {
+    constexpr float L2E = 1.4426950408889634f;
+    const float ef = lp_ex2(-L2E * fmaxf(gf, -28.f)), ei = lp_ex2(-L2E * fmaxf(gi, -28.f)), eg = lp_ex2(-2.f * L2E * fmaxf(gg, -14.f));
+    const float a = 1.f + ef, big = (1.f + ei) * (1.f + eg);
+    c = fmaf(c, big, (1.f - eg) * a) * lp_rcp(a * big);
+    const float eo = lp_ex2(-L2E * fmaxf(go, -28.f)), ec = lp_ex2(-2.f * L2E * fmaxf(c, -14.f));
+    return (1.f - ec) * lp_rcp((1.f + eo) * (1.f + ec));
+}
 __device__ __forceinline__ int lp_clamp_code(int64_t id) { return id < 0 ? 0 : (id > 511 ? 511 : static_cast<int>(id)); }
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
     unsigned v;
@@ -70,15 +84,14 @@ __device__ __forceinline__ void tc_commit_mc(uint64_t* bar, uint16_t mask) {
 }
 
 // CS = cluster size (1: every CTA loads its own copy of h_{t-1}; 4: each loads a quarter and multicasts it)
-// EW = epilogue warps per row tile (4, 8 or 16)
+// EW = epilogue warps per row tile (4 or 8)
 template <int UT, int NT, int CS, int EW>
 __global__ void __launch_bounds__(64 + 32 * EW * NT, 1)
 lstm_persist_kernel(const __grid_constant__ CUtensorMap map_h0, const __grid_constant__ CUtensorMap map_h1,
                     const __grid_constant__ CUtensorMap map_w, LpParams p) {
     constexpr int N = 4 * UT;                                   // gate columns of this CTA: [i | f | g | o] x UT units
     constexpr int UW = UT / (EW / 4);                           // hidden units per epilogue warp
-    constexpr int CH = (UW >= 8 && 64 + 32 * EW * NT <= 384) ? 8 : 4;   // units per chunk (register budget)
-    static_assert(EW % 4 == 0 && UW >= 4 && UW % CH == 0, "epilogue split");
+    static_assert(EW % 4 == 0 && UW % 8 == 0, "epilogue split: whole 8-unit groups per warp");
     constexpr uint32_t A_TILE = TC_BM * TC_BK * 2;              // 16 KB
     constexpr uint32_t STAGE_BYTES = 2 * A_TILE;                // hi + lo tile of one k-block
     constexpr int STAGES = UT == 32 ? 3 : 4;
@@ -203,41 +216,57 @@ lstm_persist_kernel(const __grid_constant__ CUtensorMap map_h0, const __grid_con
             }
         }
     } else {
-        // ------------------------------------------------------------------ epilogue: thread = utterance (TMEM lane)
-        // EW warps per row tile: warp = (TMEM lane quarter, column group); a column group is UW = UT / (EW / 4) hidden units,
-        // worked through in chunks of CH units.  With ONE warp per scheduler the epilogue was a serial latency chain (TMEM read ->
-        // table lines -> ten MUFU-deep gate math -> stores: 3 500 cycles per 8 units, 14 300 per step at UT = 32); several
-        // warps per scheduler overlap those chains.
-        const int quarter = warp & 3;                           // TMEM lanes 32 quarter .. +31 (a warp may only touch its own quarter)
+        {
+        // ------------------------------------------------------------------ epilogue, fragment layout (tcgen05.ld 16x256b)
+        // With thread = utterance every global access of a warp touches 32 different rows = 32 L1 wavefronts per instruction, and
+        // the epilogue of the large-batch configurations is bound by exactly that.  The 16x256b shape hands the
+        // accumulator out like an mma C fragment instead: per 16 lanes x 8 columns, thread l holds (row l / 4, columns
+        // 2 (l % 4) + {0, 1}) and (row l / 4 + 8, same columns).  Four threads then share a row and its 32-byte sectors: a table
+        // read or an output store of a warp touches 8 rows instead of 32.  Per 8-unit group a thread owns 4 rows x 2 units.
+        const int quarter = warp & 3;
         const int e = warp - 2;
-        const int j = e / EW;                                   // row tile of this warp
-        const int ub = ((e % EW) >> 2) * UW;                    // first unit (within the CTA's UT) of this warp's column group
+        const int j = e / EW;
+        const int ub = ((e % EW) >> 2) * UW;
         const int mt = mt0 + j;
-        const int row = mt * TC_BM + quarter * 32 + lane;
-        const bool valid = row < p.B;
+        const int cp = lane & 3, r8 = lane >> 2;
         const bool tile_live = mt * TC_BM < p.B;
-        const uint32_t tb = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + j * N;
-        const int64_t* irow = p.idx + static_cast<int64_t>(valid ? row : 0) * Tp;
-        float c[UW], hout[UW];
+        int rowk[4];
+        bool validk[4];
 #pragma unroll
-        for (int k = 0; k < UW; ++k) c[k] = 0.f;
+        for (int k = 0; k < 4; ++k) {
+            rowk[k] = mt * TC_BM + quarter * 32 + 8 * k + r8;       // k = 2 * (half of the quarter) + (upper 8 rows of the half)
+            validk[k] = rowk[k] < p.B;
+            if (!validk[k]) rowk[k] = 0;
+        }
+        const uint32_t tb = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + j * N;
+        float c[UW / 8][4][2];
+#pragma unroll
+        for (int q = 0; q < UW / 8; ++q)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) c[q][k][0] = c[q][k][1] = 0.f;
         uint32_t tphase = 0;
         bool ok = true;
-        int code = valid ? lp_clamp_code(__ldg(irow)) : 0;
-        // table values of the first chunk of step 0 (every later chunk is prefetched one chunk / one step ahead)
-        float4 xq[4][CH / 4];
-        auto fetch = [&](int cd, int ug) {
-            // permuted table (lp_permute_table_kernel): the 4 gates x 8 units of an aligned 8-unit group are ONE 128-byte line
+        int code[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) code[k] = validk[k] ? lp_clamp_code(__ldg(p.idx + static_cast<int64_t>(rowk[k]) * Tp)) : 0;
+        // permuted table, fragment flavour: [code][unit / 8][gate / 2][unit pair][gate % 2][2] -- per instruction the four threads of a
+        // row read 64 contiguous bytes (two whole sectors) of the 8-unit group's 128-byte line
+        float4 xq[4][2];
+        auto fetch = [&](const int (&cd)[4], int ug) {
             const int u = u0 + ub + ug;
-            const float4* tr = reinterpret_cast<const float4*>(p.table + static_cast<int64_t>((p.dbg & 1) ? 0 : cd) * LP_G + (u >> 3) * 32 + (u & 7));
 #pragma unroll
-            for (int g = 0; g < 4; ++g)
-#pragma unroll
-                for (int q = 0; q < CH / 4; ++q) xq[g][q] = __ldg(tr + 2 * g + q);
+            for (int k = 0; k < 4; ++k) {
+                const float4* tr = reinterpret_cast<const float4*>(p.table + static_cast<int64_t>((p.dbg & 1) ? 0 : cd[k]) * LP_G + (u >> 3) * 32) + cp;
+                xq[k][0] = __ldg(tr);          // gates i, f of the thread's two units: the four threads of a row read 64 contiguous bytes
+                xq[k][1] = __ldg(tr + 4);      // gates g, o
+            }
         };
         fetch(code, 0);
         for (int t = 0; t < Tp && ok && tile_live; ++t) {
-            const int code_next = (valid && t + 1 < Tp) ? lp_clamp_code(__ldg(irow + t + 1)) : 0;
+            int code_next[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                code_next[k] = (validk[k] && t + 1 < Tp) ? lp_clamp_code(__ldg(p.idx + static_cast<int64_t>(rowk[k]) * Tp + t + 1)) : 0;
             if (t > 0) {
                 ok = mbar_wait(&tfull_bar[j], tphase, p.err);
                 ok = __all_sync(0xffffffffu, ok);
@@ -246,89 +275,81 @@ lstm_persist_kernel(const __grid_constant__ CUtensorMap map_h0, const __grid_con
                 tc_fence_after();
                 if (warp == 2 && lane == 0) LP_STAMP(4);
             }
-            float* op = p.out + (static_cast<int64_t>(valid ? row : 0) * Tp + t) * LP_H + u0 + ub;
-            __nv_bfloat16* pr = p.planes[t & 1] + static_cast<int64_t>(valid ? row : 0) * 2 * LP_H + u0 + ub;
+            float2 hout[NT == 1 ? UW / 8 : 1][4];
 #pragma unroll
-            for (int ug = 0; ug < UW; ug += CH) {
-                uint32_t v[4][CH];
+            for (int q = 0; q < UW / 8; ++q) {
+                const int ug = 8 * q;
+                uint32_t v[2][4][4];                                    // [half][gate][row r8: cols 2cp, 2cp+1 | row r8 + 8: same]
                 if (t > 0) {
 #pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        if constexpr (CH == 8) tc_ld8(tb + g * UT + ub + ug, v[g]); else tc_ld4(tb + g * UT + ub + ug, v[g]);
-                    }
+                    for (int hf = 0; hf < 2; ++hf)
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) tc_ld_16x256b(tb + (static_cast<uint32_t>(16 * hf) << 16) + g * UT + ub + ug, v[hf][g]);
                     tc_wait_ld();
                 } else {
 #pragma unroll
-                    for (int g = 0; g < 4; ++g)
+                    for (int hf = 0; hf < 2; ++hf)
 #pragma unroll
-                        for (int k = 0; k < CH; ++k) v[g][k] = 0u;
+                        for (int g = 0; g < 4; ++g)
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) v[hf][g][i] = 0u;
                 }
-                float x[4][CH];
+                float x[4][4][2];                                       // [row k][gate][unit]
 #pragma unroll
-                for (int g = 0; g < 4; ++g)
-#pragma unroll
-                    for (int q = 0; q < CH / 4; ++q) {
-                        x[g][4 * q + 0] = xq[g][q].x; x[g][4 * q + 1] = xq[g][q].y; x[g][4 * q + 2] = xq[g][q].z; x[g][4 * q + 3] = xq[g][q].w;
-                    }
-                // prefetch the next chunk (of this step, or chunk 0 of the next step) while this one is computed
-                if (ug + CH < UW) fetch(code, ug + CH);
+                for (int k = 0; k < 4; ++k) {
+                    x[k][0][0] = xq[k][0].x; x[k][0][1] = xq[k][0].y; x[k][1][0] = xq[k][0].z; x[k][1][1] = xq[k][0].w;
+                    x[k][2][0] = xq[k][1].x; x[k][2][1] = xq[k][1].y; x[k][3][0] = xq[k][1].z; x[k][3][1] = xq[k][1].w;
+                }
+                if (q + 1 < UW / 8) fetch(code, ug + 8);
                 else if (t + 1 < Tp) fetch(code_next, 0);
-                float h[CH];
 #pragma unroll
-                for (int k = 0; k < CH; ++k) {
-                    // same expression order as lstm_gate_kernel: table + gates, then the cell
-                    const float gi = x[0][k] + __uint_as_float(v[0][k]), gf = x[1][k] + __uint_as_float(v[1][k]);
-                    const float gg = x[2][k] + __uint_as_float(v[2][k]), go = x[3][k] + __uint_as_float(v[3][k]);
-                    if (p.dbg & 4) { c[ug + k] = 0.5f * c[ug + k] + gf * gi + gg; h[k] = go * 0.001f + c[ug + k] * 0.001f; continue; }
-                    c[ug + k] = sigmoid_fast(gf) * c[ug + k] + sigmoid_fast(gi) * tanh_fast(gg);
-                    h[k] = sigmoid_fast(go) * tanh_fast(c[ug + k]);
-                }
+                for (int k = 0; k < 4; ++k) {
+                    float h2[2];
 #pragma unroll
-                for (int k = 0; k < CH; ++k) hout[ug + k] = h[k];
-                if (valid) {
-                    if (t + 1 < Tp && !(p.dbg & 16)) {
-                        // hi / lo planes of the chunk: one 16-byte (8 units) or 8-byte (4 units) store each; same rounding as tc_split_store4
-                        uint32_t ph[CH / 2], pl[CH / 2];
-#pragma unroll
-                        for (int k = 0; k < CH / 2; ++k) {
-                            const __nv_bfloat16 a = __float2bfloat16_rn(h[2 * k]), b = __float2bfloat16_rn(h[2 * k + 1]);
-                            const __nv_bfloat162 hh = __halves2bfloat162(a, b);
-                            const __nv_bfloat162 ll = __halves2bfloat162(__float2bfloat16_rn(h[2 * k] - __bfloat162float(a)),
-                                                                         __float2bfloat16_rn(h[2 * k + 1] - __bfloat162float(b)));
-                            ph[k] = *reinterpret_cast<const uint32_t*>(&hh);
-                            pl[k] = *reinterpret_cast<const uint32_t*>(&ll);
-                        }
-                        if constexpr (CH == 8) {
-                            *reinterpret_cast<uint4*>(pr + ug) = make_uint4(ph[0], ph[1], ph[CH / 2 - 2], ph[CH / 2 - 1]);
-                            *reinterpret_cast<uint4*>(pr + LP_H + ug) = make_uint4(pl[0], pl[1], pl[CH / 2 - 2], pl[CH / 2 - 1]);
-                        } else {
-                            *reinterpret_cast<uint2*>(pr + ug) = make_uint2(ph[0], ph[1]);
-                            *reinterpret_cast<uint2*>(pr + LP_H + ug) = make_uint2(pl[0], pl[1]);
-                        }
+                    for (int i = 0; i < 2; ++i) {
+                        const int hf = k >> 1, vi = 2 * (k & 1) + i;
+                        const float gi = x[k][0][i] + __uint_as_float(v[hf][0][vi]), gf = x[k][1][i] + __uint_as_float(v[hf][1][vi]);
+                        const float gg = x[k][2][i] + __uint_as_float(v[hf][2][vi]), go = x[k][3][i] + __uint_as_float(v[hf][3][vi]);
+                        float& cc = c[q][k][i];
+                        if (p.dbg & 4) { cc = 0.5f * cc + gf * gi + gg; h2[i] = go * 0.001f + cc * 0.001f; continue; }
+                        h2[i] = lp_cell(gi, gf, gg, go, cc);
+                    }
+                    if constexpr (NT == 1) hout[q][k] = make_float2(h2[0], h2[1]);
+                    else if (validk[k] && !(p.dbg & 2))      // two tiles per CTA: registers are short, the output goes out at once
+                        *reinterpret_cast<float2*>(p.out + (static_cast<int64_t>(rowk[k]) * Tp + t) * LP_H + u0 + ub + ug + 2 * cp) = make_float2(h2[0], h2[1]);
+                    if (validk[k] && t + 1 < Tp && !(p.dbg & 16)) {
+                        __nv_bfloat16* pr = p.planes[t & 1] + static_cast<int64_t>(rowk[k]) * 2 * LP_H + u0 + ub + ug + 2 * cp;
+                        const __nv_bfloat16 a = __float2bfloat16_rn(h2[0]), b = __float2bfloat16_rn(h2[1]);
+                        *reinterpret_cast<__nv_bfloat162*>(pr) = __halves2bfloat162(a, b);
+                        *reinterpret_cast<__nv_bfloat162*>(pr + LP_H) = __halves2bfloat162(__float2bfloat16_rn(h2[0] - __bfloat162float(a)),
+                                                                                          __float2bfloat16_rn(h2[1] - __bfloat162float(b)));
                     }
                 }
             }
-            code = code_next;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) code[k] = code_next[k];
             if (t + 1 < Tp) {
-                // this warp's h_t is written: publish and hand the accumulator back.  The lanes' stores are ordered before lane
-                // 0's gpu-scope release by the warp barrier (the pattern of a grid barrier: block barrier, then ONE thread fences);
-                // a fence in every lane (VQCPC_LP_DEBUG & 64) cost ~1 000 cycles more per step
                 if (warp == 2 && lane == 0) LP_STAMP(5);
                 tc_fence_before();
                 if (p.dbg & 64) __threadfence();
                 __syncwarp();
                 if (lane == 0) {
                     mbar_arrive(&tempty_bar[j]);
-                    red_release_add_u32(p.counters + mt, 1u);              // EW arrivals per CTA and step
+                    red_release_add_u32(p.counters + mt, 1u);
                 }
                 if (warp == 2 && lane == 0) LP_STAMP(6);
             }
-            // the fp32 output sequence is nobody's input: stored AFTER the release, so that the release waits only for the planes
-            if (valid && !(p.dbg & 2)) {
+            // (one tile per CTA) the fp32 output sequence is nobody's input: stored AFTER the release, which then waits for the planes only
+            if (NT == 1 && !(p.dbg & 2)) {
 #pragma unroll
-                for (int q = 0; q < UW / 4; ++q)
-                    *reinterpret_cast<float4*>(op + 4 * q) = make_float4(hout[4 * q], hout[4 * q + 1], hout[4 * q + 2], hout[4 * q + 3]);
+                for (int k = 0; k < 4; ++k) {
+                    if (!validk[k]) continue;
+                    float* op = p.out + (static_cast<int64_t>(rowk[k]) * Tp + t) * LP_H + u0 + ub + 2 * cp;
+#pragma unroll
+                    for (int q = 0; q < UW / 8; ++q) *reinterpret_cast<float2*>(op + 8 * q) = hout[q][k];
+                }
             }
+        }
         }
     }
     tc_fence_before();
@@ -340,13 +361,15 @@ lstm_persist_kernel(const __grid_constant__ CUtensorMap map_h0, const __grid_con
     }
 }
 
-// table[code][gate * 256 + unit]  ->  perm[code][unit / 8][gate][unit % 8]: what a thread of the epilogue needs for one
-// 8-unit chunk (4 gates x 8 units) is one aligned 128-byte line instead of four 32-byte pieces 1 KB apart
+// table[code][gate * 256 + unit]  ->  perm[code][unit / 8][gate / 2][unit pair][gate % 2][unit % 2]: the 4 gates x 8 units of an
+// aligned 8-unit group are ONE 128-byte line (instead of four 32-byte pieces 1 KB apart), ordered so that the four threads that
+// share a row in the fragment-layout epilogue read 64 contiguous bytes per instruction
 __global__ void lp_permute_table_kernel(const float* __restrict__ table, float* __restrict__ perm, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int code = i / LP_G, r = i % LP_G, g = r / LP_H, u = r % LP_H;
-    perm[static_cast<int64_t>(code) * LP_G + (u >> 3) * 32 + g * 8 + (u & 7)] = table[i];
+    const int o = (g >> 1) * 16 + ((u & 7) >> 1) * 4 + (g & 1) * 2 + (u & 1);
+    perm[static_cast<int64_t>(code) * LP_G + (u >> 3) * 32 + o] = table[i];
 }
 
 // ------------------------------------------------------------------------------------------------ host
@@ -437,14 +460,14 @@ int lstm_persist(const float* table_in, const int64_t* idx, const void* whh_plan
         static const int lp_dbg = [] { const char* e = getenv("VQCPC_LP_DEBUG"); return e ? atoi(e) : 0; }();
         int rc = VQCPC_ERR_ARG;
         bool done = false;
-        // epilogue warps per row tile: eight (two per scheduler) with one row tile per CTA, four with two (the two tiles' epilogues
-        // already overlap).  Measured on random codes, us/step at 512 / 1024 / 2048 / 4096 utterances: four warps 6.25 / 8.27 / 12.9 /
-        // 16.6, eight 6.11 / 7.32 / 11.0 / 17.5, sixteen - / 7.91 / 11.4 / -.  VQCPC_LP_EW=1 forces four everywhere (A/B).
+        // epilogue warps per row tile: eight (two column groups, two warps per scheduler) with one row tile of 16 or 32 units per
+        // CTA, four otherwise (8 units are one column group; with two tiles per CTA the tiles' epilogues already overlap).
+        // VQCPC_LP_EW=1 forces four everywhere (A/B).
         static const int lp_ew = [] { const char* e = getenv("VQCPC_LP_EW"); return (e && e[0] == '1') ? 1 : 2; }();
         auto try_cfg = [&](auto utc, auto ntc, auto csc, auto ewc) {
             constexpr int UT_ = decltype(utc)::value, NT_ = decltype(ntc)::value, CS_ = decltype(csc)::value, EW_ = decltype(ewc)::value;
             if (done || (CS_ > 1) != (lp_cs > 1)) return;
-            if (EW_ != ((NT_ == 2 || lp_ew == 1) ? 4 : 8)) return;
+            if (EW_ != ((NT_ == 2 || lp_ew == 1 || UT_ == 8) ? 4 : 8)) return;
             const int n_ns = LP_H / UT_;
             const int ctas = ((n_mt + NT_ - 1) / NT_) * n_ns;
             if (ctas > lp_capacity<UT_, NT_, CS_, EW_>()) return;
@@ -466,8 +489,9 @@ int lstm_persist(const float* table_in, const int64_t* idx, const void* whh_plan
         using E4 = std::integral_constant<int, 4>; using E8 = std::integral_constant<int, 8>;
         auto try_ut = [&](auto utc, auto ntc, auto csc) {
             constexpr int NT_ = decltype(ntc)::value;
+            constexpr int UT_ = decltype(utc)::value;
             try_cfg(utc, ntc, csc, E4{});
-            if constexpr (NT_ == 1) try_cfg(utc, ntc, csc, E8{});
+            if constexpr (NT_ == 1 && UT_ > 8) try_cfg(utc, ntc, csc, E8{});
         };
         try_ut(U8{}, I1{}, I4{});  try_ut(U16{}, I1{}, I4{}); try_ut(U32{}, I1{}, I4{}); try_ut(U32{}, I2{}, I4{});
         try_ut(U8{}, I1{}, I1{});  try_ut(U16{}, I1{}, I1{}); try_ut(U32{}, I1{}, I1{}); try_ut(U32{}, I2{}, I1{});
