@@ -246,9 +246,13 @@ lstm_persist_kernel(const __grid_constant__ CUtensorMap map_h0, const __grid_con
             for (int k = 0; k < 4; ++k) c[q][k][0] = c[q][k][1] = 0.f;
         uint32_t tphase = 0;
         bool ok = true;
-        int code[4];
+        // code indices are read TWO steps ahead: the table address of step t + 1 (prefetched during step t) must not wait for them
+        int code[4], code_next[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) code[k] = validk[k] ? lp_clamp_code(__ldg(p.idx + static_cast<int64_t>(rowk[k]) * Tp)) : 0;
+        for (int k = 0; k < 4; ++k) {
+            code[k] = validk[k] ? lp_clamp_code(__ldg(p.idx + static_cast<int64_t>(rowk[k]) * Tp)) : 0;
+            code_next[k] = (validk[k] && 1 < Tp) ? lp_clamp_code(__ldg(p.idx + static_cast<int64_t>(rowk[k]) * Tp + 1)) : 0;
+        }
         // permuted table, fragment flavour: [code][unit / 8][gate / 2][unit pair][gate % 2][2] -- per instruction the four threads of a
         // row read 64 contiguous bytes (two whole sectors) of the 8-unit group's 128-byte line
         float4 xq[4][2];
@@ -263,10 +267,10 @@ lstm_persist_kernel(const __grid_constant__ CUtensorMap map_h0, const __grid_con
         };
         fetch(code, 0);
         for (int t = 0; t < Tp && ok && tile_live; ++t) {
-            int code_next[4];
+            int code_nn[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-                code_next[k] = (validk[k] && t + 1 < Tp) ? lp_clamp_code(__ldg(p.idx + static_cast<int64_t>(rowk[k]) * Tp + t + 1)) : 0;
+                code_nn[k] = (validk[k] && t + 2 < Tp) ? lp_clamp_code(__ldg(p.idx + static_cast<int64_t>(rowk[k]) * Tp + t + 2)) : 0;
             if (t > 0) {
                 ok = mbar_wait(&tfull_bar[j], tphase, p.err);
                 ok = __all_sync(0xffffffffu, ok);
@@ -327,7 +331,7 @@ lstm_persist_kernel(const __grid_constant__ CUtensorMap map_h0, const __grid_con
                 }
             }
 #pragma unroll
-            for (int k = 0; k < 4; ++k) code[k] = code_next[k];
+            for (int k = 0; k < 4; ++k) { code[k] = code_next[k]; code_next[k] = code_nn[k]; }
             if (t + 1 < Tp) {
                 if (warp == 2 && lane == 0) LP_STAMP(5);
                 tc_fence_before();
