@@ -9,9 +9,9 @@
 //     (cooperative launch); CTA (mt, ns) keeps the 4 UT gate rows of its units resident in shared memory for the whole
 //     sequence as bf16 hi/lo planes in UMMA K-major SWIZZLE_128B layout (loaded once by TMA: UT = 8 / 16 / 32 -> 32 / 64 / 128 KB);
 //   * per step: TMA streams the row tile's h_{t-1} planes (128 x 256 hi + lo = 128 KB) through a ring of 32 KB stages, one
-//     thread issues tcgen05.mma (M = 128, N = 4 UT, K = 16; the three hi/lo products per k-block from one stage), the four
-//     epilogue warps (thread = utterance) read the accumulator from TMEM, add the gathered table row (prefetched during the
-//     wait), apply the cell with the cell state in REGISTERS for the whole sequence, and write h_t as fp32 into the output
+//     thread issues tcgen05.mma (M = 128, N = 4 UT, K = 16; the three hi/lo products per k-block from one stage), four or
+//     eight epilogue warps read the accumulator from TMEM in mma-fragment layout (16x256b: four threads per utterance row), add
+//     the gathered row of the input-projection table (prefetched a chunk / a step ahead), apply the cell with the cell state in REGISTERS for the whole sequence, and write h_t as fp32 into the output
 //     sequence and as bf16 hi/lo planes into the other plane buffer;
 //   * the CTAs of a row tile (and only those: utterances are independent) meet at a release/acquire counter before the next
 //     step's TMA loads -- no grid-wide barrier, no host involvement;
@@ -29,7 +29,7 @@
 
 namespace vqcpc {
 
-// threads: warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 epilogue of row tile 0 (6-9: row tile 1)
+// threads: warp 0 TMA producer, warp 1 MMA issuer, warps 2 .. 2 + EW - 1 epilogue of row tile 0 (then EW more for row tile 1)
 constexpr int LP_H = 256, LP_G = 4 * LP_H;
 constexpr int LP_KB = LP_H / TC_BK;   // 4 k-blocks of 64
 
