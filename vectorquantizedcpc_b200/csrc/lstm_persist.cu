@@ -90,7 +90,10 @@ __global__ void __launch_bounds__(64 + 32 * EW * NT, 1)
 lstm_persist_kernel(const __grid_constant__ CUtensorMap map_h0, const __grid_constant__ CUtensorMap map_h1,
                     const __grid_constant__ CUtensorMap map_w, LpParams p) {
     constexpr int N = 4 * UT;                                   // gate columns of this CTA: [i | f | g | o] x UT units
-    constexpr int UW = UT / (EW / 4);                           // hidden units per epilogue warp
+    constexpr int HSPLIT = (UT / (EW / 4) < 8) ? 2 : 1;         // 2: the warps of a lane quarter split its two 16-lane halves, not the columns
+    constexpr int CGN = EW / 4 / HSPLIT;                        // column groups
+    constexpr int UW = UT / CGN;                                // hidden units per epilogue warp
+    constexpr int NK = 4 / HSPLIT;                              // utterance rows per thread (each with 2 units per 8-unit group)
     static_assert(EW % 4 == 0 && UW % 8 == 0, "epilogue split: whole 8-unit groups per warp");
     constexpr uint32_t A_TILE = TC_BM * TC_BK * 2;              // 16 KB
     constexpr uint32_t STAGE_BYTES = 2 * A_TILE;                // hi + lo tile of one k-block
@@ -226,40 +229,42 @@ lstm_persist_kernel(const __grid_constant__ CUtensorMap map_h0, const __grid_con
         const int quarter = warp & 3;
         const int e = warp - 2;
         const int j = e / EW;
-        const int ub = ((e % EW) >> 2) * UW;
+        const int wq = (e % EW) >> 2;                           // which of the EW / 4 warps of this TMEM lane quarter
+        const int ub = (wq % CGN) * UW;                         // column group: units ub .. ub + UW - 1 of the CTA's UT
+        const int hsel = wq / CGN;                              // HSPLIT == 2: this warp owns one 16-lane half of the quarter
         const int mt = mt0 + j;
         const int cp = lane & 3, r8 = lane >> 2;
         const bool tile_live = mt * TC_BM < p.B;
-        int rowk[4];
-        bool validk[4];
+        int rowk[NK];
+        bool validk[NK];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            rowk[k] = mt * TC_BM + quarter * 32 + 8 * k + r8;       // k = 2 * (half of the quarter) + (upper 8 rows of the half)
+        for (int k = 0; k < NK; ++k) {
+            rowk[k] = mt * TC_BM + quarter * 32 + 8 * (k + 2 * hsel) + r8;      // k = 2 * (half of the quarter) + (upper 8 rows of the half)
             validk[k] = rowk[k] < p.B;
             if (!validk[k]) rowk[k] = 0;
         }
         const uint32_t tb = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + j * N;
-        float c[UW / 8][4][2];
+        float c[UW / 8][NK][2];
 #pragma unroll
         for (int q = 0; q < UW / 8; ++q)
 #pragma unroll
-            for (int k = 0; k < 4; ++k) c[q][k][0] = c[q][k][1] = 0.f;
+            for (int k = 0; k < NK; ++k) c[q][k][0] = c[q][k][1] = 0.f;
         uint32_t tphase = 0;
         bool ok = true;
         // code indices are read TWO steps ahead: the table address of step t + 1 (prefetched during step t) must not wait for them
-        int code[4], code_next[4];
+        int code[NK], code_next[NK];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < NK; ++k) {
             code[k] = validk[k] ? lp_clamp_code(__ldg(p.idx + static_cast<int64_t>(rowk[k]) * Tp)) : 0;
             code_next[k] = (validk[k] && 1 < Tp) ? lp_clamp_code(__ldg(p.idx + static_cast<int64_t>(rowk[k]) * Tp + 1)) : 0;
         }
         // permuted table, fragment flavour: [code][unit / 8][gate / 2][unit pair][gate % 2][2] -- per instruction the four threads of a
         // row read 64 contiguous bytes (two whole sectors) of the 8-unit group's 128-byte line
-        float4 xq[4][2];
-        auto fetch = [&](const int (&cd)[4], int ug) {
+        float4 xq[NK][2];
+        auto fetch = [&](const int (&cd)[NK], int ug) {
             const int u = u0 + ub + ug;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
+            for (int k = 0; k < NK; ++k) {
                 const float4* tr = reinterpret_cast<const float4*>(p.table + static_cast<int64_t>((p.dbg & 1) ? 0 : cd[k]) * LP_G + (u >> 3) * 32) + cp;
                 xq[k][0] = __ldg(tr);          // gates i, f of the thread's two units: the four threads of a row read 64 contiguous bytes
                 xq[k][1] = __ldg(tr + 4);      // gates g, o
@@ -267,9 +272,9 @@ lstm_persist_kernel(const __grid_constant__ CUtensorMap map_h0, const __grid_con
         };
         fetch(code, 0);
         for (int t = 0; t < Tp && ok && tile_live; ++t) {
-            int code_nn[4];
+            int code_nn[NK];
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
+            for (int k = 0; k < NK; ++k)
                 code_nn[k] = (validk[k] && t + 2 < Tp) ? lp_clamp_code(__ldg(p.idx + static_cast<int64_t>(rowk[k]) * Tp + t + 2)) : 0;
             if (t > 0) {
                 ok = mbar_wait(&tfull_bar[j], tphase, p.err);
@@ -279,35 +284,35 @@ lstm_persist_kernel(const __grid_constant__ CUtensorMap map_h0, const __grid_con
                 tc_fence_after();
                 if (warp == 2 && lane == 0) LP_STAMP(4);
             }
-            float2 hout[NT == 1 ? UW / 8 : 1][4];
+            float2 hout[NT == 1 ? UW / 8 : 1][NK];
 #pragma unroll
             for (int q = 0; q < UW / 8; ++q) {
                 const int ug = 8 * q;
-                uint32_t v[2][4][4];                                    // [half][gate][row r8: cols 2cp, 2cp+1 | row r8 + 8: same]
+                uint32_t v[NK / 2][4][4];                                    // [half][gate][row r8: cols 2cp, 2cp+1 | row r8 + 8: same]
                 if (t > 0) {
 #pragma unroll
-                    for (int hf = 0; hf < 2; ++hf)
+                    for (int hf = 0; hf < NK / 2; ++hf)
 #pragma unroll
-                        for (int g = 0; g < 4; ++g) tc_ld_16x256b(tb + (static_cast<uint32_t>(16 * hf) << 16) + g * UT + ub + ug, v[hf][g]);
+                        for (int g = 0; g < 4; ++g) tc_ld_16x256b(tb + (static_cast<uint32_t>(16 * (hf + hsel)) << 16) + g * UT + ub + ug, v[hf][g]);
                     tc_wait_ld();
                 } else {
 #pragma unroll
-                    for (int hf = 0; hf < 2; ++hf)
+                    for (int hf = 0; hf < NK / 2; ++hf)
 #pragma unroll
                         for (int g = 0; g < 4; ++g)
 #pragma unroll
                             for (int i = 0; i < 4; ++i) v[hf][g][i] = 0u;
                 }
-                float x[4][4][2];                                       // [row k][gate][unit]
+                float x[NK][4][2];                                       // [row k][gate][unit]
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
+                for (int k = 0; k < NK; ++k) {
                     x[k][0][0] = xq[k][0].x; x[k][0][1] = xq[k][0].y; x[k][1][0] = xq[k][0].z; x[k][1][1] = xq[k][0].w;
                     x[k][2][0] = xq[k][1].x; x[k][2][1] = xq[k][1].y; x[k][3][0] = xq[k][1].z; x[k][3][1] = xq[k][1].w;
                 }
                 if (q + 1 < UW / 8) fetch(code, ug + 8);
                 else if (t + 1 < Tp) fetch(code_next, 0);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
+                for (int k = 0; k < NK; ++k) {
                     float h2[2];
 #pragma unroll
                     for (int i = 0; i < 2; ++i) {
@@ -331,7 +336,7 @@ lstm_persist_kernel(const __grid_constant__ CUtensorMap map_h0, const __grid_con
                 }
             }
 #pragma unroll
-            for (int k = 0; k < 4; ++k) { code[k] = code_next[k]; code_next[k] = code_nn[k]; }
+            for (int k = 0; k < NK; ++k) { code[k] = code_next[k]; code_next[k] = code_nn[k]; }
             if (t + 1 < Tp) {
                 if (warp == 2 && lane == 0) LP_STAMP(5);
                 tc_fence_before();
@@ -346,7 +351,7 @@ lstm_persist_kernel(const __grid_constant__ CUtensorMap map_h0, const __grid_con
             // (one tile per CTA) the fp32 output sequence is nobody's input: stored AFTER the release, which then waits for the planes only
             if (NT == 1 && !(p.dbg & 2)) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
+                for (int k = 0; k < NK; ++k) {
                     if (!validk[k]) continue;
                     float* op = p.out + (static_cast<int64_t>(rowk[k]) * Tp + t) * LP_H + u0 + ub + 2 * cp;
 #pragma unroll
@@ -471,7 +476,7 @@ int lstm_persist(const float* table_in, const int64_t* idx, const void* whh_plan
         auto try_cfg = [&](auto utc, auto ntc, auto csc, auto ewc) {
             constexpr int UT_ = decltype(utc)::value, NT_ = decltype(ntc)::value, CS_ = decltype(csc)::value, EW_ = decltype(ewc)::value;
             if (done || (CS_ > 1) != (lp_cs > 1)) return;
-            if (EW_ != ((NT_ == 2 || lp_ew == 1 || UT_ == 8) ? 4 : 8)) return;
+            if (EW_ != ((NT_ == 2 || lp_ew == 1) ? 4 : 8)) return;
             const int n_ns = LP_H / UT_;
             const int ctas = ((n_mt + NT_ - 1) / NT_) * n_ns;
             if (ctas > lp_capacity<UT_, NT_, CS_, EW_>()) return;
@@ -493,9 +498,8 @@ int lstm_persist(const float* table_in, const int64_t* idx, const void* whh_plan
         using E4 = std::integral_constant<int, 4>; using E8 = std::integral_constant<int, 8>;
         auto try_ut = [&](auto utc, auto ntc, auto csc) {
             constexpr int NT_ = decltype(ntc)::value;
-            constexpr int UT_ = decltype(utc)::value;
             try_cfg(utc, ntc, csc, E4{});
-            if constexpr (NT_ == 1 && UT_ > 8) try_cfg(utc, ntc, csc, E8{});
+            if constexpr (NT_ == 1) try_cfg(utc, ntc, csc, E8{});
         };
         try_ut(U8{}, I1{}, I4{});  try_ut(U16{}, I1{}, I4{}); try_ut(U32{}, I1{}, I4{}); try_ut(U32{}, I2{}, I4{});
         try_ut(U8{}, I1{}, I1{});  try_ut(U16{}, I1{}, I1{}); try_ut(U32{}, I1{}, I1{}); try_ut(U32{}, I2{}, I1{});
