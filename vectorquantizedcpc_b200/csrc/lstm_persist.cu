@@ -327,11 +327,13 @@ lstm_persist_kernel(const __grid_constant__ CUtensorMap map_h0, const __grid_con
                     else if (validk[k] && !(p.dbg & 2))      // two tiles per CTA: registers are short, the output goes out at once
                         *reinterpret_cast<float2*>(p.out + (static_cast<int64_t>(rowk[k]) * Tp + t) * LP_H + u0 + ub + ug + 2 * cp) = make_float2(h2[0], h2[1]);
                     if (validk[k] && t + 1 < Tp && !(p.dbg & 16)) {
-                        __nv_bfloat16* pr = p.planes[t & 1] + static_cast<int64_t>(rowk[k]) * 2 * LP_H + u0 + ub + ug + 2 * cp;
+                        __nv_bfloat16* pr = ((t & 1) ? p.planes[1] : p.planes[0]) + static_cast<int64_t>(rowk[k]) * 2 * LP_H + u0 + ub + ug + 2 * cp;
                         const __nv_bfloat16 a = __float2bfloat16_rn(h2[0]), b = __float2bfloat16_rn(h2[1]);
-                        *reinterpret_cast<__nv_bfloat162*>(pr) = __halves2bfloat162(a, b);
-                        *reinterpret_cast<__nv_bfloat162*>(pr + LP_H) = __halves2bfloat162(__float2bfloat16_rn(h2[0] - __bfloat162float(a)),
-                                                                                          __float2bfloat16_rn(h2[1] - __bfloat162float(b)));
+                        const __nv_bfloat162 hh = __halves2bfloat162(a, b);
+                        const __nv_bfloat162 ll = __halves2bfloat162(__float2bfloat16_rn(h2[0] - __bfloat162float(a)),
+                                                                     __float2bfloat16_rn(h2[1] - __bfloat162float(b)));
+                        asm volatile("st.global.b32 [%0], %1;" ::"l"(pr), "r"(*reinterpret_cast<const uint32_t*>(&hh)) : "memory");
+                        asm volatile("st.global.b32 [%0], %1;" ::"l"(pr + LP_H), "r"(*reinterpret_cast<const uint32_t*>(&ll)) : "memory");
                     }
                 }
             }
