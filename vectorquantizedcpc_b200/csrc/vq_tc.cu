@@ -319,8 +319,12 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vq_tc_kernel(const __grid_const
                 ssq[j] = ss;
                 // SWIZZLE_128B: 16-byte chunk c of row r lives at chunk (c ^ (r & 7)) of that row's 128 bytes
                 const uint32_t off = r * 128 + ((c ^ (r & 7)) << 4);
-                *reinterpret_cast<uint4*>(hi + off) = *reinterpret_cast<const uint4*>(h2);
-                *reinterpret_cast<uint4*>(lo + off) = *reinterpret_cast<const uint4*>(l2);
+                // st.shared, not a generic store: x_s comes out of an integer alignment round trip, which hides its address space
+                {
+                    const uint4 hv = *reinterpret_cast<const uint4*>(h2), lv = *reinterpret_cast<const uint4*>(l2);
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(smem_u32(hi) + off), "r"(hv.x), "r"(hv.y), "r"(hv.z), "r"(hv.w) : "memory");
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(smem_u32(lo) + off), "r"(lv.x), "r"(lv.y), "r"(lv.z), "r"(lv.w) : "memory");
+                }
             }
             // row norms: the 8 lanes of a row reduce their partial sums (all rows' butterflies interleaved)
 #pragma unroll
