@@ -11,12 +11,13 @@
 //   * per step: TMA streams the row tile's h_{t-1} planes (128 x 256 hi + lo = 128 KB) through a ring of 32 KB stages, one
 //     thread issues tcgen05.mma (M = 128, N = 4 UT, K = 16; the three hi/lo products per k-block from one stage), four or
 //     eight epilogue warps read the accumulator from TMEM in mma-fragment layout (16x256b: four threads per utterance row), add
-//     the gathered row of the input-projection table (prefetched a chunk / a step ahead), apply the cell with the cell state in REGISTERS for the whole sequence, and write h_t as fp32 into the output
-//     sequence and as bf16 hi/lo planes into the other plane buffer;
+//     the gathered row of the input-projection table (prefetched a chunk / a step ahead), apply the cell with the cell state in
+//     REGISTERS for the whole sequence, and write h_t as fp32 into the output sequence and as bf16 hi/lo planes into the other
+//     plane buffer;
 //   * the CTAs of a row tile (and only those: utterances are independent) meet at a release/acquire counter before the next
 //     step's TMA loads -- no grid-wide barrier, no host involvement;
-//   * every CTA of a row tile needs the SAME 128 KB of h_{t-1}: clusters of 4 CTAs (neighbouring unit slices) load a quarter
-//     each and TMA-multicast it to all four (the L2 -> SM traffic, 16 MB per step at 512 utterances, was what bound the step).
+//   * every CTA of a row tile needs the SAME 128 KB of h_{t-1}: optionally (VQCPC_LSTM_CLUSTER=4, measured no faster) clusters of
+//     4 CTAs (neighbouring unit slices) load a quarter each and TMA-multicast it to all four.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <stdio.h>
