@@ -345,10 +345,11 @@ lstm_persist_kernel(const __grid_constant__ CUtensorMap map_h0, const __grid_con
                 tc_fence_before();
                 if (p.dbg & 64) __threadfence();
                 __syncwarp();
-                if (lane == 0) {
-                    mbar_arrive(&tempty_bar[j]);
-                    red_release_add_u32(p.counters + mt, 1u);
-                }
+                // ONE release per CTA and tile: the tile's epilogue warps meet at a named barrier, then a single thread fences and
+                // adds EW to the counter (eight MEMBAR.GPU per CTA and step cost 0.5 us per step: 512 utterances 5.50 -> 4.95 us)
+                if (lane == 0) mbar_arrive(&tempty_bar[j]);
+                bar_sync(1 + j, EW * 32);
+                if ((e % EW) == 0 && lane == 0) red_release_add_u32(p.counters + mt, static_cast<unsigned>(EW));
                 if (warp == 2 && lane == 0) LP_STAMP(6);
             }
             // (one tile per CTA) the fp32 output sequence is nobody's input: stored AFTER the release, which then waits for the planes only
