@@ -381,6 +381,37 @@ def test_persistent_batched_lstm_matches_oracle(B, T):
     assert torch.allclose(c[sel].cpu(), ref, rtol=RTOL, atol=ATOL_C), err
 
 
+@pytest.mark.parametrize("B,Tp", [(200, 80), (700, 50), (1500, 30), (4200, 12)])
+def test_persistent_lstm_every_utterance_against_oracle_and_run_to_run(B, Tp):
+    """The persistent LSTM's steps are chained through release / acquire counters and TMA reads of planes other CTAs wrote (one
+    release per CTA and tile after a named barrier, fragment-layout epilogue, code indices two steps ahead).  An ordering bug
+    there would show as garbage in SOME row tile, so EVERY utterance is compared with the oracle's LSTM -- uniformly random
+    codes through the C ABI, all four configurations (8 / 16 / 32-unit slices, two tiles per CTA, ragged last tile) -- and three
+    launches must agree bit for bit."""
+    import ctypes as C
+    enc, sd = make_encoder(512, True)
+    w, _keep = enc.pack_weights()
+    lib = _lib.lib()
+    g = torch.Generator().manual_seed(B)
+    idx = torch.randint(0, 512, (B, Tp), generator=g)
+    idx_d = idx.to(dev())
+    n = lib.vqcpc_lstm_workspace_bytes(B, Tp)
+    outs = []
+    for _ in range(3):
+        ws = torch.empty(n, dtype=torch.uint8, device=dev())
+        out = torch.empty(B, Tp, 256, device=dev())
+        _lib.check(lib.vqcpc_lstm_forward_ex(C.byref(w), _lib.ptr(idx_d), B, Tp, _lib.ptr(ws), n, _lib.ptr(out), 1,
+                                             _lib.current_stream_ptr()), "lstm")
+        _lib.check(lib.vqcpc_check_status(_lib.ptr(ws), _lib.current_stream_ptr()), "lstm status")
+        outs.append(out.cpu())
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    ref = oenc.lstm(sd["codebook.embedding"][idx], sd["rnn.weight_ih_l0"], sd["rnn.weight_hh_l0"], sd["rnn.bias_ih_l0"],
+                    sd["rnn.bias_hh_l0"])
+    err = float((outs[0] - ref).abs().max())
+    print(f"[persistent LSTM, all {B} utterances x {Tp} steps] max |c - oracle| = {err:.2e}")
+    assert torch.allclose(outs[0], ref, rtol=RTOL, atol=ATOL_C), err
+
+
 @pytest.mark.parametrize("mode", ["fp32", "bf16x3"])
 def test_encode_from_host_equals_encode(mode):
     """Encoder.encode_from_host streams a host-resident batch to the GPU in chunks (front part per chunk, overlapped with the
