@@ -85,13 +85,13 @@ __device__ __forceinline__ void tc_commit_mc(uint64_t* bar, uint16_t mask) {
 }
 
 // CS = cluster size (1: every CTA loads its own copy of h_{t-1}; 4: each loads a quarter and multicasts it)
-// EW = epilogue warps per row tile (4 or 8)
+// EW = epilogue warps per row tile (4, 8 or 16)
 template <int UT, int NT, int CS, int EW>
 __global__ void __launch_bounds__(64 + 32 * EW * NT, 1)
 lstm_persist_kernel(const __grid_constant__ CUtensorMap map_h0, const __grid_constant__ CUtensorMap map_h1,
                     const __grid_constant__ CUtensorMap map_w, LpParams p) {
     constexpr int N = 4 * UT;                                   // gate columns of this CTA: [i | f | g | o] x UT units
-    constexpr int HSPLIT = (UT / (EW / 4) < 8 || (NT == 2 && EW == 8)) ? 2 : 1;   // 2: the warps of a lane quarter split its two 16-lane halves, not the columns
+    constexpr int HSPLIT = (UT / (EW / 4) < 8 || (NT == 2 && EW == 8) || EW == 16) ? 2 : 1;   // 2: the warps of a lane quarter split its two 16-lane halves, not the columns
     constexpr int CGN = EW / 4 / HSPLIT;                        // column groups
     constexpr int UW = UT / CGN;                                // hidden units per epilogue warp
     constexpr int NK = 4 / HSPLIT;                              // utterance rows per thread (each with 2 units per 8-unit group)
@@ -473,14 +473,15 @@ int lstm_persist(const float* table_in, const int64_t* idx, const void* whh_plan
         static const int lp_dbg = [] { const char* e = getenv("VQCPC_LP_DEBUG"); return e ? atoi(e) : 0; }();
         int rc = VQCPC_ERR_ARG;
         bool done = false;
-        // epilogue warps per row tile: eight -- two column groups with one row tile of 16 or 32 units per CTA; the two 16-lane
-        // halves of each TMEM lane quarter with 8-unit slices and with two tiles per CTA (register budget of 576 threads).
-        // VQCPC_LP_EW=1: four (A/B; 4096 utterances 10.3 vs 9.3 us per step).
-        static const int lp_ew = [] { const char* e = getenv("VQCPC_LP_EW"); return (e && e[0] == '1') ? 1 : 2; }();
+        // epilogue warps per row tile: sixteen (two column groups x the two 16-lane halves of each TMEM lane quarter) with one row
+        // tile of 16 or 32 units per CTA, eight (the two halves) with 8-unit slices and with two tiles per CTA (576 threads either
+        // way).  VQCPC_LP_EW=1 / 2: four / eight everywhere (A/B; 2048 utterances 7.2 us per step with eight, 6.6 with sixteen;
+        // 4096 utterances 10.3 with four, 9.3 with eight).
+        static const int lp_ew = [] { const char* e = getenv("VQCPC_LP_EW"); return (e && e[0] == '1') ? 1 : (e && e[0] == '2') ? 2 : 3; }();
         auto try_cfg = [&](auto utc, auto ntc, auto csc, auto ewc) {
             constexpr int UT_ = decltype(utc)::value, NT_ = decltype(ntc)::value, CS_ = decltype(csc)::value, EW_ = decltype(ewc)::value;
             if (done || (CS_ > 1) != (lp_cs > 1)) return;
-            if (EW_ != (lp_ew == 1 ? 4 : 8)) return;
+            if (EW_ != (lp_ew == 1 ? 4 : (lp_ew == 3 && NT_ == 1 && UT_ >= 16) ? 16 : 8)) return;   // lp_ew: 1 four, 2 eight, 3 (default) as many as fit
             const int n_ns = LP_H / UT_;
             const int ctas = ((n_mt + NT_ - 1) / NT_) * n_ns;
             if (ctas > lp_capacity<UT_, NT_, CS_, EW_>()) return;
@@ -503,6 +504,7 @@ int lstm_persist(const float* table_in, const int64_t* idx, const void* whh_plan
         auto try_ut = [&](auto utc, auto ntc, auto csc) {
             try_cfg(utc, ntc, csc, E4{});
             try_cfg(utc, ntc, csc, E8{});
+            if constexpr (decltype(ntc)::value == 1 && decltype(utc)::value >= 16 && decltype(csc)::value == 1) try_cfg(utc, ntc, csc, std::integral_constant<int, 16>{});
         };
         try_ut(U8{}, I1{}, I4{});  try_ut(U16{}, I1{}, I4{}); try_ut(U32{}, I1{}, I4{}); try_ut(U32{}, I2{}, I4{});
         try_ut(U8{}, I1{}, I1{});  try_ut(U16{}, I1{}, I1{}); try_ut(U32{}, I1{}, I1{}); try_ut(U32{}, I2{}, I1{});
