@@ -579,6 +579,9 @@ static int lstm_launch(LstmParams prm, void* ll_mem, cudaStream_t stream) {
 // state, writes h_t into the output sequence and re-splits it into the planes the next step's GEMM reads.
 // ------------------------------------------------------------------------------------------------
 constexpr int LSTM_BATCHED_MIN_B = 64;
+// the persistent tcgen05 kernel (tensor-core modes) already pays from 17 utterances: 4.7 us per step at 17 .. 63 against 3.7 .. 8.2 for
+// the L2-exchange groups below (which stay the path of the fp32 mode and of 10 .. 16 utterances: 1.9 .. 4.1 us per step)
+constexpr int LSTM_PERSIST_MIN_B = 17;
 constexpr int LSTM_CLUSTER_MAX_B = 9;              // one wave of 16-CTA clusters on 148 SMs
 constexpr int LSTM_FUSED_MAX_B = 2048;            // below: fused tcgen05 step kernel; from here on: GEMM + coalesced gate kernel
 
@@ -626,7 +629,7 @@ static bool lstm_persist_enabled() {          // VQCPC_LSTM_PERSIST=0 selects th
 
 // workspace: [header][table 512x1024][ll][gates B x 1024][cstate B x 256][h planes B x 512 bf16] x 2
 static size_t lstm_batched_bytes(int B) {
-    if (B < LSTM_BATCHED_MIN_B) return 0;
+    if (B < LSTM_PERSIST_MIN_B) return 0;
     return align_up(sizeof(float) * B * LSTM_G, 256) + align_up(sizeof(float) * B * LSTM_H, 256) +
            2 * align_up(2 * static_cast<size_t>(B) * 2 * LSTM_H, 256) +      // two h-plane buffers (ping-pong across steps)
            align_up(lstm_persist_table_bytes(), 256);                         // permuted input-projection table of lstm_persist
@@ -654,14 +657,15 @@ int lstm_forward(const vqcpc_encoder_weights* w, const int64_t* idx, int B, int 
         rc = gemm_dense(w->codebook, VQ_D, w->lstm_w_ih, VQ_D, w->lstm_b, table_ws, LSTM_G, VQ_M, LSTM_G, VQ_D, stream);
     const float* table = w->lstm_table != nullptr ? w->lstm_table : table_ws;
     if (rc) return rc;
-    if (B >= LSTM_BATCHED_MIN_B) {
+    const bool tc_mode = (mode != VQCPC_GEMM_FP32) && (w->lstm_whh_p != nullptr);
+    if (B >= LSTM_BATCHED_MIN_B || (tc_mode && lstm_persist_enabled() && B >= LSTM_PERSIST_MIN_B)) {
         unsigned char* bb = static_cast<unsigned char*>(ll) + lstm_ll_bytes(LSTM_MAX_GROUPS, LSTM_MAX_NB);
         float* gates = reinterpret_cast<float*>(bb); bb += align_up(sizeof(float) * B * LSTM_G, 256);
         float* cstate = reinterpret_cast<float*>(bb); bb += align_up(sizeof(float) * B * LSTM_H, 256);
         __nv_bfloat16* hplanes = reinterpret_cast<__nv_bfloat16*>(bb); bb += align_up(2 * static_cast<size_t>(B) * 2 * LSTM_H, 256);
         __nv_bfloat16* hplanes2 = reinterpret_cast<__nv_bfloat16*>(bb); bb += align_up(2 * static_cast<size_t>(B) * 2 * LSTM_H, 256);
         float* table_perm = reinterpret_cast<float*>(bb);
-        const bool tc = (mode != VQCPC_GEMM_FP32) && (w->lstm_whh_p != nullptr);   // bf16 mode too: the recurrence stays bf16x3
+        const bool tc = tc_mode;                                                    // bf16 mode too: the recurrence stays bf16x3
         const int64_t total = static_cast<int64_t>(B) * (LSTM_H / 4);
         const unsigned grid = static_cast<unsigned>((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
         if (tc && lstm_persist_enabled()) {
