@@ -117,7 +117,8 @@ class Encoder(nn.Module):
         # its scale, >= 97 % index agreement on trained-like weights; VQ exact for that z, LSTM still bf16x3).
         self.gemm_mode = "auto"
 
-    AUTO_TC_ROWS = 4096
+    # measured on B200 (3 s utterances, ms per encode, fp32 / bf16x3): 8 utterances 0.77 / 0.70, 12: 1.05 / 0.66, 27: 1.52 / 1.10
+    AUTO_TC_ROWS = 1536
 
     def _resolve_mode(self, rows: int) -> int:
         mode = self.gemm_mode
