@@ -61,7 +61,7 @@ typedef struct {
     const void* conv_wp;      /* (C, 2*320) */
     const void* fc_wp[4];     /* (C, 2*C) */
     const void* proj_wp;      /* (64, 2*C) */
-    const void* lstm_whh_p;   /* (1024, 2*256): planes of rnn.weight_hh_l0 for the batched (B >= 17) LSTM */
+    const void* lstm_whh_p;   /* (1024, 2*256): planes of rnn.weight_hh_l0 for the batched (B >= 33) LSTM */
     /* optional, weight-only: the LSTM input projection of every CODE, table[m] = lstm_w_ih codebook[m] + lstm_b (512, 1024),
      * exactly vqcpc_linear_f32(codebook, lstm_w_ih, lstm_b).  NULL: recomputed inside every call (one 512 x 1024 x 64 GEMM). */
     const float* lstm_table;
@@ -152,7 +152,7 @@ int vqcpc_encoder_forward_ex(const vqcpc_encoder_weights* w, const float* mel, i
 size_t vqcpc_lstm_workspace_bytes(int32_t B, int32_t Tp);
 int vqcpc_lstm_forward(const vqcpc_encoder_weights* w, const int64_t* idx, int32_t B, int32_t Tp,
                        void* workspace, size_t workspace_bytes, float* out_c, void* stream);
-/* Same with an explicit arithmetic (VQCPC_GEMM_*): the tensor-core modes run batches of >= 17 utterances as one persistent
+/* Same with an explicit arithmetic (VQCPC_GEMM_*): the tensor-core modes run batches of >= 33 utterances as one persistent
  * tcgen05 launch (lstm_whh_p planes present), otherwise as the fp32 entry above.  Together with out_c == NULL in
  * vqcpc_encoder_forward_ex (front part only: conv .. VQ, no recurrence) this lets a caller encode a large batch in chunks
  * -- overlapping each chunk's host->device copy with the previous chunk's GEMMs -- and run the recurrence, whose latency chain

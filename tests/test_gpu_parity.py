@@ -381,7 +381,7 @@ def test_persistent_batched_lstm_matches_oracle(B, T):
     assert torch.allclose(c[sel].cpu(), ref, rtol=RTOL, atol=ATOL_C), err
 
 
-@pytest.mark.parametrize("B,Tp", [(17, 90), (45, 33), (200, 80), (700, 50), (1500, 30), (4200, 12)])
+@pytest.mark.parametrize("B,Tp", [(33, 90), (45, 33), (200, 80), (700, 50), (1500, 30), (4200, 12)])
 def test_persistent_lstm_every_utterance_against_oracle_and_run_to_run(B, Tp):
     """The persistent LSTM's steps are chained through release / acquire counters and TMA reads of planes other CTAs wrote (one
     release per CTA and tile after a named barrier, fragment-layout epilogue, code indices two steps ahead).  An ordering bug

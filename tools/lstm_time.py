@@ -17,7 +17,7 @@ for B in Bs:
     n = lib.vqcpc_lstm_workspace_bytes(B, Tp)
     ws = torch.empty(n, dtype=torch.uint8, device=dev)
     def run():
-        _lib.check(lib.vqcpc_lstm_forward_ex(C.byref(w), _lib.ptr(idx), B, Tp, _lib.ptr(ws), n, _lib.ptr(c), 1, _lib.current_stream_ptr()), "lstm")
+        _lib.check(lib.vqcpc_lstm_forward_ex(C.byref(w), _lib.ptr(idx), B, Tp, _lib.ptr(ws), n, _lib.ptr(c), int(os.environ.get("LP_MODE", "1")), _lib.current_stream_ptr()), "lstm")
     run(); torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()

@@ -579,9 +579,10 @@ static int lstm_launch(LstmParams prm, void* ll_mem, cudaStream_t stream) {
 // state, writes h_t into the output sequence and re-splits it into the planes the next step's GEMM reads.
 // ------------------------------------------------------------------------------------------------
 constexpr int LSTM_BATCHED_MIN_B = 64;
-// the persistent tcgen05 kernel (tensor-core modes) already pays from 17 utterances: 4.7 us per step at 17 .. 63 against 3.7 .. 8.2 for
-// the L2-exchange groups below (which stay the path of the fp32 mode and of 10 .. 16 utterances: 1.9 .. 4.1 us per step)
-constexpr int LSTM_PERSIST_MIN_B = 17;
+// the persistent tcgen05 kernel (tensor-core modes) already pays from 33 utterances: 0.70 ms per 150 steps at 17 .. 63 against
+// 0.74 .. 0.86 for the L2-exchange groups below at 33 .. 63 (which win below that: 0.47 .. 0.53 at 17 .. 32, 0.28 .. 0.31 at 10 .. 16,
+// and stay the path of the fp32 mode)
+constexpr int LSTM_PERSIST_MIN_B = 33;
 constexpr int LSTM_CLUSTER_MAX_B = 9;              // one wave of 16-CTA clusters on 148 SMs
 constexpr int LSTM_FUSED_MAX_B = 2048;            // below: fused tcgen05 step kernel; from here on: GEMM + coalesced gate kernel
 
@@ -738,8 +739,13 @@ int lstm_forward(const vqcpc_encoder_weights* w, const int64_t* idx, int B, int 
     prm.B = B;
     prm.Tp = Tp;
     // lockstep width: latency case keeps one utterance per group, large batches amortise the exchange
+    // lockstep width NB (utterances per 32-CTA group), measured on B200 (ms per 150 steps, tools/lstm_time.py with LP_MODE=0):
+    //   NB = 1: 10-12 utterances 0.28, 16: 0.63, 24: 1.18, 40: 1.81 (more groups than fit at once run in rounds)
+    //   NB = 4: 10-16: 0.31, 17-32: 0.52-0.68, 40: 0.74, 47: 0.81, 63: 0.86        NB = 8: 17-32: 0.47-0.53, 40: 0.81, 63: 0.88
     if (B >= 8 * 12) return lstm_launch<8>(prm, ll, stream);
-    if (B >= 4 * 12) return lstm_launch<4>(prm, ll, stream);
+    if (B >= 33) return lstm_launch<4>(prm, ll, stream);
+    if (B >= 17) return lstm_launch<8>(prm, ll, stream);
+    if (B >= 13) return lstm_launch<4>(prm, ll, stream);
     return lstm_launch<1>(prm, ll, stream);
 }
 
