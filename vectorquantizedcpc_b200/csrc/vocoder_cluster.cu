@@ -568,7 +568,9 @@ __global__ void __launch_bounds__(CL_THREADS, 1) exchange_floor_cluster_kernel(l
 int ar_cluster_exchange_floor(void* workspace, size_t workspace_bytes, int iters, double* mean_cycles, cudaStream_t s);
 
 // ------------------------------------------------------------------------------------------------ host
-static int g_cl_poll_delay = 300, g_cl_poll_mode = 0;
+// first probe of the grid hop this many cycles after the CTA's own publish (tools/gen_delay_sweep.py on three boards: 300 -> 1.874 /
+// 1.886 / 1.886 us per step, 350-360 -> 1.856 / 1.861 / 1.871, 450 -> - / 1.869 / 1.849; an earlier probe comes back empty and costs a round)
+static int g_cl_poll_delay = 360, g_cl_poll_mode = 0;
 int g_cl_enable = 1;
 
 // 1 = the device can hold the 7 x 16 cluster grid at one CTA per SM, 0 = it cannot (fall back to ar_kernel), cached per device
